@@ -1,0 +1,127 @@
+/*
+ * libmingb200 — C ABI of the B200-native (sm_100a) operators behind the Ming-UniVision continuous-visual-token
+ * hot path (MingTok encoder / semantic decoder / pixel decoder, Bailing-MoE AR step, rectified-flow head).
+ *
+ * The reference (inclusionAI/Ming-UniVision) is pure Python/PyTorch and has no FFI; the boundary it exposes is its
+ * Python class API.  Each entry point below therefore names the reference call site whose
+ * torch / flash-attn operator it replaces (paths relative to the reference repo).  The Python host modules in
+ * ming_univision_b200/ keep the reference's class names, method signatures and state_dict keys and call these
+ * functions through ctypes with raw device pointers.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All data pointers are DEVICE pointers (cudaMalloc'ed / torch CUDA
+ *     storage) unless a parameter is explicitly marked HOST.
+ *   - Matrices are row-major.  `ld*` arguments are row strides in ELEMENTS.  bf16 = __nv_bfloat16 (uint16 storage).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on that stream,
+ *     never allocate, never synchronise, and are CUDA-graph capturable.
+ *   - Return value: 0 (MB_OK) or a negative MB_ERR_* code; mb_last_error() returns a thread-local message.
+ *   - There is no CPU fallback: on a machine without an sm_100 device every compute entry point returns MB_ERR_ARCH.
+ */
+#ifndef MINGB200_H_
+#define MINGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK 0
+#define MB_ERR_SHAPE (-1) /* unsupported or inconsistent shape */
+#define MB_ERR_ALIGN (-2) /* pointer / stride alignment (TMA needs 16-byte aligned bases and row strides) */
+#define MB_ERR_ARCH (-3)  /* no sm_100 device */
+#define MB_ERR_CUDA (-4)  /* CUDA runtime / driver error, see mb_last_error() */
+#define MB_ERR_NCCL (-5)
+
+/* GEMM epilogues (mb_gemm_bf16 `epi`) */
+#define MB_EPI_BIAS 0     /* out = bf16(acc + bias)                                   nn.Linear */
+#define MB_EPI_GELU 1     /* out = bf16(gelu_erf(bf16(acc + bias)))                   nn.Linear -> nn.GELU() */
+#define MB_EPI_SWIGLU 2   /* packed w12: out = bf16(bf16(silu(x1)) * x2), N/2 columns F.silu(x1) * x2 */
+#define MB_EPI_RESIDUAL 3 /* out = bf16(bf16(acc + bias) + residual)                  x + f(x) */
+
+const char* mb_last_error(void);
+/* ABI version (bumped whenever a signature changes) and the device check used by the loaders. */
+int mb_abi_version(void);
+int mb_device_ok(void); /* 1 if the current device is sm_100, else 0 */
+int mb_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense linear layers  (tcgen05.mma + TMEM accumulators, operands staged by TMA, 128B-swizzled shared memory)
+ *
+ * out[M, N'] = epilogue( A[M, K] @ W[N, K]^T + bias[N] )      A, W, bias, residual, out: bf16; accumulate fp32.
+ * Replaces every nn.Linear on the path:
+ *   mingtok/vision_transformer/layers/attention.py:49,63 (qkv), :51,72 (proj); layers/swiglu_ffn.py:28-34 (w12, w3);
+ *   layers/mlp.py:27-39 (fc1 + GELU, fc2); layers/patch_embed.py:66,76 (32x32/s32 conv as GEMM after mb_patchify);
+ *   vision_transformer.py:171,177 (out_proj), :282,379 (in_proj), :366,483 (head); modeling_mingtok.py:117,183
+ *   (sem_to_pix); mingunivision/modeling_bailingmm.py:111-115 (linear_proj);
+ *   mingunivision/modeling_bailing_moe.py:760,824 (query_key_value, dense), :479-484 (expert / shared-expert MLP),
+ *   :1571-1574 (vis_head), :1619 (lm_head); mingunivision/diff_loss_rf_swiglu.py:27-34,215-219,311-313.
+ *
+ *   epi = MB_EPI_SWIGLU: W/bias must be packed by mb_pack_swiglu_rows (gate/up rows interleaved in blocks of 128),
+ *         N is the packed row count (multiple of 256) and the output has N/2 columns.
+ *   epi = MB_EPI_RESIDUAL: residual row for output row r is (res_row_mod > 0 ? r % res_row_mod : r).
+ *   Output row remap (all epilogues): out_row = r + (r / out_row_group) * out_row_pad when out_row_group > 0
+ *         (used to leave room for the cls token that the reference concatenates at the END of every image,
+ *         vision_transformer.py:221).
+ *   bias may be NULL.  K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, ldo % 8 == 0; any M, N >= 1.
+ * ------------------------------------------------------------------------------------------------------------- */
+int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                 int M, int N, int K, int epi, const void* residual, int64_t ldr, int res_row_mod, int out_row_group,
+                 int out_row_pad, void* stream);
+
+/* Weight pre-pack for MB_EPI_SWIGLU: src is the reference's w12 [2*H, K] (x1 rows then x2 rows, swiglu_ffn.py:32),
+ * dst is [2*Hp, K] with Hp = round_up(H, 128): block b holds rows x1[128b..128b+127] then x2[128b..128b+127]; rows
+ * beyond H are zero.  The same call packs the bias with K = 1.  (One-time, at load.) */
+int mb_pack_swiglu_rows(const void* src, void* dst, int H, int Hp, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Normalisation (one warp per row, fp32 statistics, bf16 in/out)
+ *   mb_layernorm: y = LN(x) * gamma + beta, eps; act = 0 none, 1 exact-erf GELU applied to bf16(LN) (encoder out
+ *   layer, vision_transformer.py:173-178).  gamma/beta may be NULL (elementwise_affine=False,
+ *   diff_loss_rf_swiglu.py:281).  Replaces nn.LayerNorm at layers/block.py:53,66,311,320,
+ *   vision_transformer.py:169,363,431.
+ * ------------------------------------------------------------------------------------------------------------- */
+int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy, int rows,
+                 int dim, float eps, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Attention, head_dim 64, packed QKV as produced by the qkv Linear:  qkv[B, S, 3, H, 64] bf16 -> out[B, S, H*64].
+ * softmax((q k^T) * scale) v with fp32 softmax; causal != 0 applies the lower-triangular mask.
+ * Replaces flash_attn_func at layers/attention.py:101 (full) and :232-234 (causal) and the eager twins :61-74,
+ * :138-163.
+ * ------------------------------------------------------------------------------------------------------------- */
+int mb_attn_hd64(const void* qkv, void* out, int B, int S, int H, float scale, int causal, void* stream);
+
+/* Decode-step attention against a static KV cache (semantic decoder, q_len = 1; layers/attention.py:213-239 with
+ * past_key_value).  qkv[B, 3, H, 64] holds the new token; its K/V are appended at position `t` of
+ * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t. */
+int mb_attn_hd64_decode(const void* qkv, void* kcache, void* vcache, void* out, int B, int H, int t, int Tmax,
+                        float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MingTok data-movement operators
+ * ------------------------------------------------------------------------------------------------------------- */
+/* im2row for the 32x32 stride-32 patch conv (layers/patch_embed.py:76-78): img[B, C, Hh, Ww] (fp32 if
+ * img_is_fp32 else bf16) -> rows[B*gh*gw, C*P*P] bf16, column order (c, py, px) = Conv2d weight.flatten(1). */
+int mb_patchify(const void* img, int img_is_fp32, void* rows, int B, int C, int Hh, int Ww, int P, void* stream);
+/* x[b, n, :] = bf16(cls + pos_cls) for every image (vision_transformer.py:221-222; cls token appended at the END). */
+int mb_fill_cls_row(void* x, const void* cls, const void* pos_cls, int B, int n_plus_1, int dim, void* stream);
+/* out[r, c] = mean_j x[r, c*g + j], g = dim / groups   (encoder shortcut, vision_transformer.py:174). */
+int mb_group_mean(const void* x, int64_t ldx, void* out, int rows, int dim, int groups, void* stream);
+/* y = x * scale + shift elementwise on bf16 (latent (de)normalisation, modeling_mingtok.py:162,168). */
+int mb_affine(const void* x, void* y, int64_t n, float scale, float shift, void* stream);
+/* Semantic-decoder input layer (vision_transformer.py:373-380):
+ * out[r, :] = bf16(bf16(W[dim, in_dim] @ x[r] + b) + repeat_interleave(x[r], dim / in_dim)); in_dim <= 64. */
+int mb_inproj_repeat(const void* x, const void* W, const void* b, void* out, int rows, int in_dim, int dim,
+                     void* stream);
+/* sem_to_pix rearrange "b (h w) (x y c) -> b (h x w y) c" (modeling_mingtok.py:184-188):
+ * in[B, g*g, f*f*C] -> out[B, (g*f)*(g*f), C]. */
+int mb_pixel_shuffle(const void* in, void* out, int B, int g, int f, int C, void* stream);
+/* unpatchify + clamp(-1, 1) (vision_transformer.py:515-527, modeling_mingtok.py:192-194):
+ * x[B, g*g, p*p*3] (channel-last inside the patch) -> img[B, 3, g*p, g*p]; out fp32 if out_is_fp32 else bf16. */
+int mb_unpatchify_clamp(const void* x, void* img, int out_is_fp32, int B, int g, int p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINGB200_H_ */

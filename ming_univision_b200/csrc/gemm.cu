@@ -1,0 +1,401 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] @ W[N,K]^T + bias).
+//
+//   warp 0        TMA producer   : cp.async.bulk.tensor 2-D loads of A (128 x 64) and W (BN x 64) tiles into a
+//                                  kStages-deep ring of 128B-swizzled shared-memory buffers, mbarrier complete_tx.
+//   warp 1        MMA issuer     : one lane issues tcgen05.mma (M=128, N=BN, K=16) with both operands read from
+//                                  shared memory through UMMA descriptors; accumulators live in TMEM, double
+//                                  buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of i+1.
+//   warps 2..9    epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> bias / GELU / SwiGLU / residual
+//                                  -> bf16 -> 16-byte global stores (each thread owns one output row segment).
+//
+// Both operands are K-major (nn.Linear weight layout), so no transposes are needed anywhere.
+// Tails in M, N and K are handled by TMA zero fill on loads and by predication on stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kNumEpiWarps = 8;
+constexpr int kGemmThreads = (2 + kNumEpiWarps) * 32;
+
+struct GemmParams {
+  int M, N, K;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* out;
+  int64_t ldo;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+  int res_row_mod;
+  int out_row_group;
+  int out_row_pad;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// Converts 32 fp32 values (one row segment) to bf16 and stores them; handles the N tail.
+__device__ __forceinline__ void store_row_segment(__nv_bfloat16* dst, const float (&v)[32], int ncols_valid) {
+  if (ncols_valid >= 32) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q;
+      q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+      q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+      q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+      q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+      d4[i] = q;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < ncols_valid) dst[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+__device__ __forceinline__ void load_bias32(const __nv_bfloat16* bias, int col0, int ncols_valid, float (&b)[32]) {
+  if (bias == nullptr) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = 0.f;
+    return;
+  }
+  if (ncols_valid >= 32) {
+    const uint4* p = reinterpret_cast<const uint4*>(bias + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 q = __ldg(p + i);
+      float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+      b[8 * i + 0] = f0.x; b[8 * i + 1] = f0.y; b[8 * i + 2] = f1.x; b[8 * i + 3] = f1.y;
+      b[8 * i + 4] = f2.x; b[8 * i + 5] = f2.y; b[8 * i + 6] = f3.x; b[8 * i + 7] = f3.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = (i < ncols_valid) ? __bfloat162float(bias[col0 + i]) : 0.f;
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_tiles = (p.M + kBM - 1) / kBM;
+  const int num_n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_k_blocks = (p.K + kBK - 1) / kBK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kNumEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / num_n_tiles;
+        const int n_tile = tile % num_n_tiles;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, m_tile * kBM);
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, n_tile * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;           // which half of the tile's columns
+    constexpr int kOutTileN = (EPI == MB_EPI_SWIGLU) ? BN / 2 : BN;
+    constexpr int kColsPerWarp = kOutTileN / 2;
+    const int n_out_total = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / num_n_tiles;
+      const int n_tile = tile % num_n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_tile * kBM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      int64_t out_row = row;
+      if (p.out_row_group > 0) out_row += static_cast<int64_t>(row / p.out_row_group) * p.out_row_pad;
+      const int64_t res_row = (p.res_row_mod > 0) ? (row % p.res_row_mod) : row;
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+
+#pragma unroll 1
+      for (int c = 0; c < kColsPerWarp; c += 32) {
+        const int tc = half * kColsPerWarp + c;       // column inside the output tile
+        const int out_col = n_tile * kOutTileN + tc;  // global output column
+        const int ncols_valid = n_out_total - out_col;
+        float v[32];
+        if constexpr (EPI == MB_EPI_SWIGLU) {
+          uint32_t g[32], u[32];
+          tmem_ld_32x32b_x32(t_row + tc, g);
+          tmem_ld_32x32b_x32(t_row + BN / 2 + tc, u);
+          tmem_ld_wait();
+          {
+            float bg[32];
+            load_bias32(p.bias, n_tile * BN + tc, 32, bg);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
+          }
+          {
+            float bu[32];
+            load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
+          }
+        } else {
+          uint32_t a[32];
+          tmem_ld_32x32b_x32(t_row + tc, a);
+          tmem_ld_wait();
+          float b[32];
+          load_bias32(p.bias, out_col, ncols_valid, b);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
+          if constexpr (EPI == MB_EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
+          }
+          if constexpr (EPI == MB_EPI_RESIDUAL) {
+            if (row_ok && ncols_valid > 0) {
+              const __nv_bfloat16* rp = p.residual + res_row * p.ldr + out_col;
+              if (ncols_valid >= 32) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(rp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint4 q = __ldg(r4 + i);
+                  const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
+                               f3 = unpack_bf16x2(q.w);
+                  v[8 * i + 0] = bf16_round(v[8 * i + 0]) + f0.x; v[8 * i + 1] = bf16_round(v[8 * i + 1]) + f0.y;
+                  v[8 * i + 2] = bf16_round(v[8 * i + 2]) + f1.x; v[8 * i + 3] = bf16_round(v[8 * i + 3]) + f1.y;
+                  v[8 * i + 4] = bf16_round(v[8 * i + 4]) + f2.x; v[8 * i + 5] = bf16_round(v[8 * i + 5]) + f2.y;
+                  v[8 * i + 6] = bf16_round(v[8 * i + 6]) + f3.x; v[8 * i + 7] = bf16_round(v[8 * i + 7]) + f3.y;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (i < ncols_valid) v[i] = bf16_round(v[i]) + __bfloat162float(rp[i]);
+              }
+            }
+          }
+        }
+        if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
+      }
+      // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+// Tile-width choice: fewer, fatter tiles (BN = 256) unless the tail wave wastes more than it saves.
+static int choose_bn(int M, int N, int sms) {
+  const int mt = (M + kBM - 1) / kBM;
+  auto cost = [&](int bn) {
+    const long tiles = static_cast<long>(mt) * ((N + bn - 1) / bn);
+    const long waves = (tiles + sms - 1) / sms;
+    return static_cast<double>(waves) * bn * (bn == 128 ? 1.10 : 1.0);
+  };
+  return cost(128) < cost(256) ? 128 : 256;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                            int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
+                            int res_row_mod, int out_row_group, int out_row_pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_gemm_bf16: no sm_100 device");
+  MB_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, MB_ERR_SHAPE, "mb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return MB_OK;
+  MB_CHECK_ARG(epi >= 0 && epi <= 3, MB_ERR_SHAPE, "mb_gemm_bf16: unknown epilogue %d", epi);
+  MB_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, MB_ERR_ALIGN,
+               "mb_gemm_bf16: K/lda/ldw/ldo must be multiples of 8 (K=%d lda=%ld ldw=%ld ldo=%ld)", K, (long)lda,
+               (long)ldw, (long)ldo);
+  MB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+               MB_ERR_ALIGN, "mb_gemm_bf16: A/W/out/bias must be 16-byte aligned");
+  if (epi == MB_EPI_SWIGLU)
+    MB_CHECK_ARG(N % 256 == 0, MB_ERR_SHAPE, "mb_gemm_bf16: SWIGLU needs packed N %% 256 == 0 (N=%d)", N);
+  if (epi == MB_EPI_RESIDUAL)
+    MB_CHECK_ARG(residual != nullptr && ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                 MB_ERR_ALIGN, "mb_gemm_bf16: RESIDUAL needs a 16-byte aligned residual with ldr %% 8 == 0");
+
+  const int sms = mb::num_sms();
+  const int bn = (epi == MB_EPI_SWIGLU) ? 256 : choose_bn(M, N, sms);
+
+  CUtensorMap ta, tb;
+  if (!make_tmap_2d_bf16(&ta, A, K, M, lda, kBK, kBM)) return MB_ERR_CUDA;
+  if (!make_tmap_2d_bf16(&tb, W, K, N, ldw, kBK, bn)) return MB_ERR_CUDA;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.ldr = ldr;
+  p.res_row_mod = res_row_mod;
+  p.out_row_group = out_row_group;
+  p.out_row_pad = out_row_pad;
+
+  const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
+  const int grid = tiles < sms ? tiles : sms;
+
+#define MB_DISPATCH(BN_)                                                                       \
+  switch (epi) {                                                                               \
+    case MB_EPI_BIAS: return launch_gemm<BN_, MB_EPI_BIAS>(ta, tb, p, grid, stream);           \
+    case MB_EPI_GELU: return launch_gemm<BN_, MB_EPI_GELU>(ta, tb, p, grid, stream);           \
+    case MB_EPI_RESIDUAL: return launch_gemm<BN_, MB_EPI_RESIDUAL>(ta, tb, p, grid, stream);   \
+    default: break;                                                                            \
+  }
+  if (epi == MB_EPI_SWIGLU) return launch_gemm<256, MB_EPI_SWIGLU>(ta, tb, p, grid, stream);
+  if (bn == 256) {
+    MB_DISPATCH(256)
+  } else {
+    MB_DISPATCH(128)
+  }
+#undef MB_DISPATCH
+  set_error("mb_gemm_bf16: unreachable dispatch");
+  return MB_ERR_SHAPE;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SwiGLU weight pre-pack
+// ------------------------------------------------------------------------------------------------------------
+namespace mb {
+__global__ void pack_swiglu_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H,
+                                        int Hp, int K) {
+  // one block per destination row
+  const int drow = blockIdx.x;
+  const int blk = drow / 256;
+  const int within = drow % 256;
+  const int is_up = within >= 128;
+  const int h = blk * 128 + (within & 127);
+  __nv_bfloat16* d = dst + static_cast<int64_t>(drow) * K;
+  if (h < H) {
+    const __nv_bfloat16* s = src + static_cast<int64_t>(is_up ? H + h : h) * K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) d[k] = s[k];
+  } else {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) d[k] = __float2bfloat16_rn(0.f);
+  }
+}
+}  // namespace mb
+
+extern "C" int mb_pack_swiglu_rows(const void* src, void* dst, int H, int Hp, int K, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(H >= 1 && Hp >= H && Hp % 128 == 0 && K >= 1, MB_ERR_SHAPE,
+               "mb_pack_swiglu_rows: need Hp %% 128 == 0 and Hp >= H (H=%d Hp=%d K=%d)", H, Hp, K);
+  pack_swiglu_rows_kernel<<<2 * Hp, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(src),
+                                                      static_cast<__nv_bfloat16*>(dst), H, Hp, K);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}

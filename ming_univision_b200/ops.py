@@ -1,0 +1,223 @@
+"""torch.Tensor -> raw pointer adapters over the C ABI (include/mingb200.h).
+
+PyTorch is used for device memory and the current CUDA stream only; every function here launches hand-written
+sm_100a kernels from libmingb200.so.  No function has an eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+EPI_BIAS, EPI_GELU, EPI_SWIGLU, EPI_RESIDUAL = 0, 1, 2, 3
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _check_bf16(*ts: torch.Tensor | None) -> None:
+    for t in ts:
+        if t is not None and (t.dtype != BF16 or not t.is_cuda):
+            raise TypeError(f"expected a CUDA bfloat16 tensor, got {t.dtype} on {t.device}")
+
+
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """View [..., D] as [rows, D] with a unit inner stride (no copy unless the layout forces one)."""
+    t2 = t.reshape(-1, t.shape[-1])
+    if t2.stride(-1) != 1:
+        t2 = t2.contiguous()
+    return t2
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GEMM
+# ---------------------------------------------------------------------------------------------------------------
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, *, epi: int = EPI_BIAS,
+           residual: torch.Tensor | None = None, res_row_mod: int = 0, out: torch.Tensor | None = None,
+           out_row_group: int = 0, out_row_pad: int = 0) -> torch.Tensor:
+    """out = epilogue(x @ weight.T + bias) on the tcgen05 GEMM.  x: [..., K], weight: [N, K] (nn.Linear layout)."""
+    _check_bf16(x, weight, bias, residual, out)
+    lib = _lib.load()
+    a = _rows2d(x)
+    M, K = a.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or weight.stride(1) != 1:
+        raise ValueError(f"weight shape {tuple(weight.shape)} incompatible with input K={K}")
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        if out_row_group:
+            raise ValueError("out_row_group needs a caller-provided output")
+        out2 = torch.empty((M, n_out), dtype=BF16, device=x.device)
+        ret = out2.view(*x.shape[:-1], n_out)
+    else:
+        out2 = _rows2d(out)
+        if out2.data_ptr() != out.data_ptr():
+            raise ValueError("out must be row-contiguous")
+        ret = out
+    r2, ldr = None, 0
+    if epi == EPI_RESIDUAL:
+        if residual is None:
+            raise ValueError("EPI_RESIDUAL needs a residual tensor")
+        r2 = _rows2d(residual)
+        ldr = r2.stride(0)
+    rc = lib.mb_gemm_bf16(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
+                          out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod, out_row_group,
+                          out_row_pad, _stream())
+    _lib.check(rc, "mb_gemm_bf16")
+    return ret
+
+
+def pack_swiglu(w12: torch.Tensor, b12: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor | None, int]:
+    """Packs the reference's w12 ([2H, K], x1 rows then x2 rows) for the fused SwiGLU epilogue.
+    Returns (packed weight [2*Hp, K], packed bias [2*Hp] or None, Hp)."""
+    _check_bf16(w12, b12)
+    lib = _lib.load()
+    H = w12.shape[0] // 2
+    K = w12.shape[1]
+    Hp = round_up(H, 128)
+    wp = torch.empty((2 * Hp, K), dtype=BF16, device=w12.device)
+    _lib.check(lib.mb_pack_swiglu_rows(w12.contiguous().data_ptr(), wp.data_ptr(), H, Hp, K, _stream()),
+               "mb_pack_swiglu_rows")
+    bp = None
+    if b12 is not None:
+        bp = torch.empty((2 * Hp,), dtype=BF16, device=w12.device)
+        _lib.check(lib.mb_pack_swiglu_rows(b12.contiguous().data_ptr(), bp.data_ptr(), H, Hp, 1, _stream()),
+                   "mb_pack_swiglu_rows")
+    return wp, bp, Hp
+
+
+def pad_cols(w: torch.Tensor, Kp: int) -> torch.Tensor:
+    """Zero-pads the input dimension of a weight [N, K] to Kp (w3 after the SwiGLU hidden padding)."""
+    N, K = w.shape
+    if K == Kp:
+        return w.contiguous()
+    wp = torch.zeros((N, Kp), dtype=w.dtype, device=w.device)
+    wp[:, :K] = w
+    return wp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# normalisation / attention
+# ---------------------------------------------------------------------------------------------------------------
+def layernorm(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-6,
+              act: int = 0) -> torch.Tensor:
+    _check_bf16(x, gamma, beta)
+    lib = _lib.load()
+    x2 = _rows2d(x)
+    y = torch.empty_like(x2, memory_format=torch.contiguous_format)
+    rc = lib.mb_layernorm(x2.data_ptr(), x2.stride(0), _ptr(gamma), _ptr(beta), y.data_ptr(), y.stride(0),
+                          x2.shape[0], x2.shape[1], float(eps), act, _stream())
+    _lib.check(rc, "mb_layernorm")
+    return y.view(x.shape)
+
+
+def attention_hd64(qkv: torch.Tensor, B: int, S: int, H: int, causal: bool) -> torch.Tensor:
+    """qkv: [B, S, 3*H*64] packed as (3, H, 64) -> [B, S, H*64]."""
+    _check_bf16(qkv)
+    lib = _lib.load()
+    if not qkv.is_contiguous() or qkv.numel() != B * S * 3 * H * 64:
+        raise ValueError("qkv must be contiguous [B, S, 3*H*64]")
+    out = torch.empty((B, S, H * 64), dtype=BF16, device=qkv.device)
+    rc = lib.mb_attn_hd64(qkv.data_ptr(), out.data_ptr(), B, S, H, 64 ** -0.5, int(causal), _stream())
+    _lib.check(rc, "mb_attn_hd64")
+    return out
+
+
+def attention_hd64_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, t: int) -> torch.Tensor:
+    """qkv: [B, 3*H*64] for the new token; caches [B, H, Tmax, 64]; appends at t and attends to 0..t."""
+    _check_bf16(qkv, kcache, vcache)
+    lib = _lib.load()
+    B, H, Tmax, hd = kcache.shape
+    if hd != 64 or not kcache.is_contiguous() or not vcache.is_contiguous() or not qkv.is_contiguous():
+        raise ValueError("caches must be contiguous [B, H, Tmax, 64]")
+    out = torch.empty((B, H * 64), dtype=BF16, device=qkv.device)
+    rc = lib.mb_attn_hd64_decode(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), B, H, t, Tmax,
+                                 64 ** -0.5, _stream())
+    _lib.check(rc, "mb_attn_hd64_decode")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MingTok data movement
+# ---------------------------------------------------------------------------------------------------------------
+def patchify(img: torch.Tensor, P: int) -> torch.Tensor:
+    lib = _lib.load()
+    if not img.is_cuda or img.dtype not in (torch.float32, BF16):
+        raise TypeError("img must be a CUDA fp32 or bf16 tensor")
+    img = img.contiguous()
+    B, Cc, Hh, Ww = img.shape
+    rows = torch.empty((B * (Hh // P) * (Ww // P), Cc * P * P), dtype=BF16, device=img.device)
+    rc = lib.mb_patchify(img.data_ptr(), int(img.dtype == torch.float32), rows.data_ptr(), B, Cc, Hh, Ww, P,
+                         _stream())
+    _lib.check(rc, "mb_patchify")
+    return rows
+
+
+def fill_cls_row(x: torch.Tensor, cls: torch.Tensor, pos_cls: torch.Tensor) -> None:
+    _check_bf16(x, cls, pos_cls)
+    lib = _lib.load()
+    B, n1, dim = x.shape
+    _lib.check(lib.mb_fill_cls_row(x.data_ptr(), cls.data_ptr(), pos_cls.data_ptr(), B, n1, dim, _stream()),
+               "mb_fill_cls_row")
+
+
+def group_mean(x: torch.Tensor, groups: int) -> torch.Tensor:
+    _check_bf16(x)
+    lib = _lib.load()
+    x2 = _rows2d(x)
+    out = torch.empty((x2.shape[0], groups), dtype=BF16, device=x.device)
+    _lib.check(lib.mb_group_mean(x2.data_ptr(), x2.stride(0), out.data_ptr(), x2.shape[0], x2.shape[1], groups,
+                                 _stream()), "mb_group_mean")
+    return out.view(*x.shape[:-1], groups)
+
+
+def affine(x: torch.Tensor, scale: float, shift: float) -> torch.Tensor:
+    _check_bf16(x)
+    lib = _lib.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(lib.mb_affine(x.data_ptr(), y.data_ptr(), x.numel(), float(scale), float(shift), _stream()),
+               "mb_affine")
+    return y
+
+
+def inproj_repeat(x: torch.Tensor, W: torch.Tensor, b: torch.Tensor | None) -> torch.Tensor:
+    _check_bf16(x, W, b)
+    lib = _lib.load()
+    x2 = _rows2d(x).contiguous()
+    dim, in_dim = W.shape
+    out = torch.empty((x2.shape[0], dim), dtype=BF16, device=x.device)
+    _lib.check(lib.mb_inproj_repeat(x2.data_ptr(), W.contiguous().data_ptr(), _ptr(b), out.data_ptr(), x2.shape[0],
+                                    in_dim, dim, _stream()), "mb_inproj_repeat")
+    return out.view(*x.shape[:-1], dim)
+
+
+def pixel_shuffle(x: torch.Tensor, g: int, f: int, Cc: int) -> torch.Tensor:
+    _check_bf16(x)
+    lib = _lib.load()
+    x = x.contiguous()
+    B = x.shape[0]
+    out = torch.empty((B, g * f * g * f, Cc), dtype=BF16, device=x.device)
+    _lib.check(lib.mb_pixel_shuffle(x.data_ptr(), out.data_ptr(), B, g, f, Cc, _stream()), "mb_pixel_shuffle")
+    return out
+
+
+def unpatchify_clamp(x: torch.Tensor, g: int, p: int, out_dtype: torch.dtype = BF16) -> torch.Tensor:
+    _check_bf16(x)
+    lib = _lib.load()
+    x = x.contiguous()
+    B = x.shape[0]
+    img = torch.empty((B, 3, g * p, g * p), dtype=out_dtype, device=x.device)
+    _lib.check(lib.mb_unpatchify_clamp(x.data_ptr(), img.data_ptr(), int(out_dtype == torch.float32), B, g, p,
+                                       _stream()), "mb_unpatchify_clamp")
+    return img

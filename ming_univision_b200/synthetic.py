@@ -1,0 +1,139 @@
+"""Seeded synthetic weights and inputs with the reference's state_dict keys and true shapes.
+
+No pretrained checkpoint, dataset or network exists in the build / benchmark environment, so
+parity tests, smoke() and bench.py all use these factories.  Every tensor is drawn from its own CPU generator seeded
+by (seed, key name), so any subset of the state_dict can be regenerated bit-identically on any machine.
+
+Distributions are chosen so activations stay O(1) through all 60 transformer blocks (which keeps the parity tests
+sensitive): Linear / conv weights ~ N(0, 1/fan_in), biases ~ N(0, 0.1^2), LayerNorm gamma ~ 1 + N(0, 0.1^2),
+beta ~ N(0, 0.1^2), cls / pos-embed ~ N(0, 0.5^2); the pixel head is scaled by 0.3 so the image is not saturated by
+the final clamp(-1, 1).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import math
+import os
+
+import torch
+
+MINGTOK_CONFIG = {  # mingtok/config/config_mingtok.json:3-26 of the reference
+    "low_level_encoder": {"img_size": 512, "patch_size": 32, "depth": 12, "embed_dim": 768,
+                          "ffn_layer": "swiglufused", "out_dim": 32},
+    "semantic_decoder": {"in_dim": 32, "patch_size": 32, "embed_dim": 1024, "decoder_depth": 24,
+                         "ffn_layer": "swiglufused"},
+    "pixel_decoder": {"patch_size": 16, "decoder_depth": 24, "norm_pix_loss": True, "embed_dim": 1024,
+                      "loss_type": "L1-plain"},
+    "scaling_factor": 8.09449291,
+    "mean": 1.46817409,
+}
+
+MINGTOK_TINY_CONFIG = {  # same topology, small widths: used for committed golden fixtures and fast CPU tests
+    "low_level_encoder": {"img_size": 128, "patch_size": 32, "depth": 2, "embed_dim": 128,
+                          "ffn_layer": "swiglufused", "out_dim": 32},
+    "semantic_decoder": {"in_dim": 32, "patch_size": 32, "embed_dim": 128, "decoder_depth": 2,
+                         "ffn_layer": "swiglufused"},
+    "pixel_decoder": {"patch_size": 16, "decoder_depth": 2, "norm_pix_loss": True, "embed_dim": 128,
+                      "loss_type": "L1-plain"},
+    "scaling_factor": 8.09449291,
+    "mean": 1.46817409,
+}
+
+
+def swiglu_hidden(dim: int, mlp_ratio: float = 4.0) -> int:
+    """SwiGLUFFNFused hidden width — mingtok/vision_transformer/layers/swiglu_ffn.py:66."""
+    return (int(int(dim * mlp_ratio) * 2 / 3) + 7) // 8 * 8
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    h = hashlib.sha256(f"{seed}:{key}".encode()).digest()
+    return torch.Generator(device="cpu").manual_seed(int.from_bytes(h[:8], "little") % (2 ** 63))
+
+
+def _normal(seed, key, shape, std, mean=0.0):
+    return torch.randn(shape, generator=_gen(seed, key), dtype=torch.float32) * std + mean
+
+
+def mingtok_param_shapes(config: dict) -> dict[str, tuple]:
+    """Reference state_dict schema (vision_transformer.py:97-171, 282-368, modeling_mingtok.py:117)."""
+    enc, sem, pix = config["low_level_encoder"], config["semantic_decoder"], config["pixel_decoder"]
+    shapes: dict[str, tuple] = {}
+
+    def linear(name, out_f, in_f):
+        shapes[name + ".weight"] = (out_f, in_f)
+        shapes[name + ".bias"] = (out_f,)
+
+    def norm(name, d):
+        shapes[name + ".weight"] = (d,)
+        shapes[name + ".bias"] = (d,)
+
+    def blocks(prefix, depth, d, ffn):
+        for i in range(depth):
+            p = f"{prefix}.blocks.0.{i}"
+            norm(p + ".norm1", d)
+            linear(p + ".attn.qkv", 3 * d, d)
+            linear(p + ".attn.proj", d, d)
+            norm(p + ".norm2", d)
+            if ffn == "swiglu":
+                hdn = swiglu_hidden(d)
+                linear(p + ".mlp.w12", 2 * hdn, d)
+                linear(p + ".mlp.w3", d, hdn)
+            else:
+                linear(p + ".mlp.fc1", 4 * d, d)
+                linear(p + ".mlp.fc2", d, 4 * d)
+
+    E, P = enc["embed_dim"], enc["patch_size"]
+    npatch = (enc["img_size"] // P) ** 2
+    shapes["low_level_encoder.cls_token"] = (1, 1, E)
+    shapes["low_level_encoder.pos_embed"] = (1, npatch + 1, E)
+    shapes["low_level_encoder.patch_embed.proj.weight"] = (E, 3, P, P)
+    shapes["low_level_encoder.patch_embed.proj.bias"] = (E,)
+    blocks("low_level_encoder", enc["depth"], E, "swiglu")
+    norm("low_level_encoder.out_norm", E)
+    linear("low_level_encoder.out_proj", enc["out_dim"], E)
+    S = sem["embed_dim"]
+    linear("semantic_decoder.in_proj", S, sem["in_dim"])
+    blocks("semantic_decoder", sem["decoder_depth"], S, "swiglu")
+    norm("semantic_decoder.norm", S)
+    D = pix["embed_dim"]
+    blocks("pixel_decoder", pix["decoder_depth"], D, "gelu")
+    norm("pixel_decoder.norm", D)
+    linear("pixel_decoder.head", pix["patch_size"] ** 2 * 3, D)
+    f = sem["patch_size"] // pix["patch_size"]
+    linear("sem_to_pix", D * f * f, S)
+    return shapes
+
+
+def mingtok_state_dict(config: dict, seed: int = 0, dtype=torch.float32) -> dict[str, torch.Tensor]:
+    sd = {}
+    for key, shape in mingtok_param_shapes(config).items():
+        if key.endswith("cls_token") or key.endswith("pos_embed"):
+            t = _normal(seed, key, shape, 0.5)
+        elif ".norm" in key or "out_norm" in key:
+            t = _normal(seed, key, shape, 0.1, 1.0 if key.endswith(".weight") else 0.0)
+        elif key.endswith(".bias"):
+            t = _normal(seed, key, shape, 0.1)
+        else:
+            fan_in = math.prod(shape[1:])
+            std = 1.0 / math.sqrt(fan_in)
+            if key.startswith("pixel_decoder.head"):
+                std *= 0.3
+            t = _normal(seed, key, shape, std)
+        sd[key] = t.to(dtype)
+    return sd
+
+
+def synthetic_images(batch: int, size: int, seed: int = 1234) -> torch.Tensor:
+    """ImageNet-val-shaped synthetic inputs in [-1, 1]: low-pass uniform field + N(0, 0.05^2)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    low = torch.rand((batch, 3, size // 8, size // 8), generator=g) * 2 - 1
+    img = torch.nn.functional.interpolate(low, size=(size, size), mode="bicubic", align_corners=False)
+    img = img + torch.randn((batch, 3, size, size), generator=g) * 0.05
+    return img.clamp(-1, 1)
+
+
+def save_config(config: dict, path: str) -> None:
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(config, f, indent=1)

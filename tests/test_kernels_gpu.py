@@ -1,0 +1,207 @@
+"""Operator-level numerics: every CUDA kernel behind the C ABI against a plain PyTorch fp32 reference of the same
+op on the same inputs (floating-point kernels; tolerances are the bf16 output rounding, stated per test)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(BF16)
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+GEMM_SHAPES = [
+    # (M, N, K)                      covers: single tile, M/N/K tails, both tile widths, long K, many tiles
+    (128, 256, 64), (128, 128, 128), (1, 32, 64), (65, 768, 768), (130, 2304, 768), (257, 1024, 2816),
+    (4160, 768, 2048), (1000, 96, 264), (300, 1000, 72), (16384, 1024, 1024), (2048, 3072, 1024), (512, 4096, 1024),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("epi", ["bias", "gelu", "residual"])
+def test_gemm_epilogues(cuda_device, M, N, K, epi):
+    from ming_univision_b200 import ops
+
+    if epi != "bias" and M * N * K > 4e9:
+        pytest.skip("large shape covered by the bias epilogue")
+    x = _rand((M, K), cuda_device, 1.0, 1)
+    w = _rand((N, K), cuda_device, 1.0 / math.sqrt(K), 2)
+    b = _rand((N,), cuda_device, 0.5, 3)
+    ref = x.float() @ w.float().t() + b.float()
+    pre = ref
+    if epi == "bias":
+        out = ops.linear(x, w, b)
+    elif epi == "gelu":
+        out = ops.linear(x, w, b, epi=ops.EPI_GELU)
+        ref = F.gelu(ref.to(BF16).float())
+    else:
+        r = _rand((M, N), cuda_device, 1.0, 4)
+        out = ops.linear(x, w, b, epi=ops.EPI_RESIDUAL, residual=r)
+        ref = ref.to(BF16).float() + r.float()
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    # bf16 rounding of the output (2^-8 relative) plus one bf16 ulp of the pre-activation / pre-residual value, whose
+    # rounding to bf16 (mirroring the reference's dtype flow) can flip when fp32 summation order differs
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2.0 ** -7 * pre.abs() + 1e-3
+    assert (err <= tol).all(), f"max err {err.max().item()} rel {_rel_err(out, ref)}"
+    assert _rel_err(out, ref) < 4e-3
+
+
+def test_gemm_no_bias_and_strided(cuda_device):
+    from ming_univision_b200 import ops
+
+    x_full = _rand((200, 512), cuda_device, 1.0, 5)
+    x = x_full[:, :256]  # row stride 512, K = 256
+    w = _rand((384, 256), cuda_device, 1 / 16, 6)
+    out = ops.linear(x, w, None)
+    ref = x.float() @ w.float().t()
+    assert _rel_err(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,K,H", [(65, 768, 2048), (130, 1024, 2736), (3, 3072, 8192), (4160, 1024, 2736)])
+def test_gemm_swiglu(cuda_device, M, K, H):
+    from ming_univision_b200 import ops
+
+    x = _rand((M, K), cuda_device, 1.0, 7)
+    w12 = _rand((2 * H, K), cuda_device, 1.0 / math.sqrt(K), 8)
+    b12 = _rand((2 * H,), cuda_device, 0.2, 9)
+    wp, bp, Hp = ops.pack_swiglu(w12, b12)
+    assert Hp % 128 == 0 and wp.shape == (2 * Hp, K)
+    out = ops.linear(x, wp, bp, epi=ops.EPI_SWIGLU)
+    assert out.shape == (M, Hp)
+    x12 = (x.float() @ w12.float().t() + b12.float()).to(BF16).float()
+    x1, x2 = x12[:, :H], x12[:, H:]
+    ref = F.silu(x1).to(BF16).float() * x2
+    torch.cuda.synchronize()
+    assert (out[:, H:].float() == 0).all(), "padded hidden columns must be exactly zero"
+    err = (out[:, :H].float() - ref).abs()
+    tol = 2.0 ** -6 * ref.abs() + 5e-3
+    assert (err <= tol).all(), f"max err {err.max().item()}"
+    assert _rel_err(out[:, :H], ref) < 6e-3
+
+
+def test_gemm_row_remap_and_rowmod_residual(cuda_device):
+    """patch-embed use: rows of image b land at b*(n+1)+p and the residual (pos-embed) is indexed by p."""
+    from ming_univision_b200 import ops
+
+    B, n, K, N = 5, 64, 3072, 768
+    x = _rand((B * n, K), cuda_device, 1.0, 10)
+    w = _rand((N, K), cuda_device, 1 / math.sqrt(K), 11)
+    b = _rand((N,), cuda_device, 0.1, 12)
+    pos = _rand((n, N), cuda_device, 1.0, 13)
+    out = torch.full((B, n + 1, N), 7.0, dtype=BF16, device=cuda_device)
+    ops.linear(x, w, b, epi=ops.EPI_RESIDUAL, residual=pos, res_row_mod=n, out=out, out_row_group=n, out_row_pad=1)
+    ref = (x.float() @ w.float().t() + b.float()).to(BF16).float().view(B, n, N) + pos.float()
+    assert (out[:, n].float() == 7.0).all(), "cls rows must be untouched"
+    assert _rel_err(out[:, :n], ref) < 4e-3
+
+
+@pytest.mark.parametrize("rows,dim", [(1, 768), (65, 1024), (4160, 768), (7, 3072), (33, 2048), (10, 64), (9, 136)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_layernorm(cuda_device, rows, dim, act):
+    from ming_univision_b200 import ops
+
+    x = _rand((rows, dim), cuda_device, 2.0, 20) + 0.5
+    g = (_rand((dim,), cuda_device, 0.1, 21).float() + 1).to(BF16)
+    b = _rand((dim,), cuda_device, 0.1, 22)
+    y = ops.layernorm(x, g, b, 1e-6, act)
+    ref = F.layer_norm(x.float(), (dim,), g.float(), b.float(), 1e-6)
+    if act:
+        ref = F.gelu(ref.to(BF16).float())
+    err = (y.float() - ref).abs()
+    assert (err <= 2.0 ** -7 * ref.abs() + 2e-3).all(), f"max err {err.max().item()}"
+    y2 = ops.layernorm(x, None, None, 1e-6, 0)
+    ref2 = F.layer_norm(x.float(), (dim,), None, None, 1e-6)
+    assert ((y2.float() - ref2).abs() <= 2.0 ** -7 * ref2.abs() + 2e-3).all()
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 65, 12), (2, 257, 16), (3, 64, 16), (2, 256, 16), (1, 1025, 12), (2, 1, 4),
+                                   (1, 130, 2)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_hd64(cuda_device, B, S, H, causal):
+    from ming_univision_b200 import ops
+
+    qkv = _rand((B, S, 3 * H * 64), cuda_device, 1.0, 30)
+    out = ops.attention_hd64(qkv, B, S, H, causal)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-1, -2)) * 64 ** -0.5
+    if causal:
+        att = att.masked_fill(torch.triu(torch.ones(S, S, device=cuda_device, dtype=torch.bool), 1), float("-inf"))
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(B, S, H * 64)
+    err = (out.float() - ref).abs()
+    # P is rounded to bf16 before the PV product (as flash-attn does): 2^-8 relative on O(1) values
+    assert err.max().item() < 2e-2, f"max err {err.max().item()}"
+    assert _rel_err(out, ref) < 8e-3
+
+
+def test_attention_decode_matches_full_causal(cuda_device):
+    from ming_univision_b200 import ops
+
+    B, H, T = 3, 16, 40
+    qkv = _rand((B, T, 3 * H * 64), cuda_device, 1.0, 31)
+    full = ops.attention_hd64(qkv, B, T, H, True)
+    kc = torch.zeros((B, H, 64, 64), dtype=BF16, device=cuda_device)
+    vc = torch.zeros_like(kc)
+    for t in range(T):
+        o = ops.attention_hd64_decode(qkv[:, t].contiguous(), kc, vc, t)
+        assert (o.float() - full[:, t].float()).abs().max().item() < 2e-2
+    k_ref = qkv.view(B, T, 3, H, 64)[:, :, 1].permute(0, 2, 1, 3)
+    assert torch.equal(kc[:, :, :T], k_ref)
+
+
+def test_mingtok_data_movement(cuda_device):
+    from einops import rearrange
+
+    from ming_univision_b200 import ops
+
+    B, C, P, g = 3, 3, 32, 4
+    img = torch.randn((B, C, g * P, g * P), device=cuda_device)
+    rows = ops.patchify(img, P)
+    w = torch.randn((16, C, P, P), device=cuda_device)
+    ref = F.conv2d(img.to(BF16).float(), w, stride=P).flatten(2).transpose(1, 2)  # [B, n, 16]
+    got = rows.float().view(B, g * g, -1) @ w.flatten(1).t()
+    assert torch.allclose(got, ref, atol=1e-2, rtol=1e-3)
+    assert torch.equal(ops.patchify(img.to(BF16), P), rows)
+
+    x = _rand((B, 5, 768), cuda_device, 1.0, 40)
+    gm = ops.group_mean(x, 32)
+    ref = rearrange(x.float(), "b n (c h) -> b n c h", c=32).mean(-1)
+    assert (gm.float() - ref).abs().max() < 1e-2
+
+    y = ops.affine(x, 8.094, 1.468)
+    assert (y.float() - (x.float() * 8.094 + 1.468)).abs().max() < 0.07
+
+    lat = _rand((B, 7, 32), cuda_device, 1.0, 41)
+    Wp = _rand((1024, 32), cuda_device, 0.2, 42)
+    bp = _rand((1024,), cuda_device, 0.2, 43)
+    got = ops.inproj_repeat(lat, Wp, bp)
+    ref = (lat.float() @ Wp.float().t() + bp.float()).to(BF16).float() + lat.float().repeat_interleave(32, dim=-1)
+    assert (got.float() - ref).abs().max() < 3e-2
+
+    s2p = _rand((B, g * g, 4 * 1024), cuda_device, 1.0, 44)
+    got = ops.pixel_shuffle(s2p, g, 2, 1024)
+    ref = rearrange(s2p, "b (h w) (x y c) -> b (h x w y) c", h=g, w=g, x=2, y=2)
+    assert torch.equal(got, ref)
+
+    tok = _rand((B, g * g, 16 * 16 * 3), cuda_device, 1.0, 45)
+    got = ops.unpatchify_clamp(tok, g, 16, torch.float32)
+    ref = torch.einsum("nhwpqc->nchpwq", tok.float().view(B, g, g, 16, 16, 3)).reshape(B, 3, g * 16, g * 16)
+    assert torch.equal(got, ref.clamp(-1, 1))
+
+    xx = torch.zeros((B, 5, 768), dtype=BF16, device=cuda_device)
+    cls, pos = _rand((768,), cuda_device, 1.0, 46), _rand((768,), cuda_device, 1.0, 47)
+    ops.fill_cls_row(xx, cls, pos)
+    assert torch.equal(xx[:, 4], (cls.float() + pos.float()).to(BF16).expand(B, -1))
+    assert (xx[:, :4] == 0).all()
