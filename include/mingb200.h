@@ -69,6 +69,11 @@ int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const v
                  int M, int N, int K, int epi, const void* residual, int64_t ldr, int res_row_mod, int out_row_group,
                  int out_row_pad, void* stream);
 
+/* Tuning / test hook: pin the GEMM tile shape instead of the built-in heuristic.  cta_group: 1 = one CTA per
+ * 128 x bn tile, 2 = CTA pair (tcgen05 cta_group::2) per 256 x bn tile, 0 = automatic; bn: 128, 256 or 0 = automatic.
+ * Process-wide; also settable through the MB_GEMM_CG / MB_GEMM_BN environment variables. */
+int mb_gemm_force_tile(int cta_group, int bn);
+
 /* Weight pre-pack for MB_EPI_SWIGLU: src is the reference's w12 [2*H, K] (x1 rows then x2 rows, swiglu_ffn.py:32),
  * dst is [2*Hp, K] with Hp = round_up(H, 128): block b holds rows x1[128b..128b+127] then x2[128b..128b+127]; rows
  * beyond H are zero.  The same call packs the bias with K = 1.  (One-time, at load.) */
@@ -80,9 +85,12 @@ int mb_pack_swiglu_rows(const void* src, void* dst, int H, int Hp, int K, void* 
  *   layer, vision_transformer.py:173-178).  gamma/beta may be NULL (elementwise_affine=False,
  *   diff_loss_rf_swiglu.py:281).  Replaces nn.LayerNorm at layers/block.py:53,66,311,320,
  *   vision_transformer.py:169,363,431.
+ *   Input row r lives at x + (r / rows_per_group) * group_stride_x + (r % rows_per_group) * ldx when
+ *   rows_per_group > 0 (reads only the first n of every n+1 tokens: the decoder drops the trailing cls token after
+ *   its final norm, vision_transformer.py:431-439); plain r * ldx when rows_per_group == 0.  Output rows are dense.
  * ------------------------------------------------------------------------------------------------------------- */
 int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy, int rows,
-                 int dim, float eps, int act, void* stream);
+                 int dim, float eps, int act, int rows_per_group, int64_t group_stride_x, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Attention, head_dim 64, packed QKV as produced by the qkv Linear:  qkv[B, S, 3, H, 64] bf16 -> out[B, S, H*64].
@@ -108,8 +116,9 @@ int mb_patchify(const void* img, int img_is_fp32, void* rows, int B, int C, int 
 int mb_fill_cls_row(void* x, const void* cls, const void* pos_cls, int B, int n_plus_1, int dim, void* stream);
 /* out[r, c] = mean_j x[r, c*g + j], g = dim / groups   (encoder shortcut, vision_transformer.py:174). */
 int mb_group_mean(const void* x, int64_t ldx, void* out, int rows, int dim, int groups, void* stream);
-/* y = x * scale + shift elementwise on bf16 (latent (de)normalisation, modeling_mingtok.py:162,168). */
-int mb_affine(const void* x, void* y, int64_t n, float scale, float shift, void* stream);
+/* y = bf16(x * scale + shift) elementwise; x is fp32 if x_is_fp32 else bf16 (latent (de)normalisation,
+ * modeling_mingtok.py:162,168 — the RF sampler hands an fp32 latent to forward_feature_decoder). */
+int mb_affine(const void* x, int x_is_fp32, void* y, int64_t n, float scale, float shift, void* stream);
 /* Semantic-decoder input layer (vision_transformer.py:373-380):
  * out[r, :] = bf16(bf16(W[dim, in_dim] @ x[r] + b) + repeat_interleave(x[r], dim / in_dim)); in_dim <= 64. */
 int mb_inproj_repeat(const void* x, const void* W, const void* b, void* out, int rows, int in_dim, int dim,

@@ -21,20 +21,26 @@ SIGNATURES = {
     "mb_device_ok": [],
     "mb_num_sms": [],
     "mb_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp],
+    "mb_gemm_force_tile": [_i, _i],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
-    "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _vp],
+    "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
     "mb_attn_hd64_decode": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "mb_patchify": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_fill_cls_row": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_group_mean": [_vp, _i64, _vp, _i, _i, _i, _vp],
-    "mb_affine": [_vp, _vp, _i64, _f, _f, _vp],
+    "mb_affine": [_vp, _i, _vp, _i64, _f, _f, _vp],
     "mb_inproj_repeat": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_pixel_shuffle": [_vp, _vp, _i, _i, _i, _i, _vp],
     "mb_unpatchify_clamp": [_vp, _vp, _i, _i, _i, _i, _vp],
 }
 
 _lib = None
+_launches = 0  # successful C-ABI calls == kernel launches issued by this process (each entry point launches one)
+
+
+def launch_count() -> int:
+    return _launches
 
 
 def header_symbols() -> list[str]:
@@ -66,6 +72,8 @@ def load() -> C.CDLL:
 
 
 def check(rc: int, what: str) -> None:
+    global _launches
+    _launches += 1
     if rc != 0:
         msg = load().mb_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed with code {rc}: {msg}")

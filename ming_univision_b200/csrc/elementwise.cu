@@ -33,11 +33,14 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int dim,
-                 float eps, int act) {
+                 float eps, int act, int rows_per_group, int64_t group_stride_x) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * ldx;
+  const __nv_bfloat16* xr = (rows_per_group > 0)
+                                ? x + static_cast<int64_t>(row / rows_per_group) * group_stride_x +
+                                      static_cast<int64_t>(row % rows_per_group) * ldx
+                                : x + static_cast<int64_t>(row) * ldx;
   float v[NV][8];
   float sum = 0.f;
 #pragma unroll
@@ -148,11 +151,14 @@ __global__ void group_mean_kernel(const __nv_bfloat16* __restrict__ x, int64_t l
   out[idx] = __float2bfloat16_rn(s / static_cast<float>(g));
 }
 
-__global__ void affine_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n,
-                              float scale, float shift) {
+template <bool kFp32In>
+__global__ void affine_kernel(const void* __restrict__ x_, __nv_bfloat16* __restrict__ y, int64_t n, float scale,
+                              float shift) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
-    y[i] = __float2bfloat16_rn(__bfloat162float(x[i]) * scale + shift);
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float v = kFp32In ? static_cast<const float*>(x_)[i] : __bfloat162float(static_cast<const __nv_bfloat16*>(x_)[i]);
+    y[i] = __float2bfloat16_rn(v * scale + shift);
+  }
 }
 
 __global__ void inproj_repeat_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
@@ -223,12 +229,14 @@ static inline int grid_for(int64_t n, int block) {
 using namespace mb;
 
 extern "C" int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const void* beta, void* y, int64_t ldy,
-                            int rows, int dim, float eps, int act, void* stream_) {
+                            int rows, int dim, float eps, int act, int rows_per_group, int64_t group_stride_x,
+                            void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_layernorm: no sm_100 device");
   MB_CHECK_ARG(rows >= 0 && dim >= 8 && dim % 8 == 0 && dim <= 4096, MB_ERR_SHAPE,
                "mb_layernorm: dim must be a multiple of 8 in [8, 4096] (dim=%d)", dim);
-  MB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, MB_ERR_ALIGN, "mb_layernorm: ldx/ldy must be multiples of 8");
+  MB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && group_stride_x % 8 == 0, MB_ERR_ALIGN,
+               "mb_layernorm: ldx/ldy/group_stride_x must be multiples of 8");
   if (rows == 0) return MB_OK;
   const int nv = (dim + 255) / 256;
   const int wpb = 8;
@@ -237,7 +245,9 @@ extern "C" int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const
   const __nv_bfloat16* gg = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
-#define MB_LN(NV_) layernorm_kernel<NV_><<<grid, block, 0, stream>>>(xx, ldx, gg, bb, yy, ldy, rows, dim, eps, act)
+#define MB_LN(NV_)                                                                                        \
+  layernorm_kernel<NV_><<<grid, block, 0, stream>>>(xx, ldx, gg, bb, yy, ldy, rows, dim, eps, act, rows_per_group, \
+                                                    group_stride_x)
   if (nv <= 1) MB_LN(1);
   else if (nv <= 2) MB_LN(2);
   else if (nv <= 3) MB_LN(3);
@@ -290,12 +300,14 @@ extern "C" int mb_group_mean(const void* x, int64_t ldx, void* out, int rows, in
   return MB_OK;
 }
 
-extern "C" int mb_affine(const void* x, void* y, int64_t n, float scale, float shift, void* stream_) {
+extern "C" int mb_affine(const void* x, int x_is_fp32, void* y, int64_t n, float scale, float shift, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_affine: no sm_100 device");
   if (n == 0) return MB_OK;
-  affine_kernel<<<grid_for(n, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
-                                                      static_cast<__nv_bfloat16*>(y), n, scale, shift);
+  if (x_is_fp32)
+    affine_kernel<true><<<grid_for(n, 256), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), n, scale, shift);
+  else
+    affine_kernel<false><<<grid_for(n, 256), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), n, scale, shift);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

@@ -8,11 +8,18 @@
 //   warps 2..9    epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> bias / GELU / SwiGLU / residual
 //                                  -> bf16 -> 16-byte global stores (each thread owns one output row segment).
 //
+// CG = 2 runs the same roles on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA
+// stages its own 128 rows of A and HALF of the W tile (BN/2 rows), the leader CTA issues M = 256 MMAs that read both
+// CTAs' shared memory, and each CTA drains its own 128 accumulator rows from its TMEM.  Per CTA this loads
+// 32 KB instead of 48 KB per 128x256x64 MACs (1.5x less L2 -> SM traffic, half the B shared-memory reads).
+//
 // Both operands are K-major (nn.Linear weight layout), so no transposes are needed anywhere.
 // Tails in M, N and K are handled by TMA zero fill on loads and by predication on stores.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -36,14 +43,16 @@ struct GemmParams {
   int out_row_pad;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kABytes = kBM * kBK * 2;
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kABytes = kBM * kBK * 2;           // this CTA's 128 rows of A
+  static constexpr int kBRows = BN / CG;                  // this CTA's share of the W tile
+  static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTileM = kBM * CG;
 };
 
 // Converts 32 fp32 values (one row segment) to bf16 and stores them; handles the N tail.
@@ -87,12 +96,18 @@ __device__ __forceinline__ void load_bias32(const __nv_bfloat16* bias, int col0,
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kTileM = Cfg::kTileM;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool is_leader = cta_rank == 0;
+  // one "worker" = a CTA (CG = 1) or a CTA pair (CG = 2)
+  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / CG;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -108,7 +123,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_tiles = (p.M + kBM - 1) / kBM;
+  const int num_m_tiles = (p.M + kTileM - 1) / kTileM;
   const int num_n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_k_blocks = (p.K + kBK - 1) / kBK;
@@ -122,16 +137,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kNumEpiWarps);
+      mbar_init(&tmem_empty[a], kNumEpiWarps * CG);  // CG = 2: the leader's barrier collects both CTAs' epilogues
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_base_slot, Cfg::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -140,27 +160,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int m_tile = tile / num_n_tiles;
         const int n_tile = tile % num_n_tiles;
+        const int a_row = m_tile * kTileM + static_cast<int>(cta_rank) * kBM;
+        const int b_row = n_tile * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, m_tile * kBM);
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, n_tile * BN);
+          if constexpr (CG == 2) {
+            // both CTAs' loads complete on the LEADER's full barrier, which expects the bytes of the whole pair
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_cg2(&tmap_a, leader_full, smem_a + stage * Cfg::kABytes, kb * kBK, a_row);
+            tma_load_2d_cg2(&tmap_b, leader_full, smem_b + stage * Cfg::kBBytes, kb * kBK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, a_row);
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, b_row);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -172,12 +202,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above have read it
+          // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
+          if constexpr (CG == 2) umma_commit_cg2_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if constexpr (CG == 2) umma_commit_cg2_mc(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -191,12 +224,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int n_out_total = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_tile * kBM + quad * 32 + lane;
+      const int row = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       int64_t out_row = row;
       if (p.out_row_group > 0) out_row += static_cast<int64_t>(row / p.out_row_group) * p.out_row_pad;
@@ -266,48 +299,84 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer may still signal our barriers until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::kSmemBytes));
     attr_set = true;
   }
-  gemm_bf16_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, CG>, ta, tb, p));
   return MB_OK;
 }
 
-// Tile-width choice: fewer, fatter tiles (BN = 256) unless the tail wave wastes more than it saves.
-static int choose_bn(int M, int N, int sms) {
-  const int mt = (M + kBM - 1) / kBM;
-  auto cost = [&](int bn) {
-    const long tiles = static_cast<long>(mt) * ((N + bn - 1) / bn);
-    const long waves = (tiles + sms - 1) / sms;
-    return static_cast<double>(waves) * bn * (bn == 128 ? 1.10 : 1.0);
-  };
-  return cost(128) < cost(256) ? 128 : 256;
+// Tile shape choice.  A "worker" is a CTA (CG = 1, 128 x BN tile) or a CTA pair (CG = 2, 256 x BN tile); the model is
+// waves x per-tile MMA time x a measured penalty for the L2 -> SM traffic of the narrower shapes (bench_ops.py).
+struct TileChoice { int cg, bn; };
+static int g_force_cg = getenv("MB_GEMM_CG") ? atoi(getenv("MB_GEMM_CG")) : 0;
+static int g_force_bn = getenv("MB_GEMM_BN") ? atoi(getenv("MB_GEMM_BN")) : 0;
+static TileChoice choose_tile(int M, int N, int sms, bool swiglu) {
+  const int force_cg = g_force_cg, force_bn = g_force_bn;
+  const TileChoice cands[4] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
+  const double penalty[4] = {1.0, 1.12, 1.25, 1.45};
+  TileChoice best = {2, 256};
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const TileChoice c = cands[i];
+    if (swiglu && c.bn != 256) continue;
+    if (force_cg && c.cg != force_cg) continue;
+    if (force_bn && c.bn != force_bn) continue;
+    const long tiles = static_cast<long>((M + 128 * c.cg - 1) / (128 * c.cg)) * ((N + c.bn - 1) / c.bn);
+    const long workers = sms / c.cg;
+    const long waves = (tiles + workers - 1) / workers;
+    const double cost = static_cast<double>(waves) * c.bn * penalty[i];
+    if (cost < best_cost) { best_cost = cost; best = c; }
+  }
+  return best;
 }
 
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int mb_gemm_force_tile(int cta_group, int bn) {
+  MB_CHECK_ARG((cta_group == 0 || cta_group == 1 || cta_group == 2) && (bn == 0 || bn == 128 || bn == 256), MB_ERR_SHAPE,
+               "mb_gemm_force_tile: cta_group in {0,1,2}, bn in {0,128,256}");
+  mb::g_force_cg = cta_group;
+  mb::g_force_bn = bn;
+  return MB_OK;
+}
 
 extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
                             int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
@@ -330,11 +399,12 @@ extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                  MB_ERR_ALIGN, "mb_gemm_bf16: RESIDUAL needs a 16-byte aligned residual with ldr %% 8 == 0");
 
   const int sms = mb::num_sms();
-  const int bn = (epi == MB_EPI_SWIGLU) ? 256 : choose_bn(M, N, sms);
+  const TileChoice tc = choose_tile(M, N, sms, epi == MB_EPI_SWIGLU);
+  const int bn = tc.bn, cg = tc.cg;
 
   CUtensorMap ta, tb;
   if (!make_tmap_2d_bf16(&ta, A, K, M, lda, kBK, kBM)) return MB_ERR_CUDA;
-  if (!make_tmap_2d_bf16(&tb, W, K, N, ldw, kBK, bn)) return MB_ERR_CUDA;
+  if (!make_tmap_2d_bf16(&tb, W, K, N, ldw, kBK, bn / cg)) return MB_ERR_CUDA;
 
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -347,23 +417,26 @@ extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.out_row_group = out_row_group;
   p.out_row_pad = out_row_pad;
 
-  const int tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn);
-  const int grid = tiles < sms ? tiles : sms;
+  const int tiles = ((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
+  const int workers = sms / cg;
+  const int grid = (tiles < workers ? tiles : workers) * cg;
 
-#define MB_DISPATCH(BN_)                                                                       \
-  switch (epi) {                                                                               \
-    case MB_EPI_BIAS: return launch_gemm<BN_, MB_EPI_BIAS>(ta, tb, p, grid, stream);           \
-    case MB_EPI_GELU: return launch_gemm<BN_, MB_EPI_GELU>(ta, tb, p, grid, stream);           \
-    case MB_EPI_RESIDUAL: return launch_gemm<BN_, MB_EPI_RESIDUAL>(ta, tb, p, grid, stream);   \
-    default: break;                                                                            \
+#define MB_DISPATCH_EPI(BN_, CG_)                                                                  \
+  switch (epi) {                                                                                   \
+    case MB_EPI_BIAS: return launch_gemm<BN_, MB_EPI_BIAS, CG_>(ta, tb, p, grid, stream);          \
+    case MB_EPI_GELU: return launch_gemm<BN_, MB_EPI_GELU, CG_>(ta, tb, p, grid, stream);          \
+    case MB_EPI_RESIDUAL: return launch_gemm<BN_, MB_EPI_RESIDUAL, CG_>(ta, tb, p, grid, stream);  \
+    default: break;                                                                                \
   }
-  if (epi == MB_EPI_SWIGLU) return launch_gemm<256, MB_EPI_SWIGLU>(ta, tb, p, grid, stream);
-  if (bn == 256) {
-    MB_DISPATCH(256)
-  } else {
-    MB_DISPATCH(128)
+  if (epi == MB_EPI_SWIGLU) {
+    if (cg == 2) return launch_gemm<256, MB_EPI_SWIGLU, 2>(ta, tb, p, grid, stream);
+    return launch_gemm<256, MB_EPI_SWIGLU, 1>(ta, tb, p, grid, stream);
   }
-#undef MB_DISPATCH
+  if (cg == 2 && bn == 256) { MB_DISPATCH_EPI(256, 2) }
+  else if (cg == 2) { MB_DISPATCH_EPI(128, 2) }
+  else if (bn == 256) { MB_DISPATCH_EPI(256, 1) }
+  else { MB_DISPATCH_EPI(128, 1) }
+#undef MB_DISPATCH_EPI
   set_error("mb_gemm_bf16: unreachable dispatch");
   return MB_ERR_SHAPE;
 }

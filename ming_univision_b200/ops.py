@@ -12,6 +12,10 @@ from . import _lib
 EPI_BIAS, EPI_GELU, EPI_SWIGLU, EPI_RESIDUAL = 0, 1, 2, 3
 BF16 = torch.bfloat16
 
+# When set to a list, linear() brackets every GEMM launch with CUDA events on the launching stream and appends
+# ((M, N, K, epi), flops, start_event, end_event) — used by bench.py for the roofline of the dominant kernel.
+PROFILE: list | None = None
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -70,9 +74,16 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
             raise ValueError("EPI_RESIDUAL needs a residual tensor")
         r2 = _rows2d(residual)
         ldr = r2.stride(0)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = lib.mb_gemm_bf16(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
                           out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod, out_row_group,
                           out_row_pad, _stream())
+    if prof is not None:
+        ev1.record()
+        prof.append(((M, N, K, epi), 2.0 * M * N * K, ev0, ev1))
     _lib.check(rc, "mb_gemm_bf16")
     return ret
 
@@ -110,13 +121,24 @@ def pad_cols(w: torch.Tensor, Kp: int) -> torch.Tensor:
 # normalisation / attention
 # ---------------------------------------------------------------------------------------------------------------
 def layernorm(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None, eps: float = 1e-6,
-              act: int = 0) -> torch.Tensor:
+              act: int = 0, drop_last_token: bool = False) -> torch.Tensor:
+    """LayerNorm over the last dim.  drop_last_token: x is [B, n+1, D] and only the first n tokens of every image are
+    normalised and returned densely as [B, n, D] (the decoder's `x_norm[:, :-1]`)."""
     _check_bf16(x, gamma, beta)
     lib = _lib.load()
+    if drop_last_token:
+        if x.dim() != 3 or not x.is_contiguous():
+            raise ValueError("drop_last_token needs a contiguous [B, n+1, D] input")
+        B, n1, D = x.shape
+        y = torch.empty((B, n1 - 1, D), dtype=BF16, device=x.device)
+        rc = lib.mb_layernorm(x.data_ptr(), D, _ptr(gamma), _ptr(beta), y.data_ptr(), D, B * (n1 - 1), D, float(eps),
+                              act, n1 - 1, n1 * D, _stream())
+        _lib.check(rc, "mb_layernorm")
+        return y
     x2 = _rows2d(x)
     y = torch.empty_like(x2, memory_format=torch.contiguous_format)
     rc = lib.mb_layernorm(x2.data_ptr(), x2.stride(0), _ptr(gamma), _ptr(beta), y.data_ptr(), y.stride(0),
-                          x2.shape[0], x2.shape[1], float(eps), act, _stream())
+                          x2.shape[0], x2.shape[1], float(eps), act, 0, 0, _stream())
     _lib.check(rc, "mb_layernorm")
     return y.view(x.shape)
 
@@ -182,12 +204,14 @@ def group_mean(x: torch.Tensor, groups: int) -> torch.Tensor:
 
 
 def affine(x: torch.Tensor, scale: float, shift: float) -> torch.Tensor:
-    _check_bf16(x)
+    """bf16(x * scale + shift); x may be fp32 (RF-sampler latents) or bf16."""
+    if not x.is_cuda or x.dtype not in (torch.float32, BF16):
+        raise TypeError("affine expects a CUDA fp32 or bf16 tensor")
     lib = _lib.load()
     x = x.contiguous()
-    y = torch.empty_like(x)
-    _lib.check(lib.mb_affine(x.data_ptr(), y.data_ptr(), x.numel(), float(scale), float(shift), _stream()),
-               "mb_affine")
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _lib.check(lib.mb_affine(x.data_ptr(), int(x.dtype == torch.float32), y.data_ptr(), x.numel(), float(scale),
+                             float(shift), _stream()), "mb_affine")
     return y
 
 

@@ -49,11 +49,19 @@ def main():
         r = torch.randn((M, n_out), device=dev).to(torch.bfloat16)
         out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
         e = {"bias": ops.EPI_BIAS, "gelu": ops.EPI_GELU, "swiglu": ops.EPI_SWIGLU, "residual": ops.EPI_RESIDUAL}[epi]
-        ms = timeit(lambda: ops.linear(x, w, b, epi=e, residual=r if epi == "residual" else None, out=out))
         ms_t = timeit(lambda: torch.nn.functional.linear(x, w, b))
-        tf = 2.0 * M * N * K / ms / 1e9
-        res.append({"op": name, "M": M, "N": N, "K": K, "epi": epi, "ms": round(ms, 4), "tflops": round(tf, 1),
-                    "cublas_ms": round(ms_t, 4), "cublas_tflops": round(2.0 * M * N * K / ms_t / 1e9, 1)})
+        row = {"op": name, "M": M, "N": N, "K": K, "epi": epi,
+               "cublas_tflops": round(2.0 * M * N * K / ms_t / 1e9, 1)}
+        from ming_univision_b200 import _lib
+        for tname, cg, bn in (("auto", 0, 0), ("pair256", 2, 256), ("pair128", 2, 128), ("single256", 1, 256),
+                              ("single128", 1, 128)):
+            if epi == "swiglu" and bn == 128:
+                continue
+            _lib.load().mb_gemm_force_tile(cg, bn)
+            ms = timeit(lambda: ops.linear(x, w, b, epi=e, residual=r if epi == "residual" else None, out=out))
+            row[tname] = round(2.0 * M * N * K / ms / 1e9, 1)
+        _lib.load().mb_gemm_force_tile(0, 0)
+        res.append(row)
         print(res[-1], flush=True)
     for name, B, S, H, causal in [("enc.attn", 64, 65, 12, False), ("sem.attn", 64, 65, 16, True),
                                   ("pix.attn", 64, 256, 16, False), ("pix512.attn", 16, 1024, 16, False)]:
