@@ -38,6 +38,8 @@ extern "C" {
 #define MB_EPI_GELU 1     /* out = bf16(gelu_erf(bf16(acc + bias)))                   nn.Linear -> nn.GELU() */
 #define MB_EPI_SWIGLU 2   /* packed w12: out = bf16(bf16(silu(x1)) * x2), N/2 columns F.silu(x1) * x2 */
 #define MB_EPI_RESIDUAL 3 /* out = bf16(bf16(acc + bias) + residual)                  x + f(x) */
+#define MB_EPI_SILU 4     /* (mb_gemv_bf16 only) out = bf16(silu(bf16(acc + bias)))  nn.Linear -> nn.SiLU() */
+#define MB_EPI_GATED 5    /* (mb_gemv_bf16 only) out = bf16(res + bf16(gate * bf16(acc + bias)))  x + gate * h */
 
 const char* mb_last_error(void);
 /* ABI version (bumped whenever a signature changes) and the device check used by the loaders. */
@@ -68,6 +70,21 @@ int mb_num_sms(void);
 int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                  int M, int N, int K, int epi, const void* residual, int64_t ldr, int res_row_mod, int out_row_group,
                  int out_row_pad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Weight-streaming skinny GEMM for the decode regime (M <= 8 rows; HBM-bound, every weight byte read once):
+ *   out[M, N'] = epilogue(A[M, K] @ W[N, K]^T + bias)       A, W, bias, residual, gate, out: bf16; accumulate fp32.
+ * Replaces the M <= 3 nn.Linear calls of the rectified-flow head (diff_loss_rf_swiglu.py:30-34, 215-219, 262-265,
+ * 283-286, 311-313), of forward_for_image_generation_inner / the AR decode step (modeling_bailing_moe.py:760, 824,
+ * 479-484, 1571-1574, 1619) and of the cached semantic-decoder step (layers/attention.py:215, swiglu_ffn.py:30-34).
+ *   epi = MB_EPI_SWIGLU takes the REFERENCE layout of w12 ([2H, K]: x1 rows then x2 rows) and writes H columns.
+ *   epi = MB_EPI_GATED : out = res + gate * (A W^T + b)   (ResBlock, diff_loss_rf_swiglu.py:272).
+ *   out_f32 (optional, may be NULL): fp32 copy of the bf16-rounded output, dense [M, N'] (logits .float(),
+ *   modeling_bailing_moe.py:1785).
+ * ------------------------------------------------------------------------------------------------------------- */
+int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                 int M, int N, int K, int epi, const void* residual, int64_t ldr, const void* gate, int64_t ldg,
+                 void* out_f32, void* stream);
 
 /* Tuning / test hook: pin the GEMM tile shape instead of the built-in heuristic.  cta_group: 1 = one CTA per
  * 128 x bn tile, 2 = CTA pair (tcgen05 cta_group::2) per 256 x bn tile, 0 = automatic; bn: 128, 256 or 0 = automatic.
@@ -129,6 +146,25 @@ int mb_pixel_shuffle(const void* in, void* out, int B, int g, int f, int C, void
 /* unpatchify + clamp(-1, 1) (vision_transformer.py:515-527, modeling_mingtok.py:192-194):
  * x[B, g*g, p*p*3] (channel-last inside the patch) -> img[B, 3, g*p, g*p]; out fp32 if out_is_fp32 else bf16. */
 int mb_unpatchify_clamp(const void* x, void* img, int out_is_fp32, int B, int g, int p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Rectified-flow head (mingunivision/diff_loss_rf_swiglu.py) row helpers
+ * ------------------------------------------------------------------------------------------------------------- */
+/* y[m] = bf16((LN(x[m]) * gamma + beta) * bf16(1 + scale[m]) + shift[m]); gamma/beta NULL for the affine-free final
+ * norm.  modulate(), diff_loss_rf_swiglu.py:184-185 at :270 and :290. */
+int mb_adaln_modulate(const void* x, int64_t ldx, const void* gamma, const void* beta, const void* shift,
+                      int64_t ld_shift, const void* scale, int64_t ld_scale, void* y, int64_t ldy, int rows, int dim,
+                      float eps, void* stream);
+/* out[s*B + b, :] = bf16(silu(bf16(temb[s, :] + c[b, :]))): the SiLU(y = t + c) input of every adaLN_modulation
+ * Linear (diff_loss_rf_swiglu.py:376, 262-265, 283-286) for all `steps` sampling steps at once, so the adaLN weights
+ * (28 % of the head) are streamed once per token instead of once per Euler step. */
+int mb_silu_add_rows(const void* temb, const void* c, void* out, int steps, int B, int dim, void* stream);
+/* CFG combine + explicit Euler update of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:145-179):
+ * v bf16 [B, C] rows (cond, uncond[, text_uncond]); B == 3: v = v_u + image_cfg (v_tu - v_u) + text_cfg (v_c - v_tu);
+ * B == 2: v = v_u + text_cfg (v_c - v_u); otherwise per-row.  x_f32[B, C] += bf16(v * dt) on every row; x_bf16
+ * receives the bf16 copy that feeds input_proj on the next step. */
+int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, float dt, float text_cfg,
+                     float image_cfg, void* stream);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,10 @@ SIGNATURES = {
     "mb_num_sms": [],
     "mb_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp],
     "mb_gemm_force_tile": [_i, _i],
+    "mb_gemv_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
+    "mb_adaln_modulate": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _f, _vp],
+    "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
     "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],

@@ -348,8 +348,11 @@ static int g_force_cg = getenv("MB_GEMM_CG") ? atoi(getenv("MB_GEMM_CG")) : 0;
 static int g_force_bn = getenv("MB_GEMM_BN") ? atoi(getenv("MB_GEMM_BN")) : 0;
 static TileChoice choose_tile(int M, int N, int sms, bool swiglu) {
   const int force_cg = g_force_cg, force_bn = g_force_bn;
+  // Measured on B200 (tools/bench_ops.py, gpurun_out/bench_ops2.log): every shape is bound by L2 -> SM operand
+  // traffic (~12-13 TB/s), so the 256-wide tiles always win per wave; the pair kernel moves 1.5x fewer bytes per
+  // MAC than the single-CTA one but quantises M to 256.  The narrow tiles only pay off when they save whole waves.
   const TileChoice cands[4] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
-  const double penalty[4] = {1.0, 1.12, 1.25, 1.45};
+  const double penalty[4] = {1.0, 1.7, 1.06, 1.7};
   TileChoice best = {2, 256};
   double best_cost = 1e30;
   for (int i = 0; i < 4; ++i) {

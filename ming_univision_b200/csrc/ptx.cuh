@@ -202,7 +202,20 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(b);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below
+// the bf16 output rounding) — ~14 instructions and two MUFU ops per element instead of erff()'s ~35, which matters
+// because the GEMM epilogue has a budget of ~30 issue slots per element at K = 1024 before it outlasts the MMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float erf_abs = fmaf(-p * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 }  // namespace mb

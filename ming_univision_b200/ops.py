@@ -245,3 +245,73 @@ def unpatchify_clamp(x: torch.Tensor, g: int, p: int, out_dtype: torch.dtype = B
     _lib.check(lib.mb_unpatchify_clamp(x.data_ptr(), img.data_ptr(), int(out_dtype == torch.float32), B, g, p,
                                        _stream()), "mb_unpatchify_clamp")
     return img
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# decode regime: weight-streaming skinny GEMM + rectified-flow row helpers
+# ---------------------------------------------------------------------------------------------------------------
+EPI_SILU, EPI_GATED = 4, 5
+
+
+def gemv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, *, epi: int = EPI_BIAS,
+         residual: torch.Tensor | None = None, gate: torch.Tensor | None = None, out: torch.Tensor | None = None,
+         out_f32: torch.Tensor | None = None) -> torch.Tensor:
+    """out = epilogue(x @ weight.T + bias) for M <= 8 rows on the HBM-streaming kernel (mb_gemv_bf16).
+    EPI_SWIGLU takes the reference w12 layout [2H, K]; EPI_GATED computes residual + gate * (...)."""
+    _check_bf16(x, weight, bias, residual, gate, out)
+    lib = _lib.load()
+    a = _rows2d(x)
+    M, K = a.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or weight.stride(1) != 1:
+        raise ValueError(f"weight shape {tuple(weight.shape)} incompatible with input K={K}")
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=x.device)
+    for t in (residual, gate):
+        if t is not None and t.stride(-1) != 1:
+            raise ValueError("residual / gate must have a unit inner stride")
+    rc = lib.mb_gemv_bf16(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias), out.data_ptr(),
+                          out.stride(0), M, N, K, epi, _ptr(residual), residual.stride(0) if residual is not None else 0,
+                          _ptr(gate), gate.stride(0) if gate is not None else 0, _ptr(out_f32), _stream())
+    _lib.check(rc, "mb_gemv_bf16")
+    return out
+
+
+def adaln_modulate(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None, shift: torch.Tensor,
+                   scale: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """bf16((LN(x) * gamma + beta) * bf16(1 + scale) + shift) row-wise; shift / scale may be strided row views."""
+    _check_bf16(x, gamma, beta, shift, scale)
+    lib = _lib.load()
+    rows, dim = x.shape
+    if shift.stride(-1) != 1 or scale.stride(-1) != 1 or x.stride(-1) != 1:
+        raise ValueError("unit inner strides required")
+    y = torch.empty((rows, dim), dtype=BF16, device=x.device)
+    rc = lib.mb_adaln_modulate(x.data_ptr(), x.stride(0), _ptr(gamma), _ptr(beta), shift.data_ptr(), shift.stride(0),
+                               scale.data_ptr(), scale.stride(0), y.data_ptr(), dim, rows, dim, float(eps), _stream())
+    _lib.check(rc, "mb_adaln_modulate")
+    return y
+
+
+def silu_add_rows(temb: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """[steps, D], [B, D] -> [steps*B, D]: bf16(silu(bf16(temb[s] + c[b]))), row index s*B + b."""
+    _check_bf16(temb, c)
+    lib = _lib.load()
+    steps, dim = temb.shape
+    B = c.shape[0]
+    out = torch.empty((steps * B, dim), dtype=BF16, device=c.device)
+    _lib.check(lib.mb_silu_add_rows(temb.contiguous().data_ptr(), c.contiguous().data_ptr(), out.data_ptr(), steps, B,
+                                    dim, _stream()), "mb_silu_add_rows")
+    return out
+
+
+def rf_euler_step(x_f32: torch.Tensor, x_bf16: torch.Tensor, v: torch.Tensor, dt: float, text_cfg: float,
+                  image_cfg: float) -> None:
+    """In-place CFG combine + Euler update of the fp32 state x (and its bf16 copy)."""
+    _check_bf16(x_bf16, v)
+    if x_f32.dtype != torch.float32 or not x_f32.is_contiguous() or not v.is_contiguous():
+        raise TypeError("x_f32 must be a contiguous fp32 tensor and v contiguous bf16")
+    lib = _lib.load()
+    B, C = x_f32.shape
+    _lib.check(lib.mb_rf_euler_step(x_f32.data_ptr(), x_bf16.data_ptr(), v.data_ptr(), B, C, float(dt),
+                                    float(text_cfg), float(image_cfg), _stream()), "mb_rf_euler_step")

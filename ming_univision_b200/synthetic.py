@@ -137,3 +137,60 @@ def save_config(config: dict, path: str) -> None:
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
         json.dump(config, f, indent=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rectified-flow head (mingunivision/diff_loss_rf_swiglu.py); defaults of setup_vishead_diffloss
+# (modeling_bailing_moe.py:1559-1584): width 3072, depth 12, mlp_mult 4, 16 steps, latent 32 channels
+# ---------------------------------------------------------------------------------------------------------------
+RF_CONFIG = {"target_channels": 32, "z_channels": 3072, "width": 3072, "depth": 12, "mlp_mult": 4,
+             "num_sampling_steps": 16}
+RF_TINY_CONFIG = {"target_channels": 32, "z_channels": 128, "width": 128, "depth": 2, "mlp_mult": 4,
+                  "num_sampling_steps": 4}
+
+
+def rf_param_shapes(cfg: dict) -> dict[str, tuple]:
+    """State-dict schema of RectifiedFlowLoss (keys below `diffloss.`; diff_loss_rf_swiglu.py:295-340)."""
+    W, C, Z = cfg["width"], cfg["target_channels"], cfg["z_channels"]
+    hidden = (int(int(W * cfg["mlp_mult"]) * 2 / 3) + 7) // 8 * 8  # SwiGLUFFNFused, :66
+    shapes: dict[str, tuple] = {}
+
+    def linear(name, out_f, in_f):
+        shapes[name + ".weight"] = (out_f, in_f)
+        shapes[name + ".bias"] = (out_f,)
+
+    linear("net.time_embed.mlp.0", W, 256)
+    linear("net.time_embed.mlp.2", W, W)
+    linear("net.cond_embed", W, Z)
+    linear("net.input_proj", W, C)
+    for i in range(cfg["depth"]):
+        p = f"net.res_blocks.{i}"
+        shapes[p + ".in_ln.weight"] = (W,)
+        shapes[p + ".in_ln.bias"] = (W,)
+        linear(p + ".mlp.w12", 2 * hidden, W)
+        linear(p + ".mlp.w3", W, hidden)
+        linear(p + ".adaLN_modulation.1", 3 * W, W)
+    linear("net.final_layer.adaLN_modulation.1", 2 * W, W)
+    linear("net.final_layer.linear", C, W)
+    return shapes
+
+
+def rf_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> dict[str, torch.Tensor]:
+    """Seeded weights.  The reference zero-initialises the adaLN and output layers (diff_loss_rf_swiglu.py:353-361),
+    which would make v == 0 and every test vacuous, so ALL layers are randomised: Linear ~ N(0, 1/fan_in) (adaLN
+    modulation scaled by 0.5, output layer by 2 so |v| ~ 1), biases ~ N(0, 0.1^2), in_ln gamma ~ 1 + N(0, 0.1^2)."""
+    sd = {}
+    for key, shape in rf_param_shapes(cfg).items():
+        if ".in_ln." in key:
+            t = _normal(seed, "rf." + key, shape, 0.1, 1.0 if key.endswith(".weight") else 0.0)
+        elif key.endswith(".bias"):
+            t = _normal(seed, "rf." + key, shape, 0.1)
+        else:
+            std = 1.0 / math.sqrt(shape[1])
+            if "adaLN_modulation" in key:
+                std *= 0.5
+            if key.startswith("net.final_layer.linear"):
+                std *= 2.0
+            t = _normal(seed, "rf." + key, shape, std)
+        sd[key] = t.to(dtype)
+    return sd

@@ -37,6 +37,5 @@ def frechet_distance(img_a: torch.Tensor, img_b: torch.Tensor) -> float:
     fa, fb = _random_features(img_a), _random_features(img_b)
     mu_a, mu_b = fa.mean(0), fb.mean(0)
     ca, cb = np.cov(fa, rowvar=False), np.cov(fb, rowvar=False)
-    covmean, _ = linalg.sqrtm(ca.dot(cb), disp=False)
-    covmean = covmean.real
+    covmean = np.asarray(linalg.sqrtm(ca.dot(cb))).real
     return float(((mu_a - mu_b) ** 2).sum() + np.trace(ca) + np.trace(cb) - 2 * np.trace(covmean))

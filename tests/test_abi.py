@@ -73,3 +73,32 @@ def test_reference_keys_live():
     ref_sd = ref.state_dict()
     assert set(ref_sd) == set(shapes)
     assert all(tuple(ref_sd[k].shape) == tuple(shapes[k]) for k in shapes)
+
+
+def test_rf_state_dict_schema_live():
+    """RectifiedFlowLoss keys/shapes == the reference module's (and == the synthetic factory's)."""
+    from ming_univision_b200.diff_loss_rf_swiglu import RectifiedFlowLoss
+    from oracle import ref_shims
+
+    cfg = synthetic.RF_TINY_CONFIG
+    m = RectifiedFlowLoss(cfg["target_channels"], cfg["z_channels"], cfg["depth"], cfg["width"],
+                          str(cfg["num_sampling_steps"]), mlp_mult=cfg["mlp_mult"])
+    shapes = synthetic.rf_param_shapes(cfg)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes) and all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.sample(torch.zeros(2, cfg["z_channels"]), text_cfg=3.0)
+    if not ref_shims.reference_available():
+        return
+    ref_shims.install()
+    import contextlib
+    import io
+
+    os.environ["XFORMERS_DISABLED"] = "1"
+    from diff_loss_rf_swiglu import RectifiedFlowLoss as RefRF
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefRF(cfg["target_channels"], cfg["z_channels"], cfg["depth"], cfg["width"],
+                    str(cfg["num_sampling_steps"]), mlp_mult=cfg["mlp_mult"])
+    rsd = ref.state_dict()
+    assert set(rsd) == set(shapes) and all(tuple(rsd[k].shape) == tuple(shapes[k]) for k in shapes)

@@ -69,3 +69,42 @@ def test_param_count_matches_survey():
     shapes = synthetic.mingtok_param_shapes(synthetic.MINGTOK_CONFIG)
     n = sum(int(np.prod(s)) for s in shapes.values())
     assert abs(n - 697.7e6) < 0.1e6, n
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rectified-flow head
+# ---------------------------------------------------------------------------------------------------------------
+def test_rf_tiny_matches_reference():
+    from oracle import rf_oracle as R
+
+    g = _load("rf_tiny.npz")
+    cfg = synthetic.RF_TINY_CONFIG
+    sd = synthetic.rf_state_dict(cfg, int(g["seed"]))
+    with torch.no_grad():
+        v = R.net_forward(sd, torch.from_numpy(g["net_x"]), torch.from_numpy(g["net_t"]), torch.from_numpy(g["net_c"]))
+    assert torch.allclose(v, torch.from_numpy(g["net_v"]), atol=2e-5, rtol=1e-5)
+    for B in (1, 2, 3):
+        tc, ic, temp = (float(x) for x in g[f"B{B}_cfg"])
+        with torch.no_grad():
+            x = R.sample(sd, torch.from_numpy(g[f"B{B}_z"]), torch.from_numpy(g[f"B{B}_noise"]),
+                         cfg["num_sampling_steps"], temp, tc, ic)
+        ref = torch.from_numpy(g[f"B{B}_x"])
+        assert torch.allclose(x, ref, atol=5e-5, rtol=1e-5), f"B={B}: {(x - ref).abs().max()}"
+
+
+def test_rf_full_matches_reference():
+    """Default-size head (width 3072, depth 12, mult 4, 16 steps; 1.285 B parameters) against the reference run."""
+    from oracle import rf_oracle as R
+
+    g = _load("rf_full.npz")
+    cfg = synthetic.RF_CONFIG
+    shapes = synthetic.rf_param_shapes(cfg)
+    assert abs(sum(int(np.prod(s)) for s in shapes.values()) - 1.285e9) < 2e6
+    sd = synthetic.rf_state_dict(cfg, int(g["seed"]))
+    torch.set_num_threads(os.cpu_count())
+    B = 2
+    tc, ic, temp = (float(x) for x in g[f"B{B}_cfg"])
+    with torch.no_grad():
+        x = R.sample(sd, torch.from_numpy(g[f"B{B}_z"]), torch.from_numpy(g[f"B{B}_noise"]), 16, temp, tc, ic)
+    ref = torch.from_numpy(g[f"B{B}_x"])
+    assert torch.allclose(x, ref, atol=2e-3, rtol=1e-3), f"{(x - ref).abs().max()}"
