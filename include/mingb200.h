@@ -88,7 +88,8 @@ int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const v
 
 /* Tuning / test hook: pin the GEMM tile shape instead of the built-in heuristic.  cta_group: 1 = one CTA per
  * 128 x bn tile, 2 = CTA pair (tcgen05 cta_group::2) per 256 x bn tile, 0 = automatic; bn: 128, 256 or 0 = automatic.
- * Process-wide; also settable through the MB_GEMM_CG / MB_GEMM_BN environment variables. */
+ * Adding 16 to cta_group forces the direct register-store epilogue instead of the staged TMA-store epilogue.
+ * Process-wide; also settable through the MB_GEMM_CG / MB_GEMM_BN / MB_GEMM_NO_TMA_EPI environment variables. */
 int mb_gemm_force_tile(int cta_group, int bn);
 
 /* Weight pre-pack for MB_EPI_SWIGLU: src is the reference's w12 [2*H, K] (x1 rows then x2 rows, swiglu_ffn.py:32),

@@ -41,6 +41,7 @@ struct GemmParams {
   int res_row_mod;
   int out_row_group;
   int out_row_pad;
+  int tma_epi;  // 1: epilogue goes through shared-memory staging + TMA store (and TMA load of the residual)
 };
 
 template <int BN, int CG>
@@ -49,10 +50,12 @@ struct GemmCfg {
   static constexpr int kBRows = BN / CG;                  // this CTA's share of the W tile
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiStageBytes = kNumEpiWarps * 4096;  // one 32-row x 64-col bf16 box per epilogue warp
   static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTileM = kBM * CG;
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // Converts 32 fp32 values (one row segment) to bf16 and stores them; handles the N tail.
@@ -96,9 +99,47 @@ __device__ __forceinline__ void load_bias32(const __nv_bfloat16* bias, int col0,
   }
 }
 
+// Accumulator chunk (this warp's 32 rows x 32 columns starting at tile column tc) -> bias / activation, fp32 in v[].
+// For MB_EPI_RESIDUAL the residual is added by the caller (it arrives either by TMA or by direct loads).
+template <int BN, int EPI>
+__device__ __forceinline__ void epi_math(const GemmParams& p, uint32_t t_row, int tc, int n_tile, int out_col,
+                                         int ncols_valid, float (&v)[32]) {
+  if constexpr (EPI == MB_EPI_SWIGLU) {
+    uint32_t g[32], u[32];
+    tmem_ld_32x32b_x32(t_row + tc, g);
+    tmem_ld_32x32b_x32(t_row + BN / 2 + tc, u);
+    tmem_ld_wait();
+    {
+      float bg[32];
+      load_bias32(p.bias, n_tile * BN + tc, 32, bg);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
+    }
+    {
+      float bu[32];
+      load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
+    }
+  } else {
+    uint32_t a[32];
+    tmem_ld_32x32b_x32(t_row + tc, a);
+    tmem_ld_wait();
+    float b[32];
+    load_bias32(p.bias, out_col, ncols_valid, b);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
+    if constexpr (EPI == MB_EPI_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
+    }
+  }
+}
+
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN, CG>;
   constexpr int kStages = Cfg::kStages;
@@ -113,12 +154,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;  // [kNumEpiWarps][32 rows][128 B], 128B-swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiStageBytes);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* epi_bar = bars + 2 * kStages + 4;   // [kNumEpiWarps] residual box landed (TMA -> epilogue warp)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kNumEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +181,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kNumEpiWarps * CG);  // CG = 2: the leader's barrier collects both CTAs' epilogues
+    }
+    for (int w = 0; w < kNumEpiWarps; ++w) mbar_init(&epi_bar[w], 1);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&tmap_out);
+      if (EPI == MB_EPI_RESIDUAL) tma_prefetch_desc(&tmap_res);
     }
     fence_mbar_init();
   }
@@ -224,6 +272,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int n_out_total = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t epi_phase = 0;
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
@@ -236,41 +285,69 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int64_t res_row = (p.res_row_mod > 0) ? (row % p.res_row_mod) : row;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
 
+      if (p.tma_epi) {
+        // ---- staged path: registers -> 128B-swizzled smem box (32 rows x 64 cols) -> one TMA store per box; the
+        // residual box arrives by TMA as well.  Every global access of the epilogue is a full-line bulk transfer
+        // (a thread-per-row register store touches 32 different lines per instruction and was the limiter at K<=1024).
+        uint8_t* stage_buf = smem_epi + ew * 4096;
+        const int row0 = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + quad * 32;
 #pragma unroll 1
-      for (int c = 0; c < kColsPerWarp; c += 32) {
-        const int tc = half * kColsPerWarp + c;       // column inside the output tile
-        const int out_col = n_tile * kOutTileN + tc;  // global output column
-        const int ncols_valid = n_out_total - out_col;
-        float v[32];
-        if constexpr (EPI == MB_EPI_SWIGLU) {
-          uint32_t g[32], u[32];
-          tmem_ld_32x32b_x32(t_row + tc, g);
-          tmem_ld_32x32b_x32(t_row + BN / 2 + tc, u);
-          tmem_ld_wait();
-          {
-            float bg[32];
-            load_bias32(p.bias, n_tile * BN + tc, 32, bg);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
+        for (int bx = 0; bx < kColsPerWarp / 64; ++bx) {
+          const int box_tc = half * kColsPerWarp + bx * 64;   // first column of the box inside the output tile
+          const int box_col = n_tile * kOutTileN + box_tc;    // global output column
+          if (box_col >= n_out_total || row0 >= p.M) continue;  // warp-uniform
+          if (lane == 0) tma_store_wait_read<0>();            // previous box fully read out of the staging buffer
+          __syncwarp();
+          if constexpr (EPI == MB_EPI_RESIDUAL) {
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&epi_bar[ew], 4096);
+              tma_load_2d(&tmap_res, &epi_bar[ew], stage_buf, box_col, row0);
+            }
           }
-          {
-            float bu[32];
-            load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
+          for (int cc = 0; cc < 2; ++cc) {
+            const int tc = box_tc + cc * 32;
+            float v[32];
+            epi_math<BN, EPI>(p, t_row, tc, n_tile, n_tile * kOutTileN + tc, n_out_total - (n_tile * kOutTileN + tc), v);
+            if constexpr (EPI == MB_EPI_RESIDUAL) {
+              if (cc == 0) mbar_wait(&epi_bar[ew], epi_phase);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4));
+                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
+                             f3 = unpack_bf16x2(q.w);
+                v[8 * j + 0] = bf16_round(v[8 * j + 0]) + f0.x; v[8 * j + 1] = bf16_round(v[8 * j + 1]) + f0.y;
+                v[8 * j + 2] = bf16_round(v[8 * j + 2]) + f1.x; v[8 * j + 3] = bf16_round(v[8 * j + 3]) + f1.y;
+                v[8 * j + 4] = bf16_round(v[8 * j + 4]) + f2.x; v[8 * j + 5] = bf16_round(v[8 * j + 5]) + f2.y;
+                v[8 * j + 6] = bf16_round(v[8 * j + 6]) + f3.x; v[8 * j + 7] = bf16_round(v[8 * j + 7]) + f3.y;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 q;
+              q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+              q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+              q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+              q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+              *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4)) = q;
+            }
           }
-        } else {
-          uint32_t a[32];
-          tmem_ld_32x32b_x32(t_row + tc, a);
-          tmem_ld_wait();
-          float b[32];
-          load_bias32(p.bias, out_col, ncols_valid, b);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
-          if constexpr (EPI == MB_EPI_GELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
+          if constexpr (EPI == MB_EPI_RESIDUAL) epi_phase ^= 1;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_out, stage_buf, box_col, row0);
+            tma_store_commit();
           }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < kColsPerWarp; c += 32) {
+          const int tc = half * kColsPerWarp + c;       // column inside the output tile
+          const int out_col = n_tile * kOutTileN + tc;  // global output column
+          const int ncols_valid = n_out_total - out_col;
+          float v[32];
+          epi_math<BN, EPI>(p, t_row, tc, n_tile, out_col, ncols_valid, v);
           if constexpr (EPI == MB_EPI_RESIDUAL) {
             if (row_ok && ncols_valid > 0) {
               const __nv_bfloat16* rp = p.residual + res_row * p.ldr + out_col;
@@ -293,8 +370,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
+          if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
         }
-        if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
       }
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
       tc_fence_before();
@@ -305,6 +382,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_epi && lane == 0) tma_store_wait_all();  // bulk stores still read our shared memory until they complete
+    (void)epi_phase;
   }
 
   tc_fence_before();
@@ -316,8 +395,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 template <int BN, int EPI, int CG>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int grid,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                       const GemmParams& p, int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, CG>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -337,7 +416,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, CG>, ta, tb, p));
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, CG>, ta, tb, to, tr, p));
   return MB_OK;
 }
 
@@ -346,6 +425,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 struct TileChoice { int cg, bn; };
 static int g_force_cg = getenv("MB_GEMM_CG") ? atoi(getenv("MB_GEMM_CG")) : 0;
 static int g_force_bn = getenv("MB_GEMM_BN") ? atoi(getenv("MB_GEMM_BN")) : 0;
+static int g_no_tma_epi = getenv("MB_GEMM_NO_TMA_EPI") ? atoi(getenv("MB_GEMM_NO_TMA_EPI")) : 0;
 static TileChoice choose_tile(int M, int N, int sms, bool swiglu) {
   const int force_cg = g_force_cg, force_bn = g_force_bn;
   // Measured on B200 (tools/bench_ops.py, gpurun_out/bench_ops2.log): every shape is bound by L2 -> SM operand
@@ -374,10 +454,11 @@ static TileChoice choose_tile(int M, int N, int sms, bool swiglu) {
 using namespace mb;
 
 extern "C" int mb_gemm_force_tile(int cta_group, int bn) {
-  MB_CHECK_ARG((cta_group == 0 || cta_group == 1 || cta_group == 2) && (bn == 0 || bn == 128 || bn == 256), MB_ERR_SHAPE,
+  MB_CHECK_ARG(((cta_group & 3) <= 2) && (cta_group & ~0x13) == 0 && (bn == 0 || bn == 128 || bn == 256), MB_ERR_SHAPE,
                "mb_gemm_force_tile: cta_group in {0,1,2}, bn in {0,128,256}");
-  mb::g_force_cg = cta_group;
+  mb::g_force_cg = cta_group & 3;
   mb::g_force_bn = bn;
+  mb::g_no_tma_epi = (cta_group >> 4) & 1;  // bit 4: force the direct-store epilogue (tests / A-B measurements)
   return MB_OK;
 }
 
@@ -420,20 +501,32 @@ extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.out_row_group = out_row_group;
   p.out_row_pad = out_row_pad;
 
+  // Staged TMA epilogue whenever the output is a plain dense matrix; the remapped / row-modulo cases (patch-embed)
+  // and very narrow outputs keep the direct register stores.
+  const int n_out = (epi == MB_EPI_SWIGLU) ? N / 2 : N;
+  const bool tma_epi = !g_no_tma_epi && out_row_group == 0 && res_row_mod == 0 && n_out >= 64 &&
+                       (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
+  p.tma_epi = tma_epi ? 1 : 0;
+  CUtensorMap to = ta, tr = ta;  // valid placeholders when unused
+  if (tma_epi) {
+    if (!make_tmap_2d_bf16(&to, out, n_out, M, ldo, 64, 32)) return MB_ERR_CUDA;
+    if (epi == MB_EPI_RESIDUAL && !make_tmap_2d_bf16(&tr, residual, n_out, M, ldr, 64, 32)) return MB_ERR_CUDA;
+  }
+
   const int tiles = ((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
   const int workers = sms / cg;
   const int grid = (tiles < workers ? tiles : workers) * cg;
 
 #define MB_DISPATCH_EPI(BN_, CG_)                                                                  \
   switch (epi) {                                                                                   \
-    case MB_EPI_BIAS: return launch_gemm<BN_, MB_EPI_BIAS, CG_>(ta, tb, p, grid, stream);          \
-    case MB_EPI_GELU: return launch_gemm<BN_, MB_EPI_GELU, CG_>(ta, tb, p, grid, stream);          \
-    case MB_EPI_RESIDUAL: return launch_gemm<BN_, MB_EPI_RESIDUAL, CG_>(ta, tb, p, grid, stream);  \
+    case MB_EPI_BIAS: return launch_gemm<BN_, MB_EPI_BIAS, CG_>(ta, tb, to, tr, p, grid, stream);          \
+    case MB_EPI_GELU: return launch_gemm<BN_, MB_EPI_GELU, CG_>(ta, tb, to, tr, p, grid, stream);          \
+    case MB_EPI_RESIDUAL: return launch_gemm<BN_, MB_EPI_RESIDUAL, CG_>(ta, tb, to, tr, p, grid, stream);  \
     default: break;                                                                                \
   }
   if (epi == MB_EPI_SWIGLU) {
-    if (cg == 2) return launch_gemm<256, MB_EPI_SWIGLU, 2>(ta, tb, p, grid, stream);
-    return launch_gemm<256, MB_EPI_SWIGLU, 1>(ta, tb, p, grid, stream);
+    if (cg == 2) return launch_gemm<256, MB_EPI_SWIGLU, 2>(ta, tb, to, tr, p, grid, stream);
+    return launch_gemm<256, MB_EPI_SWIGLU, 1>(ta, tb, to, tr, p, grid, stream);
   }
   if (cg == 2 && bn == 256) { MB_DISPATCH_EPI(256, 2) }
   else if (cg == 2) { MB_DISPATCH_EPI(128, 2) }

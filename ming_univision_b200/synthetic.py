@@ -194,3 +194,104 @@ def rf_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> dict[str, to
             t = _normal(seed, "rf." + key, shape, std)
         sd[key] = t.to(dtype)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bailing-MoE LLM (mingunivision/config.json:11-119 llm_config; rope_scaling=None -> 1-D legacy rotary)
+# ---------------------------------------------------------------------------------------------------------------
+LLM_CONFIG = dict(vocab_size=126464, hidden_size=2048, intermediate_size=5632, num_hidden_layers=28,
+                  num_attention_heads=16, num_key_value_heads=4, head_dim=128, hidden_act="silu", use_qkv_bias=False,
+                  use_bias=False, rms_norm_eps=1e-5, max_position_embeddings=32768, rope_theta=600000,
+                  rope_scaling=None, num_experts=64, num_shared_experts=2, num_experts_per_tok=6, norm_topk_prob=True,
+                  moe_intermediate_size=1408, first_k_dense_replace=0, multi_gate=True, num_image_tokens_for_gen=256,
+                  image_patch_token=126346, image_start_token=126347, pad_token_id=126081, embedding_dropout=0.0,
+                  attention_dropout=0.0, output_dropout=0.0)
+VISHEAD_CONFIG = dict(diffloss_w=3072, diffloss_d=12, num_sampling_steps="16", gen_method="flow_matching_swiglu-4",
+                      hidden_size=2048, vis_head_arch="linear2-norm", image_emb_dim_for_gen=32)
+
+LLM_TINY_CONFIG = dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                       num_attention_heads=4, num_key_value_heads=2, head_dim=32, hidden_act="silu",
+                       use_qkv_bias=False, use_bias=False, rms_norm_eps=1e-5, max_position_embeddings=4096,
+                       rope_theta=600000, rope_scaling=None, num_experts=8, num_shared_experts=1,
+                       num_experts_per_tok=2, norm_topk_prob=True, moe_intermediate_size=64, first_k_dense_replace=0,
+                       multi_gate=True, num_image_tokens_for_gen=4, image_patch_token=500, image_start_token=501,
+                       pad_token_id=0, embedding_dropout=0.0, attention_dropout=0.0, output_dropout=0.0)
+VISHEAD_TINY_CONFIG = dict(diffloss_w=128, diffloss_d=2, num_sampling_steps="4", gen_method="flow_matching_swiglu-4",
+                           hidden_size=128, vis_head_arch="linear2-norm", image_emb_dim_for_gen=32)
+
+
+def rf_config_from_vishead(vh: dict) -> dict:
+    return {"target_channels": vh["image_emb_dim_for_gen"], "z_channels": vh["diffloss_w"], "width": vh["diffloss_w"],
+            "depth": vh["diffloss_d"], "mlp_mult": int(vh["gen_method"].split("-")[1]),
+            "num_sampling_steps": int(vh["num_sampling_steps"])}
+
+
+def llm_param_shapes(cfg: dict, vh: dict | None = None, feature_dim: int | None = None) -> dict[str, tuple]:
+    """State-dict schema of BailingMoeForCausalLM (+ vis_head, diffloss when `vh`; + the wrapper's linear_proj when
+    `feature_dim`) — SURVEY.md §3.5; modeling_bailing_moe.py:479-484, 505-520, 543-552, 680-686, 1359-1389, 1543-1584."""
+    D, H, Hkv, hd = cfg["hidden_size"], cfg["num_attention_heads"], cfg["num_key_value_heads"], cfg["head_dim"]
+    E, I = cfg["num_experts"], cfg["moe_intermediate_size"]
+    shapes: dict[str, tuple] = {"model.word_embeddings.weight": (cfg["vocab_size"], D)}
+    for l in range(cfg["num_hidden_layers"]):
+        p = f"model.layers.{l}"
+        shapes[p + ".attention.query_key_value.weight"] = ((H + 2 * Hkv) * hd, D)
+        shapes[p + ".attention.dense.weight"] = (D, H * hd)
+        shapes[p + ".input_layernorm.weight"] = (D,)
+        shapes[p + ".post_attention_layernorm.weight"] = (D,)
+        for gname in ("gate", "image_gate", "audio_gate") if cfg.get("multi_gate") else ("gate",):
+            shapes[f"{p}.mlp.{gname}.weight"] = (E, D)
+        for e in range(E):
+            shapes[f"{p}.mlp.experts.{e}.gate_proj.weight"] = (I, D)
+            shapes[f"{p}.mlp.experts.{e}.up_proj.weight"] = (I, D)
+            shapes[f"{p}.mlp.experts.{e}.down_proj.weight"] = (D, I)
+        if cfg.get("num_shared_experts"):
+            Is = I * cfg["num_shared_experts"]
+            shapes[p + ".mlp.shared_experts.gate_proj.weight"] = (Is, D)
+            shapes[p + ".mlp.shared_experts.up_proj.weight"] = (Is, D)
+            shapes[p + ".mlp.shared_experts.down_proj.weight"] = (D, Is)
+    shapes["model.norm.weight"] = (D,)
+    shapes["lm_head.weight"] = (cfg["vocab_size"], D)
+    if vh is not None:
+        Z = vh["diffloss_w"]
+        shapes["vis_head.0.weight"] = (Z, D)
+        shapes["vis_head.0.bias"] = (Z,)
+        shapes["vis_head.1.weight"] = (Z,)
+        shapes["vis_head.1.bias"] = (Z,)
+        for k, v in rf_param_shapes(rf_config_from_vishead(vh)).items():
+            shapes["diffloss." + k] = v
+    if feature_dim is not None:
+        shapes["linear_proj.0.weight"] = (D, feature_dim)
+        shapes["linear_proj.0.bias"] = (D,)
+        shapes["linear_proj.2.weight"] = (D, D)
+        shapes["linear_proj.2.bias"] = (D,)
+    return shapes
+
+
+def llm_tensor(key: str, shape: tuple, seed: int = 0, dtype=torch.float32, device="cpu") -> torch.Tensor:
+    """One seeded tensor of the LLM schema.  Linear ~ N(0, 1/fan_in); router gates ~ N(0, (3/sqrt(D))^2) so top-k
+    margins are wide (no ties in bf16); norm weights ~ 1 + N(0, 0.1^2); embeddings ~ N(0, 1)."""
+    if key.startswith("diffloss."):
+        raise KeyError("use rf_state_dict for the diffloss.* keys")
+    if "layernorm" in key or key.endswith("norm.weight") or key.startswith("vis_head.1"):
+        return _normal(seed, "llm." + key, shape, 0.1, 1.0 if key.endswith(".weight") else 0.0).to(dtype)
+    if key.endswith(".bias"):
+        return _normal(seed, "llm." + key, shape, 0.1).to(dtype)
+    if "word_embeddings" in key:
+        return _normal(seed, "llm." + key, shape, 1.0).to(dtype)
+    std = 1.0 / math.sqrt(shape[-1])
+    if "gate.weight" in key and "experts" not in key:
+        std *= 3.0
+    return _normal(seed, "llm." + key, shape, std).to(dtype)
+
+
+def llm_state_dict(cfg: dict, vh: dict | None = None, feature_dim: int | None = None, seed: int = 0,
+                   dtype=torch.float32) -> dict[str, torch.Tensor]:
+    sd = {}
+    for key, shape in llm_param_shapes(cfg, vh, feature_dim).items():
+        if key.startswith("diffloss."):
+            continue
+        sd[key] = llm_tensor(key, shape, seed, dtype)
+    if vh is not None:
+        for k, v in rf_state_dict(rf_config_from_vishead(vh), seed, dtype).items():
+            sd["diffloss." + k] = v
+    return sd

@@ -28,13 +28,14 @@ GEMM_SHAPES = [
 ]
 
 
-@pytest.fixture(params=["auto", "pair256", "pair128", "single256", "single128"])
+@pytest.fixture(params=["auto", "pair256", "pair128", "single256", "single128", "pair256-direct", "single128-direct"])
 def tile(request):
-    """Pins the GEMM tile shape (CTA pair = tcgen05 cta_group::2) so every kernel variant sees every shape."""
+    """Pins the GEMM tile shape (CTA pair = tcgen05 cta_group::2) and the epilogue flavour (staged TMA store vs direct
+    register stores) so every kernel variant sees every shape."""
     from ming_univision_b200 import _lib
 
     cg, bn = {"auto": (0, 0), "pair256": (2, 256), "pair128": (2, 128), "single256": (1, 256),
-              "single128": (1, 128)}[request.param]
+              "single128": (1, 128), "pair256-direct": (2 + 16, 256), "single128-direct": (1 + 16, 128)}[request.param]
     _lib.check(_lib.load().mb_gemm_force_tile(cg, bn), "mb_gemm_force_tile")
     yield request.param
     _lib.load().mb_gemm_force_tile(0, 0)
@@ -69,6 +70,25 @@ def test_gemm_epilogues(cuda_device, tile, M, N, K, epi):
     tol = 2.0 ** -7 * ref.abs() + 2.0 ** -7 * pre.abs() + 1e-3
     assert (err <= tol).all(), f"max err {err.max().item()} rel {_rel_err(out, ref)}"
     assert _rel_err(out, ref) < 4e-3
+
+
+@pytest.mark.parametrize("direct", [False, True])
+def test_gemm_inplace_residual(cuda_device, direct):
+    """out aliases the residual (how the transformer blocks update their residual stream)."""
+    from ming_univision_b200 import _lib, ops
+
+    _lib.load().mb_gemm_force_tile(16 if direct else 0, 0)
+    M, N, K = 4160, 1024, 1024
+    x = _rand((M, K), cuda_device, 1.0, 1)
+    w = _rand((N, K), cuda_device, 1.0 / math.sqrt(K), 2)
+    b = _rand((N,), cuda_device, 0.5, 3)
+    r = _rand((M, N), cuda_device, 1.0, 4)
+    ref = (x.float() @ w.float().t() + b.float()).to(BF16).float() + r.float()
+    stream = r.clone()
+    ops.linear(x, w, b, epi=ops.EPI_RESIDUAL, residual=stream, out=stream)
+    _lib.load().mb_gemm_force_tile(0, 0)
+    assert _rel_err(stream, ref) < 4e-3
+    assert ((stream.float() - ref).abs() <= 2.0 ** -6 * ref.abs() + 2e-2).all()
 
 
 def test_gemm_no_bias_and_strided(cuda_device):

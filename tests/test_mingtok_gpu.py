@@ -93,7 +93,6 @@ def test_full_size_recon_parity(full, cuda_device):
     cfg, sd, model = full
     B = 4
     img = synthetic.synthetic_images(B, 256, seed=1234)
-    torch.set_num_threads(os.cpu_count())
     with torch.no_grad():
         ref = O.mingtok_forward(sd, img, cfg)
         ref_recon = O.pixel_decoder_forward(sd, ref["x_norm_patchtokens"], cfg["semantic_decoder"],

@@ -46,7 +46,6 @@ def test_full_size_mingtok_matches_reference_samples():
     cfg = synthetic.MINGTOK_CONFIG
     sd = synthetic.mingtok_state_dict(cfg, int(g["seed"]))
     img = synthetic.synthetic_images(1, 256, seed=int(g["img_seed"]))
-    torch.set_num_threads(os.cpu_count())
     with torch.no_grad():
         out = O.mingtok_forward(sd, img, cfg)
         recon = O.pixel_decoder_forward(sd, out["x_norm_patchtokens"], cfg["semantic_decoder"], cfg["pixel_decoder"])
@@ -101,10 +100,82 @@ def test_rf_full_matches_reference():
     shapes = synthetic.rf_param_shapes(cfg)
     assert abs(sum(int(np.prod(s)) for s in shapes.values()) - 1.285e9) < 2e6
     sd = synthetic.rf_state_dict(cfg, int(g["seed"]))
-    torch.set_num_threads(os.cpu_count())
     B = 2
     tc, ic, temp = (float(x) for x in g[f"B{B}_cfg"])
     with torch.no_grad():
         x = R.sample(sd, torch.from_numpy(g[f"B{B}_z"]), torch.from_numpy(g[f"B{B}_noise"]), 16, temp, tc, ic)
     ref = torch.from_numpy(g[f"B{B}_x"])
     assert torch.allclose(x, ref, atol=2e-3, rtol=1e-3), f"{(x - ref).abs().max()}"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bailing-MoE AR path
+# ---------------------------------------------------------------------------------------------------------------
+def _llm_fixture():
+    from oracle import bailing_oracle as L
+
+    g = _load("llm_tiny.npz")
+    cfg, vh = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG
+    tok_cfg = synthetic.MINGTOK_TINY_CONFIG
+    sd = synthetic.llm_state_dict(cfg, vh, feature_dim=tok_cfg["semantic_decoder"]["embed_dim"], seed=int(g["seed"]))
+    rf_sd = {k[len("diffloss."):]: v for k, v in sd.items() if k.startswith("diffloss.")}
+    return L, g, cfg, vh, tok_cfg, sd, rf_sd
+
+
+def test_llm_prefill_and_cfg_step_match_reference():
+    L, g, cfg, vh, tok_cfg, sd, rf_sd = _llm_fixture()
+    ids = torch.from_numpy(g["prefill_ids"])
+    emb = sd["model.word_embeddings.weight"][ids]
+    caches = L.new_caches(cfg)
+    with torch.no_grad():
+        h = L.model_forward(sd, cfg, emb, torch.ones(1, ids.shape[1], dtype=torch.long), None, caches,
+                            image_mask=torch.from_numpy(g["prefill_image_mask"]))
+        logits = L.lm_logits(sd, h[:, -1])
+    assert torch.allclose(h, torch.from_numpy(g["prefill_hidden"]), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(logits, torch.from_numpy(g["prefill_logits_last"]), atol=5e-5, rtol=1e-5)
+    assert torch.allclose(caches[0]["k"], torch.from_numpy(g["prefill_k0"]), atol=1e-5)
+    assert torch.allclose(caches[1]["v"], torch.from_numpy(g["prefill_v1"]), atol=1e-5)
+    # cached decode step, 2 CFG rows, 2-D padding mask, per-row positions
+    for c in caches:
+        c["k"], c["v"] = c["k"].repeat(2, 1, 1, 1), c["v"].repeat(2, 1, 1, 1)
+    with torch.no_grad():
+        h2 = L.model_forward(sd, cfg, torch.from_numpy(g["step_x"]), torch.from_numpy(g["step_mask"]),
+                             torch.from_numpy(g["step_pos"]), caches)
+        z = L.vis_head(sd, h2[:, -1:])
+    assert torch.allclose(h2, torch.from_numpy(g["step_hidden"]), atol=2e-5, rtol=1e-5)
+    assert torch.allclose(z, torch.from_numpy(g["step_z"]), atol=5e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["t2i", "edit"])
+def test_generate_image_matches_reference(name):
+    """oracle generate_image (LLM step + RF sampler + MingTok cached decode + linear_proj + pixel decoder) against the
+    reference's own generate_image run end to end (B = 2 and B = 3 CFG rows)."""
+    L, g, cfg, vh, tok_cfg, sd, rf_sd = _llm_fixture()
+    tok_sd = synthetic.mingtok_state_dict(tok_cfg, 0)
+    ids = torch.from_numpy(g["prefill_ids"])
+    emb = sd["model.word_embeddings.weight"][ids]
+    caches = L.new_caches(cfg)
+    S = ids.shape[1]
+    with torch.no_grad():
+        L.model_forward(sd, cfg, emb, torch.ones(1, S, dtype=torch.long), None, caches)
+    start = sd["model.word_embeddings.weight"][torch.tensor([[cfg["image_start_token"]]])]
+
+    def latent_to_sem(latent, state):
+        state = O.new_decoder_caches(tok_sd) if state is None else state
+        return O.mingtok_forward_feature_decoder(tok_sd, latent, tok_cfg, state), state
+
+    noises = [torch.from_numpy(n) for n in g[f"{name}_noises"]]
+    tm = torch.from_numpy(g[f"{name}_text_uncond"])
+    with torch.no_grad():
+        feats, lats, fmask = L.generate_image(
+            sd, cfg, rf_sd, int(vh["num_sampling_steps"]), start, caches, torch.ones(1, S + 1, dtype=torch.long),
+            torch.from_numpy(g[f"{name}_uncond"]), tm, latent_to_sem, lambda f: L.linear_proj(sd, f), noises,
+            temperature=0.9)
+        img = O.pixel_decoder_forward(tok_sd, torch.cat(feats, dim=1), tok_cfg["semantic_decoder"],
+                                      tok_cfg["pixel_decoder"])
+    assert torch.equal(fmask, torch.from_numpy(g[f"{name}_final_mask"]))
+    assert torch.allclose(torch.cat(lats, dim=1), torch.from_numpy(g[f"{name}_latents"]), atol=2e-4, rtol=1e-4)
+    assert torch.allclose(torch.cat(feats, dim=1), torch.from_numpy(g[f"{name}_feats"]), atol=5e-4, rtol=1e-4)
+    assert torch.allclose(img, torch.from_numpy(g[f"{name}_image"]), atol=1e-3, rtol=1e-3)
+    assert caches[0]["k"].shape[0] == int(g[f"{name}_cache_batch"]) == 1
+    assert caches[0]["k"].shape[2] == int(g[f"{name}_cache_len"])
