@@ -118,6 +118,14 @@ int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const void* beta
  * ------------------------------------------------------------------------------------------------------------- */
 int mb_attn_hd64(const void* qkv, void* out, int B, int S, int H, float scale, int causal, void* stream);
 
+/* General strided form (head_dim 64 or 128, GQA when Hq > Hkv): element strides (batch, token, head) per tensor;
+ * causal masks are bottom-right aligned.  Used for the LLM prefill (flash_attn_func, modeling_bailing_moe.py:988-1005)
+ * reading K/V straight from the [B, Hkv, Tmax, hd] cache. */
+int mb_attn_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, int64_t k_bs, int64_t k_ts,
+                int64_t k_hs, const void* v, int64_t v_bs, int64_t v_ts, int64_t v_hs, void* out, int64_t o_bs,
+                int64_t o_ts, int64_t o_hs, int B, int Sq, int Sk, int Hq, int Hkv, int hd, float scale, int causal,
+                void* stream);
+
 /* Decode-step attention against a static KV cache (semantic decoder, q_len = 1; layers/attention.py:213-239 with
  * past_key_value).  qkv[B, 3, H, 64] holds the new token; its K/V are appended at position `t` of
  * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t. */
@@ -166,6 +174,41 @@ int mb_silu_add_rows(const void* temb, const void* c, void* out, int steps, int 
  * receives the bf16 copy that feeds input_proj on the next step. */
 int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, float dt, float text_cfg,
                      float image_cfg, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Bailing-MoE AR step (mingunivision/modeling_bailing_moe.py).  `t_dev` arguments are optional DEVICE int32 scalars
+ * holding the current KV-cache length (so one captured CUDA graph can be replayed for every token); when NULL the
+ * host value `t_host` is used.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* BailingMoeRMSNorm.forward (:131-136): y = bf16(w * (x * rsqrt(mean(x^2) + eps))), fp32 statistics. */
+int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int dim, float eps,
+               void* stream);
+/* apply_rotary_pos_emb (:436-461) with the 1-D legacy tables (:213-237), fused with DynamicCache.update (:789):
+ * qkv[B*S, (H + 2*Hkv) * hd] -> q_out[B*S, H*hd] (rotated), K (rotated) and V appended to kcache / vcache
+ * [B, Hkv, Tmax, hd] at slots t .. t+S-1; position_ids int32 [B*S]. */
+int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, void* q_out, void* kcache, void* vcache, int B,
+                      int S, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev, int t_host, float rope_theta,
+                      void* stream);
+/* GQA attention for q_len == 1 (head_dim 128) over cache slots 0 .. T-1, skipping keys whose key_mask[b, j] == 0
+ * (the 2-D padding mask of the CFG rows; _upad_input / flash_attn_varlen_func :1009-1045, eager :795-812).
+ * key_mask may be NULL; mask_stride = elements between rows of key_mask. */
+int mb_attn_decode_gqa(const void* q, const void* kcache, const void* vcache, const int32_t* key_mask,
+                       int64_t mask_stride, void* out, int B, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev,
+                       int t_host, float scale, void* stream);
+/* BailingMoeGate.forward (:505-520) after the logits GEMM: fp32 softmax over E bf16 logits, top-k, renormalise.
+ * With logits_img + image_mask (uint8 [T]) tokens flagged as image tokens use the image gate's logits (:574-580). */
+int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* image_mask, int32_t* idx,
+                   float* weights, int T, int E, int k, int renorm, void* stream);
+/* moe_infer (:608-639) for small token counts: counting sort of the (token, slot) pairs by expert, expert gate/up +
+ * SwiGLU on the sorted pairs (Wgu[E][2I][D]: gate rows then up rows), expert down projection (Wd[E][D][I]) written
+ * back in (token, slot) order, and the fp32 weighted combine + shared-expert add + layer residual. */
+int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E, void* stream);
+int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
+                   void* hid, int T, int k, int E, int D, int I, void* stream);
+int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
+                void* out_pairs, int T, int k, int E, int D, int I, void* stream);
+int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual, void* y,
+                   int T, int k, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -26,9 +26,19 @@ SIGNATURES = {
     "mb_adaln_modulate": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],
+    "mb_rmsnorm": [_vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp],
+    "mb_rope_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
+    "mb_attn_decode_gqa": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
+    "mb_router_topk": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
     "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "mb_attn_fwd": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i, _i,
+                    _i, _i, _i, _i, _f, _i, _vp],
     "mb_attn_hd64_decode": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "mb_patchify": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_fill_cls_row": [_vp, _vp, _vp, _i, _i, _i, _vp],

@@ -363,3 +363,30 @@ extern "C" int mb_attn_hd64_decode(const void* qkv, void* kcache, void* vcache, 
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }
+
+// General strided entry: q[B, Sq, Hq, hd], k/v[B, Sk, Hkv, hd] with explicit (batch, token, head) element strides;
+// causal masks are bottom-right aligned (query i sees keys j <= i + Sk - Sq).
+extern "C" int mb_attn_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, int64_t k_bs,
+                           int64_t k_ts, int64_t k_hs, const void* v, int64_t v_bs, int64_t v_ts, int64_t v_hs,
+                           void* out, int64_t o_bs, int64_t o_ts, int64_t o_hs, int B, int Sq, int Sk, int Hq, int Hkv,
+                           int hd, float scale, int causal, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_attn_fwd: no sm_100 device");
+  MB_CHECK_ARG((hd == 64 || hd == 128) && Hkv >= 1 && Hq % Hkv == 0 && B >= 0 && B <= 65535 && Hq <= 65535,
+               MB_ERR_SHAPE, "mb_attn_fwd: head_dim must be 64 or 128 and Hq %% Hkv == 0");
+  MB_CHECK_ARG(q_ts % 8 == 0 && k_ts % 8 == 0 && v_ts % 8 == 0 && o_ts % 8 == 0 && q_hs % 8 == 0 && k_hs % 8 == 0 &&
+                   v_hs % 8 == 0 && o_hs % 8 == 0 && q_bs % 8 == 0 && k_bs % 8 == 0 && v_bs % 8 == 0 && o_bs % 8 == 0,
+               MB_ERR_ALIGN, "mb_attn_fwd: all strides must be multiples of 8 elements");
+  if (B == 0 || Sq == 0) return MB_OK;
+  AttnParams p;
+  p.q = static_cast<const __nv_bfloat16*>(q); p.k = static_cast<const __nv_bfloat16*>(k);
+  p.v = static_cast<const __nv_bfloat16*>(v); p.o = static_cast<__nv_bfloat16*>(out);
+  p.q_bs = q_bs; p.q_ts = q_ts; p.q_hs = q_hs;
+  p.k_bs = k_bs; p.k_ts = k_ts; p.k_hs = k_hs;
+  p.v_bs = v_bs; p.v_ts = v_ts; p.v_hs = v_hs;
+  p.o_bs = o_bs; p.o_ts = o_ts; p.o_hs = o_hs;
+  p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
+  return hd == 64 ? launch_attn<64>(p, B, stream) : launch_attn<128>(p, B, stream);
+}

@@ -2,10 +2,8 @@
 // semantic-decoder step):  out[M, N'] = epilogue(A[M, K] @ W[N, K]^T + bias).
 //
 // HBM-bound by construction: every weight byte is read exactly once with 16-byte, fully coalesced, L1-bypassing
-// loads; the tiny activation matrix lives in shared memory (bf16), accumulation is fp32 in registers.
-// One CTA (256 threads) owns a block of 4 output columns at a time (8 weight rows for SwiGLU: 4 gate + 4 up) and
-// splits K across ALL its threads, so the work unit is ~50 KB of weights regardless of N and the grid balances even
-// when N is small (w3: N = 3072).  Partial sums are reduced with warp shuffles + one shared-memory pass.
+// loads; the tiny activation matrix lives in shared memory (bf16), accumulation is fp32 in registers, the K-split is
+// reduced with warp shuffles.
 //
 // Algorithmic bytes per launch: N*K*2 (weights) — the roofline figure bench_rf.py reports against HBM peak.
 #include <cuda_bf16.h>
@@ -17,7 +15,6 @@
 namespace mb {
 
 constexpr int kGemvThreads = 256;
-constexpr int kGemvCols = 4;  // output columns per CTA work unit
 
 struct GemvParams {
   const __nv_bfloat16* A; int64_t lda;
@@ -48,13 +45,18 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& a) {
 }
 
 // EPI: 0 bias, 1 gelu, 2 swiglu (W = [2H, K] reference layout, out has H columns), 3 residual, 4 silu, 5 gated residual
+//
+// One WARP owns one output column at a time (two weight rows for SwiGLU: gate row n and up row n + H); the 32 lanes
+// split K in 16-byte chunks and keep kUnroll independent loads per weight row in flight.  Warps never synchronise with
+// each other after the activation matrix has been staged, so ~24 resident warps per SM x 8 outstanding 16-byte loads
+// per lane keep ~100 KB per SM in flight — what it takes to cover HBM latency at 6.5 TB/s.
 template <int MT, int EPI>
 __global__ void __launch_bounds__(kGemvThreads)
 gemv_bf16_kernel(const GemvParams p) {
-  constexpr int kRows = (EPI == MB_EPI_SWIGLU) ? 2 * kGemvCols : kGemvCols;  // weight rows per work unit
+  constexpr int kRows = (EPI == MB_EPI_SWIGLU) ? 2 : 1;  // weight rows per output column
+  constexpr int kUnroll = (EPI == MB_EPI_SWIGLU) ? 4 : 8;
   extern __shared__ __align__(16) uint8_t gemv_smem[];
-  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(gemv_smem);  // [MT][K]
-  __shared__ float red[kGemvThreads / 32][kRows * MT];
+  const uint4* sA = reinterpret_cast<const uint4*>(gemv_smem);  // [MT][K / 8] chunks of 8 bf16
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K = p.K, kchunks = K >> 3;
@@ -65,66 +67,60 @@ gemv_bf16_kernel(const GemvParams p) {
     const int m = i / kchunks, c = i % kchunks;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (m < p.M) v = *reinterpret_cast<const uint4*>(p.A + m * p.lda + c * 8);
-    reinterpret_cast<uint4*>(sA)[i] = v;
+    reinterpret_cast<uint4*>(gemv_smem)[i] = v;
   }
   __syncthreads();
 
-  const int num_units = (n_out + kGemvCols - 1) / kGemvCols;
-  for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-    const int n0 = unit * kGemvCols;
-    const __nv_bfloat16* wrow[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      int n = n0 + (r % kGemvCols);
-      if (n >= n_out) n = n_out - 1;  // clamp (result discarded)
-      if (EPI == MB_EPI_SWIGLU && r >= kGemvCols) n += n_out;
-      wrow[r] = p.W + static_cast<int64_t>(n) * p.ldw;
-    }
+  const int warps_total = gridDim.x * (kGemvThreads / 32);
+  for (int n = blockIdx.x * (kGemvThreads / 32) + warp; n < n_out; n += warps_total) {
+    const uint4* wrow[kRows];
+    wrow[0] = reinterpret_cast<const uint4*>(p.W + static_cast<int64_t>(n) * p.ldw);
+    if constexpr (kRows == 2) wrow[1] = reinterpret_cast<const uint4*>(p.W + static_cast<int64_t>(n + n_out) * p.ldw);
     float acc[kRows][MT];
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
 
-    for (int c = tid; c < kchunks; c += kGemvThreads) {
-      uint4 w[kRows];
+    for (int c0 = lane; c0 < kchunks; c0 += 32 * kUnroll) {
+      uint4 w[kRows][kUnroll];
 #pragma unroll
-      for (int r = 0; r < kRows; ++r) w[r] = ldg_stream(reinterpret_cast<const uint4*>(wrow[r]) + c);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + 32 * u;
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        const uint4 a = reinterpret_cast<const uint4*>(sA)[m * kchunks + c];
+        for (int r = 0; r < kRows; ++r) w[r][u] = (c < kchunks) ? ldg_stream(wrow[r] + c) : make_uint4(0, 0, 0, 0);
+      }
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) acc[r][m] += dot8(w[r], a);
+      for (int u = 0; u < kUnroll; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < kchunks) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint4 a = sA[m * kchunks + c];
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) acc[r][m] += dot8(w[r][u], a);
+          }
+        }
       }
     }
-    // reduce across the CTA
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
-        float v = acc[r][m];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp][r * MT + m] = v;
+        for (int o = 16; o > 0; o >>= 1) acc[r][m] += __shfl_xor_sync(0xffffffffu, acc[r][m], o);
       }
-    __syncthreads();
-    if (tid < kGemvCols * MT) {
-      const int cidx = tid / MT, m = tid % MT;
-      const int n = n0 + cidx;
-      if (n < n_out && m < p.M) {
-        float v = 0.f;
+    // lane m finalises row m (all lanes hold the full sums after the xor-reduction)
 #pragma unroll
-        for (int w = 0; w < kGemvThreads / 32; ++w) v += red[w][cidx * MT + m];
+    for (int m = 0; m < MT; ++m) {
+      if (lane == m && m < p.M) {
         float o;
         if constexpr (EPI == MB_EPI_SWIGLU) {
-          float u = 0.f;
-#pragma unroll
-          for (int w = 0; w < kGemvThreads / 32; ++w) u += red[w][(cidx + kGemvCols) * MT + m];
-          const float x1 = bf16_round(v + (p.bias ? __bfloat162float(p.bias[n]) : 0.f));
-          const float x2 = bf16_round(u + (p.bias ? __bfloat162float(p.bias[n + n_out]) : 0.f));
+          const float x1 = bf16_round(acc[0][m] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f));
+          const float x2 = bf16_round(acc[kRows - 1][m] + (p.bias ? __bfloat162float(p.bias[n + n_out]) : 0.f));
           o = bf16_round(silu(x1)) * x2;
         } else {
-          v += p.bias ? __bfloat162float(p.bias[n]) : 0.f;
+          float v = acc[0][m] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f);
           if constexpr (EPI == MB_EPI_GELU) v = gelu_erf(bf16_round(v));
           if constexpr (EPI == MB_EPI_SILU) v = silu(bf16_round(v));
           if constexpr (EPI == MB_EPI_RESIDUAL) v = bf16_round(v) + __bfloat162float(p.res[m * p.ldr + n]);
@@ -139,7 +135,6 @@ gemv_bf16_kernel(const GemvParams p) {
         if (p.out_f32) p.out_f32[m * n_out + n] = bf16_round(o);
       }
     }
-    __syncthreads();
   }
 }
 
@@ -205,8 +200,8 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.out_f32 = static_cast<float*>(out_f32);
   p.M = M; p.N = N; p.K = K;
   const int n_out = (epi == MB_EPI_SWIGLU) ? N / 2 : N;
-  const int units = (n_out + kGemvCols - 1) / kGemvCols;
-  const int per_sm = smem <= 48 * 1024 ? 3 : (smem <= 100 * 1024 ? 2 : 1);
+  const int units = (n_out + (kGemvThreads / 32) - 1) / (kGemvThreads / 32);  // CTAs needed for one column per warp
+  const int per_sm = smem <= 64 * 1024 ? 3 : (smem <= 100 * 1024 ? 2 : 1);
   int grid = num_sms() * per_sm;
   if (grid > units) grid = units;
   switch (mt) {

@@ -1,0 +1,504 @@
+// Bailing-MoE AR-step operators (mingunivision/modeling_bailing_moe.py): RMSNorm, NeoX RoPE fused with the KV-cache
+// append, GQA decode attention with a per-row key mask, softmax-top-k router, and the routed-expert FFN for small
+// token counts (pairs grouped by expert so every expert's weights are streamed once per chunk of <= 8 tokens).
+// All of these are HBM / latency bound at the CFG-row batch sizes of the path; they use 16-byte coalesced loads,
+// warp-shuffle reductions and read the current cache length from DEVICE memory so a whole AR step can be replayed as
+// one CUDA graph.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace mb {
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_stream16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float dot8f(const uint4& w, const uint4& a) {
+  const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y), w2 = unpack_bf16x2(w.z), w3 = unpack_bf16x2(w.w);
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z), a3 = unpack_bf16x2(a.w);
+  float s = w0.x * a0.x;
+  s = fmaf(w0.y, a0.y, s); s = fmaf(w1.x, a1.x, s); s = fmaf(w1.y, a1.y, s);
+  s = fmaf(w2.x, a2.x, s); s = fmaf(w2.y, a2.y, s); s = fmaf(w3.x, a3.x, s); s = fmaf(w3.y, a3.y, s);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RMSNorm: y = bf16(w * (x * rsqrt(mean(x^2) + eps)))   one warp per row
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
+               __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int dim, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * ldx;
+  float sq = 0.f;
+  for (int c = lane * 8; c < dim; c += 256) {
+    const uint4 q = *reinterpret_cast<const uint4*>(xr + c);
+    const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    sq += a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y + cc.x * cc.x + cc.y * cc.y + d.x * d.x + d.y * d.y;
+  }
+  const float r = rsqrtf(warp_sum_f(sq) / dim + eps);
+  __nv_bfloat16* yr = y + static_cast<int64_t>(row) * ldy;
+  for (int c = lane * 8; c < dim; c += 256) {
+    const uint4 q = *reinterpret_cast<const uint4*>(xr + c);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(w + c));
+    const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), cc = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    const float2 ga = unpack_bf16x2(g.x), gb = unpack_bf16x2(g.y), gc = unpack_bf16x2(g.z), gd = unpack_bf16x2(g.w);
+    uint4 o;
+    o.x = pack_bf16x2(ga.x * (a.x * r), ga.y * (a.y * r));
+    o.y = pack_bf16x2(gb.x * (b.x * r), gb.y * (b.y * r));
+    o.z = pack_bf16x2(gc.x * (cc.x * r), gc.y * (cc.y * r));
+    o.w = pack_bf16x2(gd.x * (d.x * r), gd.y * (d.y * r));
+    *reinterpret_cast<uint4*>(yr + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RoPE (rotate-half, 1-D positions, bf16 cos/sin tables as the reference's `.to(x.dtype)`) + KV-cache append.
+// qkv rows: [H q heads | Hkv k heads | Hkv v heads] x hd.  One CTA per token row, one warp per head.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ position_ids,
+                      __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kcache,
+                      __nv_bfloat16* __restrict__ vcache, int B, int S, int H, int Hkv, int hd, int Tmax,
+                      const int32_t* __restrict__ t_dev, int t_host, float theta) {
+  const int row = blockIdx.x;  // b * S + s
+  const int b = row / S, s = row % S;
+  const int slot = (t_dev ? *t_dev : t_host) + s;
+  const int pos = position_ids[row];
+  const int nheads = H + 2 * Hkv;
+  const int half = hd / 2;
+  const __nv_bfloat16* src_row = qkv + static_cast<int64_t>(row) * nheads * hd;
+  for (int head = threadIdx.x >> 5; head < nheads; head += blockDim.x >> 5) {
+    const __nv_bfloat16* src = src_row + head * hd;
+    __nv_bfloat16* dst;
+    bool rot = true;
+    if (head < H) {
+      dst = q_out + (static_cast<int64_t>(row) * H + head) * hd;
+    } else if (head < H + Hkv) {
+      dst = kcache + ((static_cast<int64_t>(b) * Hkv + (head - H)) * Tmax + slot) * hd;
+    } else {
+      dst = vcache + ((static_cast<int64_t>(b) * Hkv + (head - H - Hkv)) * Tmax + slot) * hd;
+      rot = false;
+    }
+    for (int i = threadIdx.x & 31; i < half; i += 32) {
+      const float x1 = __bfloat162float(src[i]), x2 = __bfloat162float(src[i + half]);
+      if (!rot) {
+        dst[i] = src[i];
+        dst[i + half] = src[i + half];
+      } else {
+        // inv_freq = theta^(-2i/hd); angle in fp32 exactly as torch.outer(t, inv_freq) (modeling_bailing_moe.py:219-224)
+        const float inv_freq = 1.0f / powf(theta, static_cast<float>(2 * i) / static_cast<float>(hd));
+        const float ang = static_cast<float>(pos) * inv_freq;
+        const float c = bf16_round(cosf(ang)), sn = bf16_round(sinf(ang));
+        // q*cos + rotate_half(q)*sin with bf16 rounding after every tensor op (:455-461)
+        dst[i] = __float2bfloat16_rn(bf16_round(x1 * c) + bf16_round(-x2 * sn));
+        dst[i + half] = __float2bfloat16_rn(bf16_round(x2 * c) + bf16_round(x1 * sn));
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GQA decode attention (q_len = 1), head_dim 128: one warp per (batch row, q head); lane owns 4 dims.
+// Keys 0..T-1 of the static cache, skipping keys whose mask entry is 0 (the reference's unpad/varlen path).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
+                          const __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ key_mask,
+                          int64_t mask_stride, __nv_bfloat16* __restrict__ out, int B, int H, int Hkv, int Tmax,
+                          const int32_t* __restrict__ t_dev, int t_host, float scale) {
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (wid >= B * H) return;
+  const int b = wid / H, h = wid % H, hk = h / (H / Hkv);
+  const int T = t_dev ? *t_dev : t_host;
+  const uint2 qq = *reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4);
+  const float2 q0 = unpack_bf16x2(qq.x), q1 = unpack_bf16x2(qq.y);
+  const __nv_bfloat16* kc = kcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;
+  const __nv_bfloat16* vc = vcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;
+  const int32_t* mk = key_mask ? key_mask + static_cast<int64_t>(b) * mask_stride : nullptr;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  for (int j0 = 0; j0 < T; j0 += 4) {
+    uint2 kk[4], vv[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u;
+      ok[u] = j < T && (mk == nullptr || mk[j] != 0);
+      if (ok[u]) {
+        kk[u] = *reinterpret_cast<const uint2*>(kc + static_cast<int64_t>(j) * 128);
+        vv[u] = *reinterpret_cast<const uint2*>(vc + static_cast<int64_t>(j) * 128);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;  // warp-uniform
+      const float2 k0 = unpack_bf16x2(kk[u].x), k1 = unpack_bf16x2(kk[u].y);
+      float s = q0.x * k0.x + q0.y * k0.y + q1.x * k1.x + q1.y * k1.y;
+      s = warp_sum_f(s) * scale;
+      const float m_new = fmaxf(m, s);
+      const float corr = __expf(m - m_new), pj = __expf(s - m_new);
+      const float2 v0 = unpack_bf16x2(vv[u].x), v1 = unpack_bf16x2(vv[u].y);
+      l = l * corr + pj;
+      o0 = o0 * corr + pj * v0.x; o1 = o1 * corr + pj * v0.y;
+      o2 = o2 * corr + pj * v1.x; o3 = o3 * corr + pj * v1.y;
+      m = m_new;
+    }
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  uint2 r;
+  r.x = pack_bf16x2(o0 * inv, o1 * inv);
+  r.y = pack_bf16x2(o2 * inv, o3 * inv);
+  *reinterpret_cast<uint2*>(out + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4) = r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Router: fp32 softmax over E bf16 logits, top-k (ties -> lowest index), optional renormalisation.   warp per token
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+router_topk_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __restrict__ logits_img,
+                   const uint8_t* __restrict__ image_mask, int32_t* __restrict__ idx, float* __restrict__ wout, int T,
+                   int E, int k, int renorm) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const __nv_bfloat16* lg = (logits_img != nullptr && image_mask != nullptr && image_mask[t]) ? logits_img : logits;
+  lg += static_cast<int64_t>(t) * E;
+  // up to 8 experts per lane (E <= 256)
+  float v[8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int e = lane + 32 * i;
+    v[i] = e < E ? __bfloat162float(lg[e]) : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+  mx = warp_max_f(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = (lane + 32 * i < E) ? expf(v[i] - mx) : -1.f;
+    if (v[i] > 0.f) sum += v[i];
+  }
+  sum = warp_sum_f(sum);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = v[i] >= 0.f ? v[i] / sum : -1.f;
+  float wsum = 0.f, picked_w = 0.f;
+  int picked_e = 0;
+  for (int j = 0; j < k; ++j) {
+    float best = -1.f;
+    int best_e = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = lane + 32 * i;
+      if (v[i] > best || (v[i] == best && e < best_e)) { best = v[i]; best_e = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
+      if (ob > best || (ob == best && oe < best_e)) { best = ob; best_e = oe; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (lane + 32 * i == best_e) v[i] = -1.f;  // remove the winner
+    wsum += best;
+    if (lane == j) { picked_w = best; picked_e = best_e; }
+  }
+  if (lane < k) {
+    idx[static_cast<int64_t>(t) * k + lane] = picked_e;
+    wout[static_cast<int64_t>(t) * k + lane] = renorm ? picked_w / wsum : picked_w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Counting sort of the T*k (token, slot) pairs by expert (single CTA; T*k is small on this path).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+moe_sort_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ expert_offsets,
+                int32_t* __restrict__ sorted_pair, int npairs, int E) {
+  extern __shared__ int32_t sm[];  // counts[E], cursor[E]
+  int32_t* counts = sm;
+  int32_t* cursor = sm + E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) counts[e] = 0;
+  __syncthreads();
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) atomicAdd(&counts[idx[p]], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      expert_offsets[e] = acc;
+      cursor[e] = acc;
+      acc += counts[e];
+    }
+    expert_offsets[E] = acc;
+  }
+  __syncthreads();
+  // stable order inside an expert is not required by the math (each pair is independent), but keep it deterministic:
+  // thread 0..E-1 each fills its own expert's segment in increasing pair order
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int c = cursor[e];
+    if (counts[e] == 0) continue;
+    for (int p = 0; p < npairs; ++p)
+      if (idx[p] == e) sorted_pair[c++] = p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Routed experts, small-token regime.  grid = (X column blocks, E experts).  For its expert a CTA walks the expert's
+// pairs in chunks of <= 8 rows: stages the rows in shared memory, then every warp streams weight rows (16-byte loads,
+// K split over the lanes) and accumulates all staged rows at once, so an expert's weights are read once per chunk.
+//   PHASE 0: hid[p, i]  = bf16(bf16(silu(bf16(x[tok(p)] . Wg[e][i]))) * bf16(x[tok(p)] . Wu[e][i]))     (gate/up + SwiGLU)
+//   PHASE 1: out[pair(p), n] = bf16(hid[p] . Wd[e][n])                                                   (down)
+// ------------------------------------------------------------------------------------------------------------
+template <int MT, int PHASE>
+__device__ __forceinline__ void moe_rows(const uint4* __restrict__ sA, int kchunks, const __nv_bfloat16* __restrict__ We,
+                                         int n_cols, int K, int col0, int col_step, int lane, int cnt,
+                                         __nv_bfloat16* __restrict__ dst, int64_t dst_ld, const int32_t* dst_rows,
+                                         int p0) {
+  for (int n = col0; n < n_cols; n += col_step) {
+    const uint4* w0 = reinterpret_cast<const uint4*>(We + static_cast<int64_t>(n) * K);
+    const uint4* w1 = reinterpret_cast<const uint4*>(We + static_cast<int64_t>(n + n_cols) * K);  // PHASE 0: up row
+    float a0[MT], a1[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) a0[m] = a1[m] = 0.f;
+    for (int c0 = lane; c0 < kchunks; c0 += 32 * 4) {
+      uint4 wa[4], wb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        wa[u] = c < kchunks ? ldg_stream16(w0 + c) : make_uint4(0, 0, 0, 0);
+        if (PHASE == 0) wb[u] = c < kchunks ? ldg_stream16(w1 + c) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < kchunks) {
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            const uint4 a = sA[m * kchunks + c];
+            a0[m] += dot8f(wa[u], a);
+            if (PHASE == 0) a1[m] += dot8f(wb[u], a);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      a0[m] = warp_sum_f(a0[m]);
+      if (PHASE == 0) a1[m] = warp_sum_f(a1[m]);
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (lane == m && m < cnt) {
+        if (PHASE == 0) {
+          const float g = bf16_round(a0[m]), u = bf16_round(a1[m]);
+          dst[static_cast<int64_t>(p0 + m) * dst_ld + n] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
+        } else {
+          dst[static_cast<int64_t>(dst_rows[p0 + m]) * dst_ld + n] = __float2bfloat16_rn(a0[m]);
+        }
+      }
+    }
+  }
+}
+
+template <int PHASE>
+__global__ void __launch_bounds__(256)
+moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+                  const int32_t* __restrict__ expert_offsets, const int32_t* __restrict__ sorted_pair,
+                  __nv_bfloat16* __restrict__ dst, int topk, int K, int n_cols, int64_t expert_stride) {
+  extern __shared__ __align__(16) uint8_t moe_smem[];
+  uint4* sA = reinterpret_cast<uint4*>(moe_smem);  // [8][K/8]
+  const int e = blockIdx.y;
+  const int beg = expert_offsets[e], end = expert_offsets[e + 1];
+  if (beg == end) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kchunks = K >> 3;
+  const __nv_bfloat16* We = W + static_cast<int64_t>(e) * expert_stride;
+  const int col0 = blockIdx.x * 8 + warp, col_step = gridDim.x * 8;
+  for (int p0 = beg; p0 < end; p0 += 8) {
+    const int cnt = min(8, end - p0);
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = tid; i < cnt * kchunks; i += 256) {
+      const int m = i / kchunks, c = i % kchunks;
+      // PHASE 0 gathers token rows of x; PHASE 1 reads the (already expert-sorted) hidden rows
+      const int64_t src_row = (PHASE == 0) ? (sorted_pair[p0 + m] / topk) : (p0 + m);
+      sA[m * kchunks + c] = *reinterpret_cast<const uint4*>(A + src_row * K + c * 8);
+    }
+    __syncthreads();
+    const int64_t dst_ld = (PHASE == 0) ? n_cols : n_cols;
+    if (cnt == 1) moe_rows<1, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
+    else if (cnt == 2) moe_rows<2, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
+    else if (cnt <= 4) moe_rows<4, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
+    else moe_rows<8, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
+  }
+}
+
+// y[t] = bf16( bf16( bf16(sum_j w[t,j] * out_pairs[t*k+j]) + shared[t] ) + residual[t] )
+// (moe_infer's fp32 weighted sum :632-638, `y + shared_experts(identity)` :604-605, layer residual :1226)
+__global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ out_pairs, const float* __restrict__ w,
+                                   const __nv_bfloat16* __restrict__ shared, const __nv_bfloat16* __restrict__ residual,
+                                   __nv_bfloat16* __restrict__ y, int T, int k, int D) {
+  const int64_t total = static_cast<int64_t>(T) * D;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / D;
+    const int d = static_cast<int>(i % D);
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) acc += w[t * k + j] * __bfloat162float(out_pairs[(t * k + j) * D + d]);
+    float v = bf16_round(acc);
+    if (shared) v = bf16_round(v + __bfloat162float(shared[i]));
+    if (residual) v = v + __bfloat162float(residual[i]);
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int dim, float eps,
+                          void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_rmsnorm: no sm_100 device");
+  MB_CHECK_ARG(rows >= 0 && dim >= 8 && dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, MB_ERR_SHAPE,
+               "mb_rmsnorm: dim, ldx, ldy must be multiples of 8");
+  if (rows == 0) return MB_OK;
+  rmsnorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                     static_cast<const __nv_bfloat16*>(w),
+                                                     static_cast<__nv_bfloat16*>(y), ldy, rows, dim, eps);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, void* q_out, void* kcache, void* vcache,
+                                 int B, int S, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev, int t_host,
+                                 float rope_theta, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_rope_kv_append: no sm_100 device");
+  MB_CHECK_ARG(B >= 0 && S >= 0 && H >= 1 && Hkv >= 1 && hd % 2 == 0, MB_ERR_SHAPE, "mb_rope_kv_append: bad shape");
+  MB_CHECK_ARG(t_dev != nullptr || (t_host >= 0 && t_host + S <= Tmax), MB_ERR_SHAPE,
+               "mb_rope_kv_append: cache overflow (t=%d S=%d Tmax=%d)", t_host, S, Tmax);
+  if (B * S == 0) return MB_OK;
+  rope_kv_append_kernel<<<B * S, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), position_ids,
+                                                   static_cast<__nv_bfloat16*>(q_out),
+                                                   static_cast<__nv_bfloat16*>(kcache),
+                                                   static_cast<__nv_bfloat16*>(vcache), B, S, H, Hkv, hd, Tmax, t_dev,
+                                                   t_host, rope_theta);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_attn_decode_gqa(const void* q, const void* kcache, const void* vcache, const int32_t* key_mask,
+                                  int64_t mask_stride, void* out, int B, int H, int Hkv, int hd, int Tmax,
+                                  const int32_t* t_dev, int t_host, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_attn_decode_gqa: no sm_100 device");
+  MB_CHECK_ARG(hd == 128 && H % Hkv == 0, MB_ERR_SHAPE, "mb_attn_decode_gqa: head_dim must be 128 and H %% Hkv == 0");
+  MB_CHECK_ARG(t_dev != nullptr || (t_host >= 0 && t_host <= Tmax), MB_ERR_SHAPE, "mb_attn_decode_gqa: bad length");
+  if (B == 0) return MB_OK;
+  attn_decode_gqa128_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+      static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
+      Tmax, t_dev, t_host, scale);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* image_mask, int32_t* idx,
+                              float* weights, int T, int E, int k, int renorm, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_router_topk: no sm_100 device");
+  MB_CHECK_ARG(E >= 1 && E <= 256 && k >= 1 && k <= 32 && k <= E, MB_ERR_SHAPE, "mb_router_topk: E <= 256, k <= 32");
+  if (T == 0) return MB_OK;
+  router_topk_kernel<<<(T + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits),
+                                                      static_cast<const __nv_bfloat16*>(logits_img), image_mask, idx,
+                                                      weights, T, E, k, renorm);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E,
+                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_sort: no sm_100 device");
+  MB_CHECK_ARG(E >= 1 && E <= 4096, MB_ERR_SHAPE, "mb_moe_sort: bad expert count");
+  moe_sort_kernel<<<1, 256, 2 * E * sizeof(int32_t), stream>>>(idx, expert_offsets, sorted_pair, T * k, E);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
+                            void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(8) * K * 2;
+  MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= 10240");
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[phase]) {
+    if (phase == 0)
+      MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    else
+      MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set[phase] = true;
+  }
+  int xblocks = (n_cols + 8 * 11 - 1) / (8 * 11);  // ~11 columns per warp
+  if (xblocks < 1) xblocks = 1;
+  dim3 grid(xblocks, E);
+  if (phase == 0)
+    moe_expert_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
+                                                      static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                                                      static_cast<__nv_bfloat16*>(dst), topk, K, n_cols, expert_stride);
+  else
+    moe_expert_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
+                                                      static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                                                      static_cast<__nv_bfloat16*>(dst), topk, K, n_cols, expert_stride);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
+                              void* hid, int T, int k, int E, int D, int I, void* stream_) {
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_gate_up: no sm_100 device");
+  if (T == 0) return MB_OK;
+  return launch_moe_phase(0, x, Wgu, expert_offsets, sorted_pair, hid, k, E, D, I, static_cast<int64_t>(2) * I * D,
+                          static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
+                           void* out_pairs, int T, int k, int E, int D, int I, void* stream_) {
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_down: no sm_100 device");
+  if (T == 0) return MB_OK;
+  return launch_moe_phase(1, hid, Wd, expert_offsets, sorted_pair, out_pairs, k, E, I, D, static_cast<int64_t>(D) * I,
+                          static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual,
+                              void* y, int T, int k, int D, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_combine: no sm_100 device");
+  const int64_t total = static_cast<int64_t>(T) * D;
+  if (total == 0) return MB_OK;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  moe_combine_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out_pairs), weights,
+                                               static_cast<const __nv_bfloat16*>(shared),
+                                               static_cast<const __nv_bfloat16*>(residual),
+                                               static_cast<__nv_bfloat16*>(y), T, k, D);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}

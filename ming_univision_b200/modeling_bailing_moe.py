@@ -1,0 +1,449 @@
+"""B200-native Bailing-MoE AR path: same class names, parameter tree (state_dict keys) and method signatures as the
+reference's ``mingunivision/modeling_bailing_moe.py`` for the rows of SURVEY.md §8(a) a12–a20:
+
+  BailingMoeRMSNorm :122-136 · BailingMoeMLP :471-484 · BailingMoeGate :487-520 · BailingMoeSparseMoeBlock :523-639 ·
+  BailingMoeAttention :656-829 · BailingMoeDecoderLayer :1150-1239 · BailingMoeModel :1359-1540 ·
+  BailingMoeForCausalLM :1543-1965 (setup_vishead_diffloss, compute_logit, forward_for_image_generation_inner,
+  generate_image).
+
+Every operator runs in libmingb200.so (ops.py); the nn.Modules only own parameters.  Token counts on this path are
+tiny (CFG rows B <= 3 per step, prompts of tens of tokens), so all linears go through the HBM-streaming kernel for
+<= 8 rows and through the tcgen05 GEMM otherwise; routed experts are grouped by expert on the device (no host sync —
+the reference's `tokens_per_expert.cpu()` at :616 is gone).  1-D legacy RoPE (rope_scaling=None).
+KV caches are static [Bmax, Hkv, Tmax, hd] tensors written in place.  Inference only, bf16.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+from transformers import PretrainedConfig
+
+from . import ops
+from .diff_loss_rf_swiglu import RectifiedFlowLoss
+
+BF16 = torch.bfloat16
+
+
+class BailingMoeConfig(PretrainedConfig):
+    """Field-compatible with mingunivision/configuration_bailing_moe.py:6-84."""
+    model_type = "bailing_moe"
+
+    def __init__(self, vocab_size=30592, hidden_size=1024, intermediate_size=None, num_hidden_layers=24,
+                 num_attention_heads=16, num_key_value_heads=0, hidden_act="silu", use_qkv_bias=False, use_bias=True,
+                 rms_norm_eps=1e-05, norm_head=False, tie_word_embeddings=False, embedding_dropout=0.1,
+                 attention_dropout=0.1, output_dropout=0.1, initializer_range=0.02, max_position_embeddings=16384,
+                 rope_theta=10000.0, use_cache=True, use_sliding_window=False, sliding_window=4096,
+                 max_window_layers=28, rope_scaling=None, pad_token_id=126081, num_experts=16, num_shared_experts=0,
+                 num_experts_per_tok=2, num_image_tokens_for_gen=256, norm_topk_prob=True, moe_intermediate_size=None,
+                 first_k_dense_replace=0, head_dim=None, output_router_logits=False, multi_gate=False,
+                 image_patch_token=126346, image_start_token=126347, **kwargs):
+        self.num_hidden_layers = num_hidden_layers
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.intermediate_size = intermediate_size
+        self.num_attention_heads = num_attention_heads
+        self.num_key_value_heads = num_key_value_heads
+        self.hidden_act = hidden_act
+        self.use_qkv_bias = use_qkv_bias
+        self.use_bias = use_bias
+        self.norm_head = norm_head
+        self.rms_norm_eps = rms_norm_eps
+        self.embedding_dropout = embedding_dropout
+        self.attention_dropout = attention_dropout
+        self.output_dropout = output_dropout
+        self.initializer_range = initializer_range
+        self.max_position_embeddings = max_position_embeddings
+        self.rope_theta = rope_theta
+        self.use_cache = use_cache
+        self.use_sliding_window = use_sliding_window
+        self.sliding_window = sliding_window
+        self.max_window_layers = max_window_layers
+        self.head_dim = head_dim or self.hidden_size // self.num_attention_heads
+        self.rope_scaling = rope_scaling
+        self.num_experts = num_experts
+        self.num_shared_experts = num_shared_experts
+        self.num_experts_per_tok = num_experts_per_tok
+        self.num_image_tokens_for_gen = num_image_tokens_for_gen
+        self.norm_topk_prob = norm_topk_prob
+        self.moe_intermediate_size = moe_intermediate_size
+        self.first_k_dense_replace = first_k_dense_replace
+        self.output_router_logits = output_router_logits
+        self.multi_gate = multi_gate
+        self.image_patch_token = image_patch_token
+        self.image_start_token = image_start_token
+        super().__init__(pad_token_id=pad_token_id, tie_word_embeddings=tie_word_embeddings, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers
+# ---------------------------------------------------------------------------------------------------------------
+class BailingMoeRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+
+class BailingMoeMLP(nn.Module):
+    def __init__(self, config, intermediate_size):
+        super().__init__()
+        self.gate_proj = nn.Linear(config.hidden_size, intermediate_size, bias=False)
+        self.up_proj = nn.Linear(config.hidden_size, intermediate_size, bias=False)
+        self.down_proj = nn.Linear(intermediate_size, config.hidden_size, bias=False)
+
+
+class BailingMoeGate(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.top_k = config.num_experts_per_tok
+        self.num_experts = config.num_experts
+        self.norm_topk_prob = config.norm_topk_prob
+        self.weight = nn.Parameter(torch.empty((config.num_experts, config.hidden_size)))
+
+
+class BailingMoeSparseMoeBlock(nn.Module):
+    """Parameters of the MoE block; `forward` is the MoE operator boundary of SURVEY.md §8(b):
+    forward(hidden_states, image_mask=None, audio_mask=None) -> (y, (router_logits, topk_idx))."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.num_experts_per_tok = config.num_experts_per_tok
+        self.experts = nn.ModuleList([BailingMoeMLP(config, config.moe_intermediate_size)
+                                      for _ in range(config.num_experts)])
+        self.multi_gate = config.multi_gate
+        if self.multi_gate:
+            self.image_gate = BailingMoeGate(config)
+            self.audio_gate = BailingMoeGate(config)
+        self.gate = BailingMoeGate(config)
+        if config.num_shared_experts is not None and config.num_shared_experts > 0:
+            self.shared_experts = BailingMoeMLP(config, config.moe_intermediate_size * config.num_shared_experts)
+        self._pk = None
+
+    def _pack(self):
+        dev = self.gate.weight.device
+        if self._pk is None or self._pk["dev"] != dev:
+            d = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+            pk = {"dev": dev, "gate": d(self.gate.weight)}
+            if self.multi_gate:
+                pk["image_gate"] = d(self.image_gate.weight)
+            # per-expert slabs: Wgu[e] = [gate_proj; up_proj] ([2I, D]), Wd[e] = down_proj ([D, I])
+            pk["Wgu"] = torch.stack([torch.cat([d(e.gate_proj.weight), d(e.up_proj.weight)], dim=0)
+                                     for e in self.experts]).contiguous()
+            pk["Wd"] = torch.stack([d(e.down_proj.weight) for e in self.experts]).contiguous()
+            if hasattr(self, "shared_experts"):
+                s = self.shared_experts
+                pk["s12"] = torch.cat([d(s.gate_proj.weight), d(s.up_proj.weight)], dim=0).contiguous()
+                pk["s12p"], _, hp = ops.pack_swiglu(pk["s12"], None)
+                pk["s3"] = d(s.down_proj.weight)
+                pk["s3p"] = ops.pad_cols(pk["s3"], hp)
+            self._pk = pk
+        return self._pk
+
+    def _apply(self, fn, *a, **k):
+        self._pk = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def _run(self, x2d: torch.Tensor, residual: Optional[torch.Tensor], image_mask: Optional[torch.Tensor]):
+        """x2d [T, D] (post-attention-norm) -> (residual + moe(x) [T, D], router logits [T, E], topk idx [T, k])."""
+        pk = self._pack()
+        cfg = self.config
+        logits = _dense(x2d, pk["gate"])
+        logits_img, im = None, None
+        if self.multi_gate and image_mask is not None:
+            logits_img = _dense(x2d, pk["image_gate"])
+            im = image_mask.reshape(-1).to(torch.uint8).contiguous()
+        idx, w = ops.router_topk(logits, cfg.num_experts_per_tok, cfg.num_experts_per_tok > 1 and cfg.norm_topk_prob,
+                                 logits_img, im)
+        shared = None
+        if "s12" in pk:
+            if x2d.shape[0] <= 8:
+                shared = ops.gemv(ops.gemv(x2d, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
+            else:
+                shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
+        y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual)
+        return y, logits, idx
+
+    @torch.no_grad()
+    def forward(self, hidden_states, image_mask=None, audio_mask=None):
+        """modeling_bailing_moe.py:556-606 (audio routing is out of scope)."""
+        if audio_mask is not None:
+            raise NotImplementedError("audio routing is outside the continuous-visual-token path")
+        B, S, D = hidden_states.shape
+        y, logits, idx = self._run(hidden_states.reshape(B * S, D).contiguous(), None, image_mask)
+        return y.view(B, S, D), (logits.view(B, S, -1), idx.view(B, S, -1).long())
+
+
+class BailingMoeAttention(nn.Module):
+    def __init__(self, config, layer_idx=None):
+        super().__init__()
+        self.layer_idx = layer_idx
+        hd = config.head_dim
+        self.query_key_value = nn.Linear(config.hidden_size, (config.num_attention_heads + 2 * config.num_key_value_heads) * hd,
+                                         bias=config.use_qkv_bias)
+        self.dense = nn.Linear(config.num_attention_heads * hd, config.hidden_size, bias=config.use_bias)
+
+
+class BailingMoeDecoderLayer(nn.Module):
+    def __init__(self, config, layer_idx):
+        super().__init__()
+        if config.num_experts is None or layer_idx < config.first_k_dense_replace:
+            raise NotImplementedError("dense (non-MoE) decoder layers are not on the Ming-UniVision path "
+                                      "(first_k_dense_replace = 0, mingunivision/config.json:41)")
+        self.attention = BailingMoeAttention(config, layer_idx)
+        self.mlp = BailingMoeSparseMoeBlock(config)
+        self.input_layernorm = BailingMoeRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = BailingMoeRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+
+def _dense(x2d: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    """nn.Linear on the streaming kernel (<= 8 rows) or the tcgen05 GEMM."""
+    if x2d.shape[0] <= 8:
+        return ops.gemv(x2d, w, bias, **kw)
+    return ops.linear(x2d, w, bias, **kw)
+
+
+class BailingKVCache:
+    """Static KV cache: per layer K, V of shape [Bmax, Hkv, Tmax, hd] (bf16).  Stands in for the HF DynamicCache the
+    reference threads through `past_key_values` (cache .repeat / trim of generate_image, :1891-1902 / :1954-1962,
+    become a row copy / a batch counter)."""
+
+    def __init__(self, config, max_batch: int, max_len: int, device):
+        L, Hkv, hd = config.num_hidden_layers, config.num_key_value_heads, config.head_dim
+        self.k = [torch.zeros((max_batch, Hkv, max_len, hd), dtype=BF16, device=device) for _ in range(L)]
+        self.v = [torch.zeros((max_batch, Hkv, max_len, hd), dtype=BF16, device=device) for _ in range(L)]
+        self.seq_len = 0
+        self.batch = 1
+        self.max_len = max_len
+        self.max_batch = max_batch
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self.seq_len
+
+    def repeat_rows(self, B: int) -> None:
+        if B > self.max_batch:
+            raise ValueError("KV cache allocated for fewer rows")
+        for k, v in zip(self.k, self.v):
+            for b in range(self.batch, B):
+                k[b, :, :self.seq_len].copy_(k[0, :, :self.seq_len])
+                v[b, :, :self.seq_len].copy_(v[0, :, :self.seq_len])
+        self.batch = B
+
+    def trim_rows(self) -> None:
+        self.batch = 1
+
+
+class BailingMoeModel(nn.Module):
+    def __init__(self, config: BailingMoeConfig):
+        super().__init__()
+        self.config = config
+        self.vocab_size = config.vocab_size
+        self.word_embeddings = nn.Embedding(config.vocab_size, config.hidden_size)
+        self.layers = nn.ModuleList([BailingMoeDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
+        self.norm = BailingMoeRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self._pk = None
+
+    def _apply(self, fn, *a, **k):
+        self._pk = None
+        return super()._apply(fn, *a, **k)
+
+    def _pack(self):
+        dev = self.norm.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("BailingMoeModel (B200-native) runs on CUDA only; there is no CPU fallback")
+        if self._pk is None or self._pk["dev"] != dev:
+            d = lambda t: None if t is None else t.detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+            layers = []
+            for lyr in self.layers:
+                a = lyr.attention
+                layers.append(dict(ln1=d(lyr.input_layernorm.weight), ln2=d(lyr.post_attention_layernorm.weight),
+                                   qkv_w=d(a.query_key_value.weight), qkv_b=d(a.query_key_value.bias),
+                                   dense_w=d(a.dense.weight), dense_b=d(a.dense.bias)))
+            self._pk = dict(dev=dev, layers=layers, norm=d(self.norm.weight), emb=d(self.word_embeddings.weight))
+        return self._pk
+
+    def embed(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """word_embeddings lookup (row gather of the packed bf16 table; pure indexing, no arithmetic)."""
+        return self._pack()["emb"][input_ids]
+
+    @torch.no_grad()
+    def forward_tokens(self, inputs_embeds: torch.Tensor, position_ids: torch.Tensor, cache: BailingKVCache,
+                       key_mask: Optional[torch.Tensor] = None, image_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """BailingMoeModel.forward (:1391-1540) for this path's two regimes.
+        inputs_embeds [B, S, D]; position_ids int [B, S]; the S new tokens are appended at cache slots seq_len..;
+        S == 1: cached decode of B rows, `key_mask` int32 [B, >= seq_len+1] marks attendable slots (2-D padding mask of
+        the CFG rows); S > 1: causal prefill into an empty cache (all-ones mask).  Returns final-norm hidden [B, S, D]."""
+        pk = self._pack()
+        cfg = self.config
+        B, S, D = inputs_embeds.shape
+        H, hd = cfg.num_attention_heads, cfg.head_dim
+        t0 = cache.seq_len
+        if t0 + S > cache.max_len:
+            raise ValueError(f"KV cache overflow: {t0}+{S} > {cache.max_len}")
+        if S > 1 and (t0 != 0 or (key_mask is not None and bool((key_mask[:, :S] == 0).any()))):
+            raise NotImplementedError("multi-token forward is implemented for a causal prefill into an empty cache")
+        h = inputs_embeds.to(BF16).reshape(B * S, D).contiguous().clone()
+        pos = position_ids.reshape(-1).to(torch.int32).contiguous()
+        eps = cfg.rms_norm_eps
+        im = None if image_mask is None else image_mask.reshape(-1)
+        for li, (lp, lyr) in enumerate(zip(pk["layers"], self.layers)):
+            x = ops.rmsnorm(h, lp["ln1"], eps)
+            qkv = _dense(x, lp["qkv_w"], lp["qkv_b"])
+            # rows 0..B-1 of the [Bmax, Hkv, Tmax, hd] cache are a contiguous prefix the kernels index directly
+            q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta)
+            if S == 1:
+                a = ops.attn_decode_gqa(q, cache.k[li], cache.v[li], key_mask, H, t0 + 1)
+            else:
+                a = ops.attn_prefill_gqa(q, cache.k[li], cache.v[li], B, S, H)
+            _dense(a, lp["dense_w"], lp["dense_b"], epi=ops.EPI_RESIDUAL, residual=h, out=h)
+            x = ops.rmsnorm(h, lp["ln2"], eps)
+            h, _, _ = lyr.mlp._run(x, h, im)
+        cache.seq_len = t0 + S
+        return ops.rmsnorm(h, pk["norm"], eps).view(B, S, D)
+
+
+class BailingMoeForCausalLM(nn.Module):
+    """Parameters under the reference's keys (model.*, lm_head.*, vis_head.*, diffloss.*) and the image-generation
+    entry points of :1543-1965."""
+
+    def __init__(self, config: BailingMoeConfig):
+        super().__init__()
+        self.config = config
+        self.model = BailingMoeModel(config)
+        self.vocab_size = config.vocab_size
+        self.norm_head = config.norm_head
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.vis_head = None
+        self.diffloss = None
+        self.num_generated_images = 0
+        self._pk = None
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def _apply(self, fn, *a, **k):
+        self._pk = None
+        return super()._apply(fn, *a, **k)
+
+    def setup_vishead_diffloss(self, diffloss_w=3072, diffloss_d=12, num_sampling_steps="16",
+                               gen_method="flow_matching_swiglu-4", hidden_size=2048, vis_head_arch="linear2-norm",
+                               image_emb_dim_for_gen=32):
+        """modeling_bailing_moe.py:1559-1584."""
+        assert vis_head_arch == "linear2-norm"
+        assert gen_method.startswith("flow_matching_swiglu-")
+        self.vis_head = nn.Sequential(nn.Linear(hidden_size, diffloss_w), nn.LayerNorm(diffloss_w, eps=1e-6))
+        self.diffloss = RectifiedFlowLoss(target_channels=image_emb_dim_for_gen, z_channels=diffloss_w,
+                                          width=diffloss_w, depth=diffloss_d, num_sampling_steps=num_sampling_steps,
+                                          mlp_mult=int(gen_method.split("-")[1]), grad_checkpointing=False)
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._pk = None
+
+    def reset_image_gen_status(self):
+        self.num_generated_images = 0
+
+    def get_input_embeddings(self):
+        return self.model.word_embeddings
+
+    def _pack(self):
+        dev = self.lm_head.weight.device
+        if self._pk is None or self._pk["dev"] != dev:
+            d = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+            pk = dict(dev=dev, lm_head=d(self.lm_head.weight))
+            if self.vis_head is not None:
+                pk.update(vh_w=d(self.vis_head[0].weight), vh_b=d(self.vis_head[0].bias),
+                          vh_g=d(self.vis_head[1].weight), vh_beta=d(self.vis_head[1].bias))
+            self._pk = pk
+        return self._pk
+
+    def new_cache(self, max_len: int, max_batch: int = 3) -> BailingKVCache:
+        return BailingKVCache(self.config, max_batch, max_len, self.lm_head.weight.device)
+
+    @torch.no_grad()
+    def compute_logit(self, hidden_states: torch.Tensor) -> torch.Tensor:
+        """:1604-1620 + the `.float()` of :1785/:1817: bf16 lm_head GEMM, logits returned in fp32."""
+        if self.norm_head:
+            raise NotImplementedError("norm_head is False on the Ming-UniVision path (config.json)")
+        pk = self._pack()
+        x = hidden_states.reshape(-1, hidden_states.shape[-1]).to(BF16).contiguous()
+        if x.shape[0] <= 8:
+            f32 = torch.empty((x.shape[0], self.vocab_size), dtype=torch.float32, device=x.device)
+            ops.gemv(x, pk["lm_head"], None, out_f32=f32)
+            return f32.view(*hidden_states.shape[:-1], -1)
+        return ops.linear(x, pk["lm_head"], None).float().view(*hidden_states.shape[:-1], -1)
+
+    @torch.no_grad()
+    def compute_vis_z(self, hidden_last: torch.Tensor) -> torch.Tensor:
+        """z = vis_head(h) = LayerNorm(Linear(h)) (:1571-1574, :1657-1662); h [B, D] -> z [B, Z] bf16."""
+        pk = self._pack()
+        y = _dense(hidden_last.contiguous(), pk["vh_w"], pk["vh_b"])
+        return ops.layernorm(y, pk["vh_g"], pk["vh_beta"], 1e-6)
+
+    @torch.no_grad()
+    def forward_for_image_generation_inner(self, inputs_embeds, attention_mask, position_ids, past_key_values,
+                                           image_gen_temperature=1.0, image_gen_text_cfg=3.0, image_gen_image_cfg=1.1,
+                                           noise=None, **kwargs):
+        """:1622-1673: one LLM step on the given embeddings, z = vis_head(last hidden), latent = diffloss.sample(z).
+        attention_mask: int32 [B, >= cache_len + S] key mask (see BailingMoeModel.forward_tokens)."""
+        hidden = self.model.forward_tokens(inputs_embeds, position_ids, past_key_values, key_mask=attention_mask)
+        z = self.compute_vis_z(hidden[:, -1])
+        x = self.diffloss.sample(z, temperature=image_gen_temperature, text_cfg=image_gen_text_cfg,
+                                 image_cfg=image_gen_image_cfg, noise=noise)
+        return x.unsqueeze(1), hidden
+
+    @torch.no_grad()
+    def generate_image(self, input_embeds, past_key_values: BailingKVCache, attention_mask, uncond_attention_mask,
+                       text_uncond_attention_mask, latent_to_sem_func, linear_proj, sem_to_pix_func,
+                       image_gen_text_cfg=3.0, image_gen_image_cfg=1.1, image_gen_temperature=1.0, noises=None):
+        """:1844-1965.  CFG rows are batch rows (B = 2: cond + uncond; B = 3: + text-uncond); the KV cache of the cond
+        prefill is replicated to the rows and trimmed back to row 0 afterwards.  As in the reference, the CFG scales
+        handed to the sampler are the hard-wired defaults 3.0 / 1.1: `generate_image` passes them under the wrong
+        keyword names so they never reach `diffloss.sample` — only the temperature propagates.
+        `noises` (test hook): sequence of [1, C] tensors replacing the per-token torch.randn draw."""
+        cfg = self.config
+        dev = input_embeds.device
+        assert attention_mask.shape[0] == 1
+        attention_mask = attention_mask.to(torch.int32)
+        if uncond_attention_mask is not None:
+            uncond_attention_mask = uncond_attention_mask.to(torch.int32)
+            n_c, n_u = attention_mask.shape[1], uncond_attention_mask.shape[1]
+            if n_u < n_c:
+                uncond_attention_mask = torch.cat((uncond_attention_mask, attention_mask[:, n_u:]), dim=1)
+            attention_mask = torch.cat((attention_mask, uncond_attention_mask), dim=0)
+        if text_uncond_attention_mask is not None and int(text_uncond_attention_mask.sum()) > 0:
+            text_uncond_attention_mask = text_uncond_attention_mask.to(torch.int32)
+            n_c, n_u = attention_mask.shape[1], text_uncond_attention_mask.shape[1]
+            if n_u < n_c:
+                text_uncond_attention_mask = torch.cat((text_uncond_attention_mask, attention_mask[0:1, n_u:]), dim=1)
+            if int((text_uncond_attention_mask == uncond_attention_mask).sum()) != uncond_attention_mask.numel():
+                attention_mask = torch.cat((attention_mask, text_uncond_attention_mask), dim=0)
+        B = attention_mask.shape[0]
+        n_tok = cfg.num_image_tokens_for_gen
+        cache = past_key_values
+        if B > 1:
+            input_embeds = input_embeds.repeat((B, 1, 1))
+            cache.repeat_rows(B)
+        # key mask buffer for the whole generation: prompt part now, one more "1" column per generated token
+        t_now = attention_mask.shape[1]
+        mask = torch.ones((B, t_now + n_tok + 1), dtype=torch.int32, device=dev)
+        mask[:, :t_now] = attention_mask.to(dev)
+        pos0 = (attention_mask.long().cumsum(-1) - 1)[:, -1:].to(dev)  # position of the current token per row
+        output_tokens, sem_cache, hidden = [], None, None
+        for token_idx in range(n_tok + 1):
+            position_ids = (pos0 + token_idx).to(torch.int32)
+            latent, hidden = self.forward_for_image_generation_inner(
+                inputs_embeds=input_embeds, attention_mask=mask, position_ids=position_ids, past_key_values=cache,
+                image_gen_temperature=image_gen_temperature,
+                noise=None if noises is None else noises[token_idx].to(dev))
+            if token_idx < n_tok:
+                feat = latent_to_sem_func(latent, past_key_values=sem_cache)
+                sem_cache = feat["past_key_values"]
+                output_token = feat["x_norm_patchtokens"]
+                output_tokens.append(output_token)
+                input_embeds = linear_proj(output_token)
+        cache.trim_rows()
+        final_mask = mask[:, :t_now + n_tok]
+        image_tensor = sem_to_pix_func(torch.cat(output_tokens, dim=1))
+        return image_tensor, hidden, final_mask

@@ -1,0 +1,123 @@
+"""B200-native multimodal wrapper: the continuous-visual-token surface of the reference's
+``mingunivision/modeling_bailingmm.py`` (MingUniVisionForConditionalGeneration :85-308) — `vision` (MingTok), `model`
+(BailingMoeForCausalLM with vis_head + diffloss), `linear_proj`, `extract_image_feature`, `prompt_wrap_vision`,
+`reset_inner_state`, and the image-generation entry that the reference reaches through HF `generate`
+(forward :1769-1796 -> generate_image).  HF GenerationMixin text decoding is glue outside SURVEY.md §8(a)-(e) (row f.1);
+`generate_image_from_prompt` drives prefill + generate_image directly, as SURVEY.md §7 recommends.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .mingtok.modeling_mingtok import MingTok, MingTokConfig
+from .modeling_bailing_moe import BailingMoeConfig, BailingMoeForCausalLM
+
+BF16 = torch.bfloat16
+
+
+class LinearProj(nn.Sequential):
+    """nn.Sequential(Linear(feature_dim, hidden), GELU, Linear(hidden, hidden)) — modeling_bailingmm.py:111-115 —
+    keys linear_proj.0.* / linear_proj.2.*; executed as two GEMMs with the exact-erf GELU fused into the first."""
+
+    def __init__(self, feature_dim: int, hidden: int):
+        super().__init__(nn.Linear(feature_dim, hidden), nn.GELU(), nn.Linear(hidden, hidden))
+        self._pk = None
+
+    def _apply(self, fn, *a, **k):
+        self._pk = None
+        return super()._apply(fn, *a, **k)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        dev = self[0].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("linear_proj (B200-native) runs on CUDA only; there is no CPU fallback")
+        if self._pk is None or self._pk[0].device != dev:
+            d = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()  # noqa: E731
+            self._pk = (d(self[0].weight), d(self[0].bias), d(self[2].weight), d(self[2].bias))
+        w0, b0, w2, b2 = self._pk
+        x2 = x.reshape(-1, x.shape[-1])
+        x2 = x2.contiguous() if x2.dtype == BF16 else ops.affine(x2, 1.0, 0.0)
+        if x2.shape[0] <= 8:
+            y = ops.gemv(ops.gemv(x2, w0, b0, epi=ops.EPI_GELU), w2, b2)
+        else:
+            y = ops.linear(ops.linear(x2, w0, b0, epi=ops.EPI_GELU), w2, b2)
+        return y.view(*x.shape[:-1], -1)
+
+
+class MingUniVisionForConditionalGeneration(nn.Module):
+    def __init__(self, llm_config: BailingMoeConfig, mingtok_config: MingTokConfig, vishead_diffloss_config: dict,
+                 mlp_depth: int = 2):
+        super().__init__()
+        if mlp_depth != 2:
+            raise NotImplementedError("mlp_depth = 2 on the Ming-UniVision path (config.json)")
+        self.vision = MingTok(mingtok_config)
+        self.model = BailingMoeForCausalLM(llm_config)
+        self.linear_proj = LinearProj(self.vision.feature_dim, llm_config.hidden_size)
+        vh = dict(vishead_diffloss_config, hidden_size=llm_config.hidden_size,
+                  image_emb_dim_for_gen=self.vision.latent_dim)
+        self.model.setup_vishead_diffloss(**vh)
+        self.past_key_values = None
+        self.past_attention_mask = None
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    def reset_inner_state(self):
+        """modeling_bailingmm.py:303-308."""
+        self.past_key_values = None
+        self.past_attention_mask = None
+        self.model.reset_image_gen_status()
+
+    @torch.no_grad()
+    def extract_image_feature(self, pixel_values, grid_thw=None):
+        """:131-138: MingTok encoder + semantic decoder, then linear_proj."""
+        feats = self.vision(pixel_values)["x_norm_patchtokens"]
+        return self.linear_proj(feats)
+
+    @torch.no_grad()
+    def prompt_wrap_vision(self, input_ids, inputs_embeds, vision_embeds, image_token_id=None):
+        """:152-177: scatter the image embeddings into the positions of the `<imagePatch>` token."""
+        if vision_embeds is None or input_ids is None:
+            return inputs_embeds, None
+        if len(vision_embeds.shape) == 3:
+            vision_embeds = vision_embeds.reshape(-1, vision_embeds.shape[-1])
+        image_token_id = self.model.config.image_patch_token if image_token_id is None else image_token_id
+        n_image_tokens = int((input_ids == image_token_id).sum())
+        if n_image_tokens != vision_embeds.shape[0]:
+            raise ValueError(f"Image features and image tokens do not match: tokens: {n_image_tokens}, "
+                             f"features {vision_embeds.shape[0]}")
+        image_mask = (input_ids == image_token_id)
+        out = inputs_embeds.clone()
+        out[image_mask] = vision_embeds.to(out.dtype)
+        return out, image_mask
+
+    @torch.no_grad()
+    def generate_image_from_prompt(self, input_ids, pixel_values=None, uncond_attention_mask=None,
+                                   text_uncond_attention_mask=None, image_gen_temperature=1.0, noises=None):
+        """Prefill `input_ids` (optionally with an input image scattered at its `<imagePatch>` positions), then run
+        BailingMoeForCausalLM.generate_image on the `<image>` start token — the sequence forward() performs when HF
+        generate feeds it that token (modeling_bailing_moe.py:1769-1796).  Returns (image [1,3,H,W], final mask)."""
+        llm, cfg = self.model, self.model.config
+        dev = input_ids.device
+        S = input_ids.shape[1]
+        emb = llm.model.embed(input_ids)
+        image_mask = None
+        if pixel_values is not None:
+            emb, image_mask = self.prompt_wrap_vision(input_ids, emb, self.extract_image_feature(pixel_values))
+        cache = llm.new_cache(max_len=S + 1 + cfg.num_image_tokens_for_gen + 8)
+        pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0)
+        llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
+        start = llm.model.embed(torch.tensor([[cfg.image_start_token]], device=dev))
+        am = torch.ones((1, S + 1), dtype=torch.int32, device=dev)
+        img, _, fmask = llm.generate_image(
+            input_embeds=start, past_key_values=cache, attention_mask=am, uncond_attention_mask=uncond_attention_mask,
+            text_uncond_attention_mask=text_uncond_attention_mask,
+            latent_to_sem_func=self.vision.forward_feature_decoder, linear_proj=self.linear_proj,
+            sem_to_pix_func=self.vision.forward_pixel_decoder, image_gen_temperature=image_gen_temperature,
+            noises=noises)
+        self.past_key_values, self.past_attention_mask = cache, fmask[0:1]
+        return img[0:1], fmask

@@ -315,3 +315,106 @@ def rf_euler_step(x_f32: torch.Tensor, x_bf16: torch.Tensor, v: torch.Tensor, dt
     B, C = x_f32.shape
     _lib.check(lib.mb_rf_euler_step(x_f32.data_ptr(), x_bf16.data_ptr(), v.data_ptr(), B, C, float(dt),
                                     float(text_cfg), float(image_cfg), _stream()), "mb_rf_euler_step")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Bailing-MoE AR step
+# ---------------------------------------------------------------------------------------------------------------
+def _iptr(t: torch.Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if t.dtype != torch.int32 or not t.is_cuda:
+        raise TypeError("expected a CUDA int32 tensor")
+    return t.data_ptr()
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+    _check_bf16(x, w)
+    lib = _lib.load()
+    x2 = _rows2d(x)
+    y = torch.empty_like(x2, memory_format=torch.contiguous_format)
+    _lib.check(lib.mb_rmsnorm(x2.data_ptr(), x2.stride(0), w.data_ptr(), y.data_ptr(), y.stride(0), x2.shape[0],
+                              x2.shape[1], float(eps), _stream()), "mb_rmsnorm")
+    return y.view(x.shape)
+
+
+def rope_kv_append(qkv: torch.Tensor, position_ids: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor,
+                   B: int, S: int, H: int, t: int, rope_theta: float, t_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """qkv [B*S, (H+2Hkv)*hd] -> rotated q [B*S, H*hd]; rotated K and V written into the caches at slots t..t+S-1."""
+    _check_bf16(qkv, kcache, vcache)
+    lib = _lib.load()
+    _, Hkv, Tmax, hd = kcache.shape
+    q = torch.empty((B * S, H * hd), dtype=BF16, device=qkv.device)
+    rc = lib.mb_rope_kv_append(qkv.data_ptr(), _iptr(position_ids), q.data_ptr(), kcache.data_ptr(), vcache.data_ptr(),
+                               B, S, H, Hkv, hd, Tmax, _iptr(t_dev), int(t), float(rope_theta), _stream())
+    _lib.check(rc, "mb_rope_kv_append")
+    return q
+
+
+def attn_decode_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, key_mask: torch.Tensor | None,
+                    H: int, T: int, t_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """q [B, H*128] against cache slots 0..T-1 (key_mask int32 [B, >=T], 0 = skip)."""
+    _check_bf16(q, kcache, vcache)
+    lib = _lib.load()
+    B, Hkv, Tmax, hd = kcache.shape
+    B = q.shape[0]
+    out = torch.empty((B, H * hd), dtype=BF16, device=q.device)
+    rc = lib.mb_attn_decode_gqa(q.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), _iptr(key_mask),
+                                key_mask.stride(0) if key_mask is not None else 0, out.data_ptr(), B, H, Hkv, hd, Tmax,
+                                _iptr(t_dev), int(T), hd ** -0.5, _stream())
+    _lib.check(rc, "mb_attn_decode_gqa")
+    return out
+
+
+def attn_prefill_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, B: int, S: int, H: int) -> torch.Tensor:
+    """Causal GQA attention of S new tokens (already appended at slots 0..S-1) for head_dim 64/128: q [B*S, H*hd]."""
+    _check_bf16(q, kcache, vcache)
+    lib = _lib.load()
+    _, Hkv, Tmax, hd = kcache.shape
+    out = torch.empty((B * S, H * hd), dtype=BF16, device=q.device)
+    rc = lib.mb_attn_fwd(q.data_ptr(), S * H * hd, H * hd, hd, kcache.data_ptr(), Hkv * Tmax * hd, hd, Tmax * hd,
+                         vcache.data_ptr(), Hkv * Tmax * hd, hd, Tmax * hd, out.data_ptr(), S * H * hd, H * hd, hd,
+                         B, S, S, H, Hkv, hd, hd ** -0.5, 1, _stream())
+    _lib.check(rc, "mb_attn_fwd")
+    return out
+
+
+def router_topk(logits: torch.Tensor, k: int, renorm: bool, logits_img: torch.Tensor | None = None,
+                image_mask: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+    _check_bf16(logits, logits_img)
+    lib = _lib.load()
+    T, E = logits.shape
+    idx = torch.empty((T, k), dtype=torch.int32, device=logits.device)
+    w = torch.empty((T, k), dtype=torch.float32, device=logits.device)
+    if image_mask is not None and image_mask.dtype != torch.uint8:
+        raise TypeError("image_mask must be uint8")
+    rc = lib.mb_router_topk(logits.contiguous().data_ptr(), _ptr(logits_img), _ptr(image_mask), idx.data_ptr(),
+                            w.data_ptr(), T, E, k, int(renorm), _stream())
+    _lib.check(rc, "mb_router_topk")
+    return idx, w
+
+
+def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor,
+                shared: torch.Tensor | None, residual: torch.Tensor | None) -> torch.Tensor:
+    """moe_infer + shared-expert add + residual: x [T, D]; Wgu [E, 2I, D]; Wd [E, D, I]; idx int32 [T, k]; w fp32."""
+    _check_bf16(x, Wgu, Wd, shared, residual)
+    lib = _lib.load()
+    T, D = x.shape
+    E, I2, _ = Wgu.shape
+    I = I2 // 2
+    k = idx.shape[1]
+    dev = x.device
+    offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+    sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    hid = torch.empty((T * k, I), dtype=BF16, device=dev)
+    out_pairs = torch.empty((T * k, D), dtype=BF16, device=dev)
+    y = torch.empty((T, D), dtype=BF16, device=dev)
+    s = _stream()
+    _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, s), "mb_moe_sort")
+    _lib.check(lib.mb_moe_gate_up(x.contiguous().data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                                  hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
+    _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                               out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, k,
+                                  D, s), "mb_moe_combine")
+    return y

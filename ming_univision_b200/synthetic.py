@@ -210,7 +210,7 @@ VISHEAD_CONFIG = dict(diffloss_w=3072, diffloss_d=12, num_sampling_steps="16", g
                       hidden_size=2048, vis_head_arch="linear2-norm", image_emb_dim_for_gen=32)
 
 LLM_TINY_CONFIG = dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
-                       num_attention_heads=4, num_key_value_heads=2, head_dim=32, hidden_act="silu",
+                       num_attention_heads=4, num_key_value_heads=2, head_dim=128, hidden_act="silu",
                        use_qkv_bias=False, use_bias=False, rms_norm_eps=1e-5, max_position_embeddings=4096,
                        rope_theta=600000, rope_scaling=None, num_experts=8, num_shared_experts=1,
                        num_experts_per_tok=2, norm_topk_prob=True, moe_intermediate_size=64, first_k_dense_replace=0,

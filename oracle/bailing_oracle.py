@@ -92,6 +92,8 @@ def mlp(sd, prefix, x):
 def gate(sd, prefix, cfg, x2d):
     """BailingMoeGate.forward — :505-520."""
     logits = F.linear(x2d, sd[prefix + ".weight"])
+    if cfg.get("router_logits_bf16"):  # emulate the GPU regime: F.linear under bf16 autocast returns bf16 logits (:509)
+        logits = logits.to(torch.bfloat16).float()
     scores = logits.softmax(dim=-1, dtype=torch.float32)
     w, idx = torch.topk(scores, k=cfg["num_experts_per_tok"], dim=-1)
     if cfg["num_experts_per_tok"] > 1 and cfg.get("norm_topk_prob", True):

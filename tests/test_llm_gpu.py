@@ -1,0 +1,201 @@
+"""Bailing-MoE AR path on the GPU: operator kernels against PyTorch fp32 references of the same op, then the product
+modules (BailingMoeForCausalLM.generate_image through MingUniVisionForConditionalGeneration) against the fp32 oracle and
+the golden outputs of the UNMODIFIED reference's own `generate_image` (tests/golden/llm_tiny.npz).
+
+Stated tolerances: hidden states / z / logits of one step: relative L2 <= 2e-2; latents, features and image after the
+4-token AR loop with the RF sampler in the loop: relative L2 <= 5e-2 (bf16 everywhere vs an all-fp32 reference)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ming_univision_b200 import synthetic
+from oracle import bailing_oracle as L
+from parity_metrics import rel_l2
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev).to(BF16)
+
+
+def test_rmsnorm(cuda_device):
+    from ming_univision_b200 import ops
+
+    x = _rand((5, 2048), cuda_device, 2.0, 1)
+    w = (_rand((2048,), cuda_device, 0.1, 2).float() + 1).to(BF16)
+    y = ops.rmsnorm(x, w, 1e-5)
+    ref = L.rmsnorm(x.float().cpu(), w.float().cpu(), 1e-5)
+    assert ((y.float().cpu() - ref).abs() <= 2.0 ** -7 * ref.abs() + 1e-3).all()
+
+
+def test_rope_kv_append_and_decode_attention(cuda_device):
+    from ming_univision_b200 import ops
+
+    B, H, Hkv, hd, Tmax, theta = 3, 16, 4, 128, 64, 600000.0
+    kc = torch.zeros((B, Hkv, Tmax, hd), dtype=BF16, device=cuda_device)
+    vc = torch.zeros_like(kc)
+    T = 37
+    # fill the cache through the prefill form of the kernel (S = T tokens per row)
+    qkv = _rand((B * T, (H + 2 * Hkv) * hd), cuda_device, 1.0, 3)
+    pos = torch.stack([torch.arange(T) + 3 * b for b in range(B)]).to(torch.int32).to(cuda_device).reshape(-1)
+    q = ops.rope_kv_append(qkv, pos, kc, vc, B, T, H, 0, theta)
+    x = qkv.float().cpu().view(B, T, H + 2 * Hkv, hd)
+    cos, sin = L.rope_tables(hd, theta, 64)
+    p = pos.cpu().long().view(B, T)
+    c, s = cos[p].unsqueeze(2), sin[p].unsqueeze(2)
+    rq = x[:, :, :H] * c + L.rotate_half(x[:, :, :H]) * s
+    rk = x[:, :, H:H + Hkv] * c + L.rotate_half(x[:, :, H:H + Hkv]) * s
+    assert (q.float().cpu().view(B, T, H, hd) - rq).abs().max() < 5e-2
+    assert (kc[:, :, :T].float().cpu().permute(0, 2, 1, 3) - rk).abs().max() < 5e-2
+    assert torch.equal(vc[:, :, :T].cpu().permute(0, 2, 1, 3), qkv.cpu().view(B, T, H + 2 * Hkv, hd)[:, :, H + Hkv:])
+    # decode attention with a per-row key mask
+    qd = _rand((B, H * hd), cuda_device, 1.0, 4)
+    mask = torch.ones((B, Tmax), dtype=torch.int32, device=cuda_device)
+    mask[1, 2:9] = 0
+    mask[2, 20:30] = 0
+    out = ops.attn_decode_gqa(qd, kc, vc, mask, H, T)
+    kf = kc[:, :, :T].float().cpu().repeat_interleave(H // Hkv, dim=1)
+    vf = vc[:, :, :T].float().cpu().repeat_interleave(H // Hkv, dim=1)
+    sc = torch.einsum("bhd,bhtd->bht", qd.float().cpu().view(B, H, hd), kf) / math.sqrt(hd)
+    sc = sc.masked_fill(mask[:, None, :T].cpu() == 0, float("-inf"))
+    ref = torch.einsum("bht,bhtd->bhd", sc.softmax(-1), vf).reshape(B, H * hd)
+    assert (out.float().cpu() - ref).abs().max() < 2e-2
+    # prefill attention reading K/V from the cache == torch causal attention
+    a = ops.attn_prefill_gqa(q, kc, vc, B, T, H)
+    qf = q.float().cpu().view(B, T, H, hd).permute(0, 2, 1, 3)
+    sc = (qf @ kf.transpose(-1, -2)) / math.sqrt(hd)
+    sc = sc.masked_fill(torch.triu(torch.ones(T, T, dtype=torch.bool), 1), float("-inf"))
+    ref = (sc.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(B * T, H * hd)
+    assert (a.float().cpu() - ref).abs().max() < 3e-2
+
+
+def test_router_topk(cuda_device):
+    from ming_univision_b200 import ops
+
+    T, E, k = 37, 64, 6
+    lg = _rand((T, E), cuda_device, 2.0, 5)
+    lg_img = _rand((T, E), cuda_device, 2.0, 6)
+    im = (torch.arange(T) % 3 == 0).to(torch.uint8).to(cuda_device)
+    idx, w = ops.router_topk(lg, k, True, lg_img, im)
+    sel = torch.where(im.bool().cpu()[:, None], lg_img.float().cpu(), lg.float().cpu())
+    sc = sel.softmax(-1)
+    rw, ridx = torch.topk(sc, k, dim=-1)
+    rw = rw / rw.sum(-1, keepdim=True)
+    assert torch.equal(idx.cpu().long(), ridx)
+    assert torch.allclose(w.cpu(), rw, atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("T", [1, 3, 40])
+def test_moe_block_operator(cuda_device, T):
+    """BailingMoeSparseMoeBlock.forward (the MoE operator boundary) against the oracle's per-token expert loop."""
+    from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig, BailingMoeSparseMoeBlock
+
+    cfg = dict(synthetic.LLM_TINY_CONFIG, num_experts=16, num_experts_per_tok=6, moe_intermediate_size=96,
+               num_shared_experts=2)
+    sd_all = synthetic.llm_state_dict(dict(cfg, num_hidden_layers=1), None, None, seed=3)
+    pre = "model.layers.0.mlp."
+    sd = {k[len(pre):]: v for k, v in sd_all.items() if k.startswith(pre)}
+    with torch.device(cuda_device):
+        blk = BailingMoeSparseMoeBlock(BailingMoeConfig(**cfg))
+    blk.load_state_dict({k: v.to(cuda_device) for k, v in sd.items()}, strict=True)
+    blk = blk.to(BF16)
+    x = _rand((1, T, cfg["hidden_size"]), cuda_device, 1.0, 7)
+    im = (torch.arange(T) % 2 == 0).view(1, T).to(cuda_device)
+    y, (logits, idx) = blk(x, image_mask=im)
+    sdb = {k: v.to(BF16).float() for k, v in sd_all.items()}
+    ref, ridx = L.moe_block(sdb, "model.layers.0.mlp", dict(cfg, router_logits_bf16=True), x.float().cpu(), im.cpu())
+    # expert choice is discrete: a bf16 rounding flip of a near-tie may legitimately differ, so require (almost) all
+    # tokens to route identically and compare the outputs of those tokens
+    same = (idx.cpu().view(-1, 6) == ridx).all(dim=1)
+    assert same.float().mean() >= 0.9, f"only {int(same.sum())}/{T} tokens routed like the reference"
+    assert rel_l2(y.view(-1, y.shape[-1]).cpu()[same], ref.view(-1, ref.shape[-1])[same]) < 1e-2
+
+
+@pytest.fixture(scope="module")
+def tiny_model(cuda_device):
+    from ming_univision_b200.mingtok import MingTokConfig
+    from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig
+    from ming_univision_b200.modeling_bailingmm import MingUniVisionForConditionalGeneration
+
+    cfg, vh, tok = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG, synthetic.MINGTOK_TINY_CONFIG
+    with torch.device(cuda_device):
+        m = MingUniVisionForConditionalGeneration(BailingMoeConfig(**cfg), MingTokConfig(**tok), vh)
+    sd = {}
+    for k, v in synthetic.llm_state_dict(cfg, vh, tok["semantic_decoder"]["embed_dim"], 0).items():
+        sd[k if k.startswith("linear_proj.") else "model." + k] = v
+    for k, v in synthetic.mingtok_state_dict(tok, 0).items():
+        sd["vision." + k] = v
+    m.load_state_dict({k: v.to(cuda_device) for k, v in sd.items()}, strict=True)
+    return m.to(BF16)
+
+
+def test_prefill_and_cfg_step_vs_reference(tiny_model, cuda_device):
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    llm = tiny_model.model
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    S = ids.shape[1]
+    cache = llm.new_cache(max_len=32)
+    pos = torch.arange(S, device=cuda_device, dtype=torch.int32).unsqueeze(0)
+    h = llm.model.forward_tokens(llm.model.embed(ids), pos, cache,
+                                 image_mask=torch.from_numpy(g["prefill_image_mask"]).to(cuda_device))
+    assert rel_l2(h, torch.from_numpy(g["prefill_hidden"])) < 2e-2
+    logits = llm.compute_logit(h[:, -1])
+    assert logits.dtype == torch.float32
+    assert rel_l2(logits, torch.from_numpy(g["prefill_logits_last"])) < 2e-2
+    assert rel_l2(cache.k[0][0:1, :, :S], torch.from_numpy(g["prefill_k0"])) < 1e-2
+    assert rel_l2(cache.v[1][0:1, :, :S], torch.from_numpy(g["prefill_v1"])) < 1e-2
+    # one cached step, 2 CFG rows with a 2-D mask and per-row positions
+    cache.repeat_rows(2)
+    mask = torch.from_numpy(g["step_mask"]).to(torch.int32).to(cuda_device)
+    h2 = llm.model.forward_tokens(torch.from_numpy(g["step_x"]).to(cuda_device), torch.from_numpy(g["step_pos"]).to(cuda_device),
+                                  cache, key_mask=mask)
+    assert rel_l2(h2, torch.from_numpy(g["step_hidden"])) < 2e-2
+    z = llm.compute_vis_z(h2[:, -1])
+    assert rel_l2(z, torch.from_numpy(g["step_z"]).reshape(2, -1)) < 2e-2
+    assert cache.get_seq_length() == S + 1
+
+
+@pytest.mark.parametrize("name", ["t2i", "edit"])
+def test_generate_image_vs_reference(tiny_model, cuda_device, name):
+    """The product `generate_image` (LLM step -> vis_head -> RF sampler -> MingTok cached decode -> linear_proj, x4,
+    then the pixel decoder) against the reference's own generate_image (B = 2 and B = 3 CFG rows)."""
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    noises = [torch.from_numpy(n) for n in g[f"{name}_noises"]]
+    lats, feats = [], []
+    vision = tiny_model.vision
+    orig = vision.forward_feature_decoder
+
+    def spy(latent, past_key_values=None):
+        r = orig(latent, past_key_values=past_key_values)
+        lats.append(latent.float().cpu())
+        feats.append(r["x_norm_patchtokens"].float().cpu())
+        return r
+
+    vision.forward_feature_decoder = spy
+    try:
+        tm = torch.from_numpy(g[f"{name}_text_uncond"]).to(cuda_device)
+        img, fmask = tiny_model.generate_image_from_prompt(
+            ids, uncond_attention_mask=torch.from_numpy(g[f"{name}_uncond"]).to(cuda_device),
+            text_uncond_attention_mask=tm, image_gen_temperature=0.9, noises=noises)
+    finally:
+        vision.forward_feature_decoder = orig
+    ref_l, ref_f = torch.from_numpy(g[f"{name}_latents"]), torch.from_numpy(g[f"{name}_feats"])
+    got_l, got_f = torch.cat(lats, dim=1), torch.cat(feats, dim=1)
+    B = ref_l.shape[0]
+    assert got_l.shape == ref_l.shape and fmask.shape[0] == B
+    assert torch.equal(fmask.cpu().long(), torch.from_numpy(g[f"{name}_final_mask"]))
+    e_l, e_f = rel_l2(got_l, ref_l), rel_l2(got_f, ref_f)
+    e_i = rel_l2(img, torch.from_numpy(g[f"{name}_image"])[0:1])
+    print(f"generate_image {name} (B={B}): latents {e_l:.3e} feats {e_f:.3e} image {e_i:.3e}")
+    assert e_l < 5e-2 and e_f < 5e-2 and e_i < 5e-2
+    assert tiny_model.past_key_values.get_seq_length() == int(g[f"{name}_cache_len"])
+    assert tiny_model.past_key_values.batch == 1

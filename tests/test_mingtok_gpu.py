@@ -109,10 +109,14 @@ def test_full_size_recon_parity(full, cuda_device):
     assert e_lat < 3e-2 and e_feat < 3e-2 and e_rec < 3e-2
     assert d_psnr <= 0.01
     assert fd <= 1e-3
-    # golden samples of the unmodified reference (image 0 of the same seeded batch)
+    # golden samples of the unmodified reference (its own single-image input, regenerated from the seed)
     g = np.load(os.path.join(GOLD, "mingtok_full_256.npz"))
-    sel = recon[0:1].flatten()[torch.from_numpy(g["recon_idx"])]
-    assert rel_l2(sel, torch.from_numpy(g["recon_val"])) < 3e-2
+    img1 = synthetic.synthetic_images(1, 256, seed=int(g["img_seed"])).to(cuda_device)
+    out1 = model.forward(img1)
+    rec1 = model.forward_pixel_decoder(out1["x_norm_patchtokens"], out_dtype=torch.float32).cpu()
+    for key, got in (("latent", out1["latent"]), ("feats", out1["x_norm_patchtokens"]), ("recon", rec1)):
+        sel = got.float().cpu().flatten()[torch.from_numpy(g[key + "_idx"])]
+        assert rel_l2(sel, torch.from_numpy(g[key + "_val"])) < 3e-2, key
 
 
 def test_full_size_batch_invariance(full, cuda_device):
