@@ -159,33 +159,41 @@ attn_fwd_kernel(const AttnParams p) {
       }
     }
 
-    // ---- mask + online softmax (rows g and g+8 of this warp's 16)
+    // ---- mask + online softmax (rows g and g+8 of this warp's 16).  Scores stay UNSCALED; the softmax scale is folded
+    // into one FMA per element: p = ex2(s * scale_log2 - m * scale_log2).
     const int key0 = nb * kBN;
     const int qrow0 = q0 + warp * 16 + g;
+    const bool full_tile = (key0 + kBN <= p.Sk) && (!p.causal || key0 + kBN - 1 <= q0 + warp * 16 + shift);
     float m_new[2] = {m_run[0], m_run[1]};
+    if (!full_tile) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key0 + j * 8 + 2 * t + (e & 1);
+          const int qrow = qrow0 + ((e >> 1) << 3);
+          bool ok = key < p.Sk;
+          if (p.causal) ok = ok && (key <= qrow + shift);
+          if (!ok) s[j][e] = -INFINITY;
+        }
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = key0 + j * 8 + 2 * t + (e & 1);
-        const int qrow = qrow0 + ((e >> 1) << 3);
-        bool ok = key < p.Sk;
-        if (p.causal) ok = ok && (key <= qrow + shift);
-        const float val = ok ? s[j][e] * p.scale_log2 : -INFINITY;
-        s[j][e] = val;
-        m_new[e >> 1] = fmaxf(m_new[e >> 1], val);
-      }
+      m_new[0] = fmaxf(m_new[0], fmaxf(s[j][0], s[j][1]));
+      m_new[1] = fmaxf(m_new[1], fmaxf(s[j][2], s[j][3]));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 1));
       m_new[r] = fmaxf(m_new[r], __shfl_xor_sync(0xffffffffu, m_new[r], 2));
     }
-    float corr[2], msafe[2];
+    float corr[2], mneg[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      msafe[r] = (m_new[r] == -INFINITY) ? 0.f : m_new[r];
-      corr[r] = exp2f(m_run[r] - msafe[r]);  // m_run = -inf -> 0
+      const float msafe = (m_new[r] == -INFINITY) ? 0.f : m_new[r];
+      corr[r] = fast_ex2((m_run[r] - msafe) * p.scale_log2);  // m_run = -inf -> 0
+      mneg[r] = -msafe * p.scale_log2;
       m_run[r] = m_new[r];
       l_run[r] *= corr[r];
     }
@@ -194,7 +202,7 @@ attn_fwd_kernel(const AttnParams p) {
     for (int j = 0; j < 8; ++j) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float pv = exp2f(s[j][e] - msafe[e >> 1]);
+        const float pv = fast_ex2(fmaf(s[j][e], p.scale_log2, mneg[e >> 1]));
         s[j][e] = pv;
         rowsum[e >> 1] += pv;
       }

@@ -203,21 +203,34 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(b);
 }
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below
-// the bf16 output rounding) — ~14 instructions and two MUFU ops per element instead of erff()'s ~35, which matters
-// because the GEMM epilogue has a budget of ~30 issue slots per element at K = 1024 before it outlasts the MMAs.
+// the bf16 output rounding) on the MUFU rcp / ex2 units: ~13 issue slots per element.  This matters because the GEMM
+// epilogue has a budget of ~30 slots per element at K = 1024 before it outlasts the MMAs (erff() costs ~35; ncu on the
+// first version of this epilogue showed 35 instructions per element and a 33 % tensor pipe, profiles/r01).
+//   gelu(x) = x/2 + |x|/2 * erf(|x| / sqrt 2)
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * z * z);
-  const float erf_abs = fmaf(-p * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float e = fast_ex2(z * (z * -1.4426950408889634f));
+  const float erf_abs = fmaf(-(p * t), e, 1.0f);
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return x * fast_rcp(1.0f + fast_ex2(x * -1.4426950408889634f)); }
 
 }  // namespace mb
 
