@@ -152,7 +152,8 @@ def _dev_bf16(t: torch.Tensor, device) -> torch.Tensor:
 
 
 class _PackedBlock:
-    __slots__ = ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "ffn", "w1", "b1", "w2", "b2")
+    __slots__ = ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "ffn", "w1", "b1", "w2", "b2",
+                 "w12_ref", "b12_ref", "w3_ref")
 
     def __init__(self, blk: _Block, device):
         d = lambda t: _dev_bf16(t, device)  # noqa: E731
@@ -162,8 +163,10 @@ class _PackedBlock:
         self.n2w, self.n2b = d(blk.norm2.weight), d(blk.norm2.bias)
         if isinstance(blk.mlp, _SwiGLUFFN):
             self.ffn = "swiglu"
-            self.w1, self.b1, hp = ops.pack_swiglu(d(blk.mlp.w12.weight), d(blk.mlp.w12.bias))
-            self.w2, self.b2 = ops.pad_cols(d(blk.mlp.w3.weight), hp), d(blk.mlp.w3.bias)
+            # reference layout kept for the q_len = 1 decode step (HBM-streaming kernel), packed layout for the GEMM
+            self.w12_ref, self.b12_ref, self.w3_ref = d(blk.mlp.w12.weight), d(blk.mlp.w12.bias), d(blk.mlp.w3.weight)
+            self.w1, self.b1, hp = ops.pack_swiglu(self.w12_ref, self.b12_ref)
+            self.w2, self.b2 = ops.pad_cols(self.w3_ref, hp), d(blk.mlp.w3.bias)
         else:
             self.ffn = "gelu"
             self.w1, self.b1 = d(blk.mlp.fc1.weight), d(blk.mlp.fc1.bias)
@@ -184,14 +187,24 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, S: int, H: int, causal
 
 
 def _run_block_step(pb: _PackedBlock, x: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, t: int) -> torch.Tensor:
-    """One cached decode step of a CausalBlock: x is [B, D] (q_len == 1)."""
+    """One cached decode step of a CausalBlock: x is [B, D] (q_len == 1, B = CFG rows <= 8): every linear is a
+    weight-streaming pass (mb_gemv_bf16), HBM-bound."""
+    if x.shape[0] > 8:
+        h = ops.layernorm(x, pb.n1w, pb.n1b)
+        qkv = ops.linear(h, pb.qkv_w, pb.qkv_b)
+        a = ops.attention_hd64_decode(qkv, kc, vc, t)
+        ops.linear(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x)
+        h = ops.layernorm(x, pb.n2w, pb.n2b)
+        hid = ops.linear(h, pb.w1, pb.b1, epi=ops.EPI_SWIGLU)
+        ops.linear(hid, pb.w2, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x)
+        return x
     h = ops.layernorm(x, pb.n1w, pb.n1b)
-    qkv = ops.linear(h, pb.qkv_w, pb.qkv_b)
+    qkv = ops.gemv(h, pb.qkv_w, pb.qkv_b)
     a = ops.attention_hd64_decode(qkv, kc, vc, t)
-    ops.linear(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x)
+    ops.gemv(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x)
     h = ops.layernorm(x, pb.n2w, pb.n2b)
-    hid = ops.linear(h, pb.w1, pb.b1, epi=ops.EPI_SWIGLU)
-    ops.linear(hid, pb.w2, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x)
+    hid = ops.gemv(h, pb.w12_ref, pb.b12_ref, epi=ops.EPI_SWIGLU)
+    ops.gemv(hid, pb.w3_ref, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x)
     return x
 
 
