@@ -35,132 +35,134 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
   return r;
 }
 
-__device__ __forceinline__ void unpack8f(const uint4& q, float (&f)[8]) {
-  const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
-  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 // EPI: 0 bias, 1 gelu, 2 swiglu (W = [2H, K] reference layout, out has H columns), 3 residual, 4 silu, 5 gated residual
 //
-// Work decomposition: a CTA has 8 warps; KSPLIT consecutive warps share one output column and split its K range, so a
-// CTA produces 8 / KSPLIT columns per iteration.  KSPLIT is chosen on the host so that even a narrow layer
-// (w3: N = 3072, K = 8192) spreads over every warp slot of the GPU and each lane has all of its 16-byte loads in flight
-// at once.  Activations are staged ONCE per CTA in shared memory as fp32 (no per-use bf16 unpacking), MT is the exact
-// row count (no padding to a power of two): at M = 3 the inner loop is 8 unpack + 24 FMA + 6 LDS.128 per 16-byte
-// weight chunk, ~50 % of the issue slots at HBM speed.
-template <int MT, int EPI, int KSPLIT>
+// The streaming kernel must spend almost no issue slots per weight byte, or it cannot keep enough loads in flight to
+// reach HBM speed (a CUDA-core version needed ~110 instructions per 32 weight bytes per lane and topped out at ~40 % of
+// the copy bandwidth).  So the dot products run on the tensor cores, fed DIRECTLY from coalesced 16-byte global loads:
+//   * a warp owns a tile of 16 weight rows (x2 for SwiGLU: gate rows n.. and up rows n + H..); lane (g = lane / 4,
+//     t = lane % 4) loads 16 bytes of row g and of row g + 8 at K offset 32 kg + 8 t  — 64 contiguous bytes per row
+//     across the 4 lanes of a quad, every byte of W read exactly once;
+//   * those 8 + 8 bf16 are the A fragments of two mma.m16n8k16: the MMA's k index is a PERMUTATION of the memory order
+//     (lane t's elements {0,1} and {2,3} take k' = 2t, 2t+1 and 2t+8, 2t+9), which is harmless for a dot product as
+//     long as the B fragment uses the same permutation — and it does, because lane (g, t) reads activation row g (a
+//     token) at the same K offset 32 kg + 8 t from shared memory with one conflict-free 16-byte load;
+//   * n = 8 MMA columns = up to 8 tokens (rows >= M read a shared zero row).
+// Per 1 KB of weights a warp issues 2 LDG.128 + 1 LDS.128 + 2 HMMA.  KSPLIT warps of a CTA share one row tile and split
+// its K range (narrow layers still fill the GPU); their partial sums meet in shared memory.
+template <int EPI, int KSPLIT>
 __global__ void __launch_bounds__(kGemvThreads)
 gemv_bf16_kernel(const GemvParams p) {
-  constexpr int kRows = (EPI == MB_EPI_SWIGLU) ? 2 : 1;  // weight rows per output column
+  constexpr int kTiles = (EPI == MB_EPI_SWIGLU) ? 2 : 1;  // 16-row tiles per work item
   constexpr int kUnroll = (EPI == MB_EPI_SWIGLU) ? 4 : 8;
-  constexpr int kColsPerIter = (kGemvThreads / 32) / KSPLIT;
+  constexpr int kItemsPerIter = (kGemvThreads / 32) / KSPLIT;
   extern __shared__ __align__(16) uint8_t gemv_smem[];
-  float* sA = reinterpret_cast<float*>(gemv_smem);  // [MT][K] fp32
-  __shared__ float red[2][kGemvThreads / 32][kRows * MT];
+  __shared__ float red[2][kGemvThreads / 32][kTiles * 4][32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int K = p.K, kchunks = K >> 3;
+  const int kgroups = (kchunks + 3) >> 2;               // groups of 32 k
+  const int row_bytes = kgroups * 64 + 64;               // +64 B: consecutive token rows land in different bank halves
   const int n_out = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
 
-  for (int i = tid; i < MT * kchunks; i += kGemvThreads) {
-    const int m = i / kchunks, c = i % kchunks;
-    float f[8];
-    unpack8f(*reinterpret_cast<const uint4*>(p.A + m * p.lda + c * 8), f);
-    float4* dst = reinterpret_cast<float4*>(sA + m * K + c * 8);
-    dst[0] = make_float4(f[0], f[1], f[2], f[3]);
-    dst[1] = make_float4(f[4], f[5], f[6], f[7]);
+  // stage the activations: rows 0..M-1, then one zero row shared by the unused MMA columns
+  for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
+    const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (m < p.M && c < kchunks) v = *reinterpret_cast<const uint4*>(p.A + m * p.lda + c * 8);
+    *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = v;
   }
   __syncthreads();
+  const uint8_t* xrow = gemv_smem + min(g, p.M) * row_bytes + t * 16;
 
-  const int col_slot = warp / KSPLIT, ks = warp % KSPLIT;
-  const int per = (kchunks + KSPLIT - 1) / KSPLIT;
-  const int c_beg = ks * per, c_end = min(kchunks, c_beg + per);
-  const int iters = (n_out + gridDim.x * kColsPerIter - 1) / (gridDim.x * kColsPerIter);
+  const int item_slot = warp / KSPLIT, ks = warp % KSPLIT;
+  const int per = (kgroups + KSPLIT - 1) / KSPLIT;
+  const int kg_beg = ks * per, kg_end = min(kgroups, kg_beg + per);
+  const int n_items = (n_out + 15) / 16;
+  const int iters = (n_items + gridDim.x * kItemsPerIter - 1) / (gridDim.x * kItemsPerIter);
   for (int it = 0; it < iters; ++it) {
-    const int n_raw = (it * gridDim.x + blockIdx.x) * kColsPerIter + col_slot;
-    const bool valid = n_raw < n_out;
-    const int n = valid ? n_raw : n_out - 1;
-    const uint4* wrow[kRows];
-    wrow[0] = reinterpret_cast<const uint4*>(p.W + static_cast<int64_t>(n) * p.ldw);
-    if constexpr (kRows == 2) wrow[1] = reinterpret_cast<const uint4*>(p.W + static_cast<int64_t>(n + n_out) * p.ldw);
-    float acc[kRows][MT];
+    const int item = (it * gridDim.x + blockIdx.x) * kItemsPerIter + item_slot;
+    const bool item_valid = item < n_items;
+    const int n0 = (item_valid ? item : 0) * 16;
+    // the two rows this lane streams (clamped at the matrix edge; the results of clamped rows are never stored)
+    const __nv_bfloat16* wr[kTiles][2];
 #pragma unroll
-    for (int r = 0; r < kRows; ++r)
+    for (int tl = 0; tl < kTiles; ++tl) {
+      const int base = tl * n_out;
+      wr[tl][0] = p.W + static_cast<int64_t>(base + min(n0 + g, n_out - 1)) * p.ldw + t * 8;
+      wr[tl][1] = p.W + static_cast<int64_t>(base + min(n0 + g + 8, n_out - 1)) * p.ldw + t * 8;
+    }
+    float acc[kTiles][4];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
+    for (int tl = 0; tl < kTiles; ++tl) acc[tl][0] = acc[tl][1] = acc[tl][2] = acc[tl][3] = 0.f;
 
-    for (int c0 = c_beg + lane; c0 < c_end; c0 += 32 * kUnroll) {
-      uint4 w[kRows][kUnroll];
+    for (int kg0 = kg_beg; kg0 < kg_end; kg0 += kUnroll) {
+      uint4 w[kTiles][2][kUnroll];
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int c = c0 + 32 * u;
+        const int kg = kg0 + u;
+        const bool ok = kg < kg_end && (kg * 4 + t) < kchunks;
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) w[r][u] = (c < c_end) ? ldg_stream(wrow[r] + c) : make_uint4(0, 0, 0, 0);
+        for (int tl = 0; tl < kTiles; ++tl) {
+          w[tl][0][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][0] + kg * 32)) : make_uint4(0, 0, 0, 0);
+          w[tl][1][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][1] + kg * 32)) : make_uint4(0, 0, 0, 0);
+        }
       }
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
-        const int c = c0 + 32 * u;
-        if (c < c_end) {
-          float wf[kRows][8];
+        const int kg = kg0 + u;
+        if (kg < kg_end) {
+          const uint4 xb = *reinterpret_cast<const uint4*>(xrow + kg * 64);
 #pragma unroll
-          for (int r = 0; r < kRows; ++r) unpack8f(w[r][u], wf[r]);
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const float4 a0 = *reinterpret_cast<const float4*>(sA + m * K + c * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(sA + m * K + c * 8 + 4);
-#pragma unroll
-            for (int r = 0; r < kRows; ++r) {
-              float s = acc[r][m];
-              s = fmaf(wf[r][0], a0.x, s); s = fmaf(wf[r][1], a0.y, s); s = fmaf(wf[r][2], a0.z, s);
-              s = fmaf(wf[r][3], a0.w, s); s = fmaf(wf[r][4], a1.x, s); s = fmaf(wf[r][5], a1.y, s);
-              s = fmaf(wf[r][6], a1.z, s); s = fmaf(wf[r][7], a1.w, s);
-              acc[r][m] = s;
-            }
+          for (int tl = 0; tl < kTiles; ++tl) {
+            mma16816(acc[tl], w[tl][0][u].x, w[tl][1][u].x, w[tl][0][u].y, w[tl][1][u].y, xb.x, xb.y);
+            mma16816(acc[tl], w[tl][0][u].z, w[tl][1][u].z, w[tl][0][u].w, w[tl][1][u].w, xb.z, xb.w);
           }
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r)
-#pragma unroll
-      for (int m = 0; m < MT; ++m) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[r][m] += __shfl_xor_sync(0xffffffffu, acc[r][m], o);
-      }
     if constexpr (KSPLIT > 1) {
-      // combine the K-slices of the KSPLIT warps that share this column (double-buffered scratch, one barrier / iter)
-      float* slot = red[it & 1][warp];
-      if (lane == 0) {
+      // combine the K-slices of the KSPLIT warps that share this item (double-buffered scratch, one barrier / iter)
 #pragma unroll
-        for (int r = 0; r < kRows; ++r)
+      for (int tl = 0; tl < kTiles; ++tl)
 #pragma unroll
-          for (int m = 0; m < MT; ++m) slot[r * MT + m] = acc[r][m];
-      }
+        for (int e = 0; e < 4; ++e) red[it & 1][warp][tl * 4 + e][lane] = acc[tl][e];
       __syncthreads();
       if (ks == 0) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r)
+        for (int tl = 0; tl < kTiles; ++tl)
 #pragma unroll
-          for (int m = 0; m < MT; ++m) {
+          for (int e = 0; e < 4; ++e) {
             float v = 0.f;
 #pragma unroll
-            for (int j = 0; j < KSPLIT; ++j) v += red[it & 1][warp + j][r * MT + m];
-            acc[r][m] = v;
+            for (int j = 0; j < KSPLIT; ++j) v += red[it & 1][warp + j][tl * 4 + e][lane];
+            acc[tl][e] = v;
           }
       }
     }
-    if (ks == 0 && valid) {
-      // lane m finalises row m (every lane holds the full sums)
+    if (ks == 0 && item_valid) {
+      // accumulator element e: row n0 + g + 8 (e >> 1), token 2 t + (e & 1)
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        if (lane == m) {
+      for (int e = 0; e < 4; ++e) {
+        const int n = n0 + g + 8 * (e >> 1);
+        const int m = 2 * t + (e & 1);
+        if (n < n_out && m < p.M) {
           float o;
           if constexpr (EPI == MB_EPI_SWIGLU) {
-            const float x1 = bf16_round(acc[0][m] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f));
-            const float x2 = bf16_round(acc[kRows - 1][m] + (p.bias ? __bfloat162float(p.bias[n + n_out]) : 0.f));
+            const float x1 = bf16_round(acc[0][e] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f));
+            const float x2 = bf16_round(acc[kTiles - 1][e] + (p.bias ? __bfloat162float(p.bias[n + n_out]) : 0.f));
             o = bf16_round(silu(x1)) * x2;
           } else {
-            float v = acc[0][m] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f);
+            float v = acc[0][e] + (p.bias ? __bfloat162float(p.bias[n]) : 0.f);
             if constexpr (EPI == MB_EPI_GELU) v = gelu_erf(bf16_round(v));
             if constexpr (EPI == MB_EPI_SILU) v = silu(bf16_round(v));
             if constexpr (EPI == MB_EPI_RESIDUAL) v = bf16_round(v) + __bfloat162float(p.res[m * p.ldr + n]);
@@ -179,18 +181,18 @@ gemv_bf16_kernel(const GemvParams p) {
   }
 }
 
-template <int MT, int KSPLIT>
+template <int KSPLIT>
 static int launch_gemv_ks(const GemvParams& p, int epi, int grid, size_t smem, cudaStream_t stream) {
-#define MB_GEMV_CASE(E_)                                                                                  \
-  case E_: {                                                                                              \
-    static bool attr_set = false;                                                                         \
-    if (!attr_set) {                                                                                      \
-      MB_CHECK_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<MT, E_, KSPLIT>,                                \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));       \
-      attr_set = true;                                                                                    \
-    }                                                                                                     \
-    gemv_bf16_kernel<MT, E_, KSPLIT><<<grid, kGemvThreads, smem, stream>>>(p);                            \
-    break;                                                                                                \
+#define MB_GEMV_CASE(E_)                                                                                       \
+  case E_: {                                                                                                   \
+    static bool attr_set = false;                                                                              \
+    if (!attr_set) {                                                                                           \
+      MB_CHECK_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<E_, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         160 * 1024));                                                         \
+      attr_set = true;                                                                                         \
+    }                                                                                                          \
+    gemv_bf16_kernel<E_, KSPLIT><<<grid, kGemvThreads, smem, stream>>>(p);                                     \
+    break;                                                                                                     \
   }
   switch (epi) {
     MB_GEMV_CASE(MB_EPI_BIAS)
@@ -206,16 +208,6 @@ static int launch_gemv_ks(const GemvParams& p, int epi, int grid, size_t smem, c
 #undef MB_GEMV_CASE
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
-}
-
-template <int MT>
-static int launch_gemv(const GemvParams& p, int epi, int ksplit, int grid, size_t smem, cudaStream_t stream) {
-  switch (ksplit) {
-    case 1: return launch_gemv_ks<MT, 1>(p, epi, grid, smem, stream);
-    case 2: return launch_gemv_ks<MT, 2>(p, epi, grid, smem, stream);
-    case 4: return launch_gemv_ks<MT, 4>(p, epi, grid, smem, stream);
-    default: return launch_gemv_ks<MT, 8>(p, epi, grid, smem, stream);
-  }
 }
 
 }  // namespace mb
@@ -237,8 +229,9 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
   if (epi == MB_EPI_RESIDUAL || epi == MB_EPI_GATED)
     MB_CHECK_ARG(residual != nullptr, MB_ERR_SHAPE, "mb_gemv_bf16: residual epilogue without a residual pointer");
   if (epi == MB_EPI_GATED) MB_CHECK_ARG(gate != nullptr, MB_ERR_SHAPE, "mb_gemv_bf16: GATED epilogue without a gate");
-  const size_t smem = static_cast<size_t>(M) * K * 4;
-  MB_CHECK_ARG(smem <= 200 * 1024, MB_ERR_SHAPE, "mb_gemv_bf16: M*K too large for shared memory (M=%d K=%d)", M, K);
+  const int kgroups_h = (K / 8 + 3) / 4;
+  const size_t smem = static_cast<size_t>(M + 1) * (kgroups_h * 64 + 64);
+  MB_CHECK_ARG(smem <= 160 * 1024, MB_ERR_SHAPE, "mb_gemv_bf16: M*K too large for shared memory (M=%d K=%d)", M, K);
 
   GemvParams p;
   p.A = static_cast<const __nv_bfloat16*>(A); p.lda = lda;
@@ -250,25 +243,21 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.out_f32 = static_cast<float*>(out_f32);
   p.M = M; p.N = N; p.K = K;
   const int n_out = (epi == MB_EPI_SWIGLU) ? N / 2 : N;
-  // K-split: enough (column, K-slice) work items to occupy ~16 warps on every SM, but >= 2 chunks per lane and slice
-  const int kchunks = K / 8;
+  // K-split: enough (row tile, K-slice) work items to give every SM ~8 busy warps, but >= 8 k-groups per slice
+  const int n_items = (n_out + 15) / 16;
   int ksplit = 1;
-  while (ksplit < 8 && static_cast<long>(n_out) * ksplit < static_cast<long>(num_sms()) * 16 &&
-         kchunks / (ksplit * 2) >= 64)
+  while (ksplit < 8 && static_cast<long>(n_items) * ksplit < static_cast<long>(num_sms()) * 8 &&
+         kgroups_h / (ksplit * 2) >= 8)
     ksplit *= 2;
-  const int cols_per_iter = (kGemvThreads / 32) / ksplit;
-  const int units = (n_out + cols_per_iter - 1) / cols_per_iter;
-  const int per_sm = smem <= 64 * 1024 ? 3 : (smem <= 100 * 1024 ? 2 : 1);
+  const int items_per_iter = (kGemvThreads / 32) / ksplit;
+  const int units = (n_items + items_per_iter - 1) / items_per_iter;
+  const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
   int grid = num_sms() * per_sm;
   if (grid > units) grid = units;
-  switch (M) {
-    case 1: return launch_gemv<1>(p, epi, ksplit, grid, smem, stream);
-    case 2: return launch_gemv<2>(p, epi, ksplit, grid, smem, stream);
-    case 3: return launch_gemv<3>(p, epi, ksplit, grid, smem, stream);
-    case 4: return launch_gemv<4>(p, epi, ksplit, grid, smem, stream);
-    case 5: return launch_gemv<5>(p, epi, ksplit, grid, smem, stream);
-    case 6: return launch_gemv<6>(p, epi, ksplit, grid, smem, stream);
-    case 7: return launch_gemv<7>(p, epi, ksplit, grid, smem, stream);
-    default: return launch_gemv<8>(p, epi, ksplit, grid, smem, stream);
+  switch (ksplit) {
+    case 1: return launch_gemv_ks<1>(p, epi, grid, smem, stream);
+    case 2: return launch_gemv_ks<2>(p, epi, grid, smem, stream);
+    case 4: return launch_gemv_ks<4>(p, epi, grid, smem, stream);
+    default: return launch_gemv_ks<8>(p, epi, grid, smem, stream);
   }
 }
