@@ -128,9 +128,10 @@ int mb_attn_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const v
 
 /* Decode-step attention against a static KV cache (semantic decoder, q_len = 1; layers/attention.py:213-239 with
  * past_key_value).  qkv[B, 3, H, 64] holds the new token; its K/V are appended at position `t` of
- * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t. */
+ * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t.
+ * The position is t + *t_dev when t_dev (an optional DEVICE int32 scalar) is given — see the AR-step note below. */
 int mb_attn_hd64_decode(const void* qkv, void* kcache, void* vcache, void* out, int B, int H, int t, int Tmax,
-                        float scale, void* stream);
+                        float scale, const int32_t* t_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MingTok data-movement operators
@@ -177,8 +178,8 @@ int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, flo
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Bailing-MoE AR step (mingunivision/modeling_bailing_moe.py).  `t_dev` arguments are optional DEVICE int32 scalars
- * holding the current KV-cache length (so one captured CUDA graph can be replayed for every token); when NULL the
- * host value `t_host` is used.
+ * holding the current KV-cache length, so ONE captured CUDA graph can be replayed for every generated token; the
+ * effective value is always  (t_dev ? *t_dev : 0) + t_host.
  * ------------------------------------------------------------------------------------------------------------- */
 /* BailingMoeRMSNorm.forward (:131-136): y = bf16(w * (x * rsqrt(mean(x^2) + eps))), fp32 statistics. */
 int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int dim, float eps,

@@ -39,7 +39,7 @@ SIGNATURES = {
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
     "mb_attn_fwd": [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _vp, _i64, _i64, _i64, _i, _i,
                     _i, _i, _i, _i, _f, _i, _vp],
-    "mb_attn_hd64_decode": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "mb_attn_hd64_decode": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp],
     "mb_patchify": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_fill_cls_row": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_group_mean": [_vp, _i64, _vp, _i, _i, _i, _vp],

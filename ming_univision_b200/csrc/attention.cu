@@ -327,8 +327,9 @@ static int launch_attn(const AttnParams& p, int B, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 attn_hd64_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kcache,
-                        __nv_bfloat16* __restrict__ vcache, __nv_bfloat16* __restrict__ out, int B, int H, int t,
-                        int Tmax, float scale) {
+                        __nv_bfloat16* __restrict__ vcache, __nv_bfloat16* __restrict__ out, int B, int H, int t_host,
+                        int Tmax, float scale, const int32_t* __restrict__ t_dev) {
+  const int t = (t_dev ? *t_dev : 0) + t_host;
   const int warp_global = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (warp_global >= B * H) return;
@@ -393,16 +394,16 @@ extern "C" int mb_attn_hd64(const void* qkv, void* out, int B, int S, int H, flo
 }
 
 extern "C" int mb_attn_hd64_decode(const void* qkv, void* kcache, void* vcache, void* out, int B, int H, int t,
-                                   int Tmax, float scale, void* stream_) {
+                                   int Tmax, float scale, const int32_t* t_dev, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_attn_hd64_decode: no sm_100 device");
-  MB_CHECK_ARG(B >= 0 && H >= 1 && t >= 0 && t < Tmax, MB_ERR_SHAPE,
+  MB_CHECK_ARG(B >= 0 && H >= 1 && t >= 0 && (t_dev != nullptr || t < Tmax), MB_ERR_SHAPE,
                "mb_attn_hd64_decode: position t=%d outside the cache (Tmax=%d)", t, Tmax);
   if (B == 0) return MB_OK;
   const int warps = B * H;
   attn_hd64_decode_kernel<<<(warps + 3) / 4, 128, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(kcache),
-      static_cast<__nv_bfloat16*>(vcache), static_cast<__nv_bfloat16*>(out), B, H, t, Tmax, scale);
+      static_cast<__nv_bfloat16*>(vcache), static_cast<__nv_bfloat16*>(out), B, H, t, Tmax, scale, t_dev);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

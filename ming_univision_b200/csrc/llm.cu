@@ -81,7 +81,7 @@ rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
                       const int32_t* __restrict__ t_dev, int t_host, float theta) {
   const int row = blockIdx.x;  // b * S + s
   const int b = row / S, s = row % S;
-  const int slot = (t_dev ? *t_dev : t_host) + s;
+  const int slot = (t_dev ? *t_dev : 0) + t_host + s;
   const int pos = position_ids[row];
   const int nheads = H + 2 * Hkv;
   const int half = hd / 2;
@@ -128,7 +128,7 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
   const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (wid >= B * H) return;
   const int b = wid / H, h = wid % H, hk = h / (H / Hkv);
-  const int T = t_dev ? *t_dev : t_host;
+  const int T = (t_dev ? *t_dev : 0) + t_host;
   const uint2 qq = *reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4);
   const float2 q0 = unpack_bf16x2(qq.x), q1 = unpack_bf16x2(qq.y);
   const __nv_bfloat16* kc = kcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;

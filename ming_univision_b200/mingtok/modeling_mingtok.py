@@ -139,9 +139,15 @@ class MingTokKVCache:
         self.seq_len = 0
         self.max_len = max_len
         self.batch = batch
+        # device-side copy of seq_len for CUDA-graph replay of the decode step (kept in sync by the graph itself)
+        self.t_dev = torch.zeros((1,), dtype=torch.int32, device=device)
 
     def get_seq_length(self, layer_idx: int = 0) -> int:
         return self.seq_len
+
+    def reset(self) -> None:
+        self.seq_len = 0
+        self.t_dev.zero_()
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -186,13 +192,14 @@ def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, S: int, H: int, causal
     return x
 
 
-def _run_block_step(pb: _PackedBlock, x: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, t: int) -> torch.Tensor:
+def _run_block_step(pb: _PackedBlock, x: torch.Tensor, kc: torch.Tensor, vc: torch.Tensor, t: int,
+                    t_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One cached decode step of a CausalBlock: x is [B, D] (q_len == 1, B = CFG rows <= 8): every linear is a
     weight-streaming pass (mb_gemv_bf16), HBM-bound."""
     if x.shape[0] > 8:
         h = ops.layernorm(x, pb.n1w, pb.n1b)
         qkv = ops.linear(h, pb.qkv_w, pb.qkv_b)
-        a = ops.attention_hd64_decode(qkv, kc, vc, t)
+        a = ops.attention_hd64_decode(qkv, kc, vc, t, t_dev)
         ops.linear(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x)
         h = ops.layernorm(x, pb.n2w, pb.n2b)
         hid = ops.linear(h, pb.w1, pb.b1, epi=ops.EPI_SWIGLU)
@@ -200,7 +207,7 @@ def _run_block_step(pb: _PackedBlock, x: torch.Tensor, kc: torch.Tensor, vc: tor
         return x
     h = ops.layernorm(x, pb.n1w, pb.n1b)
     qkv = ops.gemv(h, pb.qkv_w, pb.qkv_b)
-    a = ops.attention_hd64_decode(qkv, kc, vc, t)
+    a = ops.attention_hd64_decode(qkv, kc, vc, t, t_dev)
     ops.gemv(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x)
     h = ops.layernorm(x, pb.n2w, pb.n2b)
     hid = ops.gemv(h, pb.w12_ref, pb.b12_ref, epi=ops.EPI_SWIGLU)
@@ -378,13 +385,26 @@ class MingTok(PreTrainedModel):
         t = cache.seq_len
         if t >= cache.max_len:
             raise ValueError(f"semantic-decoder KV cache is full ({cache.max_len} tokens)")
-        lat = ops.affine(hidden_states.reshape(B, -1), self.scaling_factor, self.mean)
+        xn = self._decode_step(hidden_states.reshape(B, -1), cache, t, None)
+        cache.seq_len = t + 1
+        cache.t_dev.fill_(t + 1)
+        return {"x_prenorm": None, "x_norm_patchtokens": xn.view(B, 1, -1), "past_key_values": cache}
+
+    @torch.no_grad()
+    def _decode_step(self, latent_norm: torch.Tensor, cache: MingTokKVCache, t: int,
+                     t_dev: Optional[torch.Tensor]) -> torch.Tensor:
+        """One cached causal step on a normalised latent [B, C] (fp32 or bf16) at position t (+ *t_dev): fixed shapes,
+        no host sync — capturable in a CUDA graph (the AR-step graph of BailingMoeForCausalLM.generate_image)."""
+        pk = self._pack()
+        lat = ops.affine(latent_norm, self.scaling_factor, self.mean)
         x = ops.inproj_repeat(lat, pk.in_w, pk.in_b)
         for i, pb in enumerate(pk.sem_blocks):
-            _run_block_step(pb, x, cache.k[i], cache.v[i], t)
-        cache.seq_len = t + 1
-        xn = ops.layernorm(x, pk.sem_nw, pk.sem_nb)
-        return {"x_prenorm": None, "x_norm_patchtokens": xn.view(B, 1, -1), "past_key_values": cache}
+            _run_block_step(pb, x, cache.k[i], cache.v[i], t, t_dev)
+        return ops.layernorm(x, pk.sem_nw, pk.sem_nb)
+
+    def new_decode_cache(self, batch: int, max_len: int = 264) -> MingTokKVCache:
+        pk = self._pack()
+        return MingTokKVCache(len(pk.sem_blocks), batch, self.semantic_decoder.num_heads, max_len, pk.device)
 
     @torch.no_grad()
     def forward_feature_decoder_wo_cache(self, hidden_states):

@@ -271,17 +271,23 @@ class BailingMoeModel(nn.Module):
 
     @torch.no_grad()
     def forward_tokens(self, inputs_embeds: torch.Tensor, position_ids: torch.Tensor, cache: BailingKVCache,
-                       key_mask: Optional[torch.Tensor] = None, image_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       key_mask: Optional[torch.Tensor] = None, image_mask: Optional[torch.Tensor] = None,
+                       t_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
         """BailingMoeModel.forward (:1391-1540) for this path's two regimes.
         inputs_embeds [B, S, D]; position_ids int [B, S]; the S new tokens are appended at cache slots seq_len..;
         S == 1: cached decode of B rows, `key_mask` int32 [B, >= seq_len+1] marks attendable slots (2-D padding mask of
-        the CFG rows); S > 1: causal prefill into an empty cache (all-ones mask).  Returns final-norm hidden [B, S, D]."""
+        the CFG rows); S > 1: causal prefill into an empty cache (all-ones mask).  Returns final-norm hidden [B, S, D].
+        With `t_dev` (device int32 scalar = current cache length, S must be 1) the call has fixed shapes and reads the
+        position from device memory, so it can be captured in a CUDA graph; the caller advances cache.seq_len."""
         pk = self._pack()
         cfg = self.config
         B, S, D = inputs_embeds.shape
         H, hd = cfg.num_attention_heads, cfg.head_dim
-        t0 = cache.seq_len
-        if t0 + S > cache.max_len:
+        graph_mode = t_dev is not None
+        if graph_mode and S != 1:
+            raise ValueError("t_dev is for the single-token decode step")
+        t0 = 0 if graph_mode else cache.seq_len
+        if not graph_mode and t0 + S > cache.max_len:
             raise ValueError(f"KV cache overflow: {t0}+{S} > {cache.max_len}")
         if S > 1 and (t0 != 0 or (key_mask is not None and bool((key_mask[:, :S] == 0).any()))):
             raise NotImplementedError("multi-token forward is implemented for a causal prefill into an empty cache")
@@ -293,15 +299,16 @@ class BailingMoeModel(nn.Module):
             x = ops.rmsnorm(h, lp["ln1"], eps)
             qkv = _dense(x, lp["qkv_w"], lp["qkv_b"])
             # rows 0..B-1 of the [Bmax, Hkv, Tmax, hd] cache are a contiguous prefix the kernels index directly
-            q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta)
+            q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta, t_dev)
             if S == 1:
-                a = ops.attn_decode_gqa(q, cache.k[li], cache.v[li], key_mask, H, t0 + 1)
+                a = ops.attn_decode_gqa(q, cache.k[li], cache.v[li], key_mask, H, t0 + 1, t_dev)
             else:
                 a = ops.attn_prefill_gqa(q, cache.k[li], cache.v[li], B, S, H)
             _dense(a, lp["dense_w"], lp["dense_b"], epi=ops.EPI_RESIDUAL, residual=h, out=h)
             x = ops.rmsnorm(h, lp["ln2"], eps)
             h, _, _ = lyr.mlp._run(x, h, im)
-        cache.seq_len = t0 + S
+        if not graph_mode:
+            cache.seq_len = t0 + S
         return ops.rmsnorm(h, pk["norm"], eps).view(B, S, D)
 
 
@@ -320,11 +327,14 @@ class BailingMoeForCausalLM(nn.Module):
         self.diffloss = None
         self.num_generated_images = 0
         self._pk = None
+        self.use_cuda_graph = True
+        self._gen_ws = {}
         for p in self.parameters():
             p.requires_grad_(False)
 
     def _apply(self, fn, *a, **k):
         self._pk = None
+        self._gen_ws = {}
         return super()._apply(fn, *a, **k)
 
     def setup_vishead_diffloss(self, diffloss_w=3072, diffloss_d=12, num_sampling_steps="16",
@@ -425,6 +435,9 @@ class BailingMoeForCausalLM(nn.Module):
         if B > 1:
             input_embeds = input_embeds.repeat((B, 1, 1))
             cache.repeat_rows(B)
+        if self.use_cuda_graph and self._graphable(latent_to_sem_func, linear_proj):
+            return self._generate_image_graphed(input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func,
+                                                linear_proj, sem_to_pix_func, image_gen_temperature, noises)
         # key mask buffer for the whole generation: prompt part now, one more "1" column per generated token
         t_now = attention_mask.shape[1]
         mask = torch.ones((B, t_now + n_tok + 1), dtype=torch.int32, device=dev)
@@ -447,3 +460,91 @@ class BailingMoeForCausalLM(nn.Module):
         final_mask = mask[:, :t_now + n_tok]
         image_tensor = sem_to_pix_func(torch.cat(output_tokens, dim=1))
         return image_tensor, hidden, final_mask
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # CUDA-graph fast path of the AR visual-token loop: one replay per generated token
+    # ---------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _graphable(latent_to_sem_func, linear_proj) -> bool:
+        """The whole token step can be captured when the callbacks are this package's own modules (fixed shapes, no
+        host sync): MingTok.forward_feature_decoder and LinearProj."""
+        from .mingtok.modeling_mingtok import MingTok
+        from .modeling_bailingmm import LinearProj
+
+        vision = getattr(latent_to_sem_func, "__self__", None)
+        return isinstance(vision, MingTok) and getattr(latent_to_sem_func, "__name__", "") == "forward_feature_decoder" \
+            and isinstance(linear_proj, LinearProj)
+
+    def _token_step(self, ws) -> None:
+        """LLM step -> vis_head -> RF sampler (hard-wired CFG 3.0 / 1.1) -> semantic-decoder step -> linear_proj, all on
+        static buffers and device-side positions (forward_for_image_generation_inner + the loop body of generate_image)."""
+        hidden = self.model.forward_tokens(ws["embeds"], ws["pos"], ws["cache"], key_mask=ws["mask"], t_dev=ws["t_llm"])
+        ws["hidden"].copy_(hidden)
+        z = self.compute_vis_z(hidden[:, -1])
+        ws["x"].copy_(ws["noise"].expand(ws["B"], -1) * ws["temperature"])
+        self.diffloss._sample_body(self.diffloss._pack(), z, ws["x"], 3.0, 1.1)
+        feat = ws["vision"]._decode_step(ws["x"], ws["sem_cache"], 0, ws["sem_cache"].t_dev)
+        ws["feats"].index_copy_(1, ws["t_idx"], feat.unsqueeze(1))
+        ws["embeds"].copy_(ws["linear_proj"](feat.unsqueeze(1)))
+        ws["t_llm"].add_(1)
+        ws["sem_cache"].t_dev.add_(1)
+        ws["t_idx"].add_(1)
+        ws["pos"].add_(1)
+
+    def _generate_image_graphed(self, input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func, linear_proj,
+                                sem_to_pix_func, temperature, noises):
+        dev = input_embeds.device
+        vision = latent_to_sem_func.__self__
+        t_now = attention_mask.shape[1]
+        if cache.seq_len != t_now - 1 or cache.seq_len + n_tok + 1 > cache.max_len:
+            raise ValueError("KV cache / attention mask length mismatch or cache too small for the generation")
+        key = (B, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len)
+        ws = self._gen_ws.get(key)
+        if ws is None:
+            C, D, F = self.diffloss.in_channels, self.config.hidden_size, vision.feature_dim
+            ws = dict(B=B, temperature=float(temperature), cache=cache, vision=vision, linear_proj=linear_proj,
+                      embeds=torch.zeros((B, 1, D), dtype=BF16, device=dev),
+                      hidden=torch.zeros((B, 1, D), dtype=BF16, device=dev),
+                      noise=torch.zeros((1, C), dtype=torch.float32, device=dev),
+                      x=torch.zeros((B, C), dtype=torch.float32, device=dev),
+                      feats=torch.zeros((B, n_tok + 1, F), dtype=BF16, device=dev),
+                      pos=torch.zeros((B, 1), dtype=torch.int32, device=dev),
+                      mask=torch.ones((B, cache.max_len), dtype=torch.int32, device=dev),
+                      t_llm=torch.zeros((1,), dtype=torch.int32, device=dev),
+                      t_idx=torch.zeros((1,), dtype=torch.int64, device=dev),
+                      sem_cache=vision.new_decode_cache(B, n_tok + 8), graph=None)
+            self._gen_ws = {key: ws}  # one workspace at a time (a new cache / batch size re-captures)
+
+        def reset_state():
+            ws["embeds"].copy_(input_embeds.to(BF16))
+            ws["mask"].fill_(1)
+            ws["mask"][:, :t_now] = attention_mask.to(dev)
+            ws["pos"].copy_((attention_mask.long().cumsum(-1) - 1)[:, -1:].to(torch.int32))
+            ws["t_llm"].fill_(cache.seq_len)
+            ws["t_idx"].zero_()
+            ws["sem_cache"].reset()
+
+        reset_state()
+        if ws["graph"] is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture; its cache writes are overwritten by the real run
+                self._token_step(ws)
+            torch.cuda.current_stream().wait_stream(side)
+            reset_state()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._token_step(ws)
+            ws["graph"] = g
+            reset_state()
+        for token_idx in range(n_tok + 1):
+            # RNG stays on the host side as in the reference (torch.randn(1, C) per token, diff_loss_rf_swiglu.py:118)
+            ws["noise"].copy_(torch.randn(1, ws["noise"].shape[1], device=dev) if noises is None
+                              else noises[token_idx].to(dev))
+            ws["graph"].replay()
+        cache.seq_len += n_tok + 1
+        cache.trim_rows()
+        final_mask = ws["mask"][:, :t_now + n_tok].clone()
+        image_tensor = sem_to_pix_func(ws["feats"][:, :n_tok])
+        self._last_gen_latent_hidden = ws["hidden"]
+        return image_tensor, ws["hidden"].clone(), final_mask

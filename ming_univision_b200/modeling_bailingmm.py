@@ -108,7 +108,12 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         image_mask = None
         if pixel_values is not None:
             emb, image_mask = self.prompt_wrap_vision(input_ids, emb, self.extract_image_feature(pixel_values))
-        cache = llm.new_cache(max_len=S + 1 + cfg.num_image_tokens_for_gen + 8)
+        # a persistent workspace cache (so the captured AR-step graph stays valid across calls)
+        need = S + 1 + cfg.num_image_tokens_for_gen + 8
+        cache = getattr(self, "_ws_cache", None)
+        if cache is None or cache.max_len < need or cache.k[0].device != dev:
+            cache = self._ws_cache = llm.new_cache(max_len=max(need, 512))
+        cache.seq_len, cache.batch = 0, 1
         pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0)
         llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
         start = llm.model.embed(torch.tensor([[cfg.image_start_token]], device=dev))

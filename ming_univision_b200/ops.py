@@ -155,8 +155,9 @@ def attention_hd64(qkv: torch.Tensor, B: int, S: int, H: int, causal: bool) -> t
     return out
 
 
-def attention_hd64_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, t: int) -> torch.Tensor:
-    """qkv: [B, 3*H*64] for the new token; caches [B, H, Tmax, 64]; appends at t and attends to 0..t."""
+def attention_hd64_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, t: int,
+                          t_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """qkv: [B, 3*H*64] for the new token; caches [B, H, Tmax, 64]; appends at t (+ *t_dev) and attends to 0..t."""
     _check_bf16(qkv, kcache, vcache)
     lib = _lib.load()
     B, H, Tmax, hd = kcache.shape
@@ -164,7 +165,7 @@ def attention_hd64_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch
         raise ValueError("caches must be contiguous [B, H, Tmax, 64]")
     out = torch.empty((B, H * 64), dtype=BF16, device=qkv.device)
     rc = lib.mb_attn_hd64_decode(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), B, H, t, Tmax,
-                                 64 ** -0.5, _stream())
+                                 64 ** -0.5, None if t_dev is None else t_dev.data_ptr(), _stream())
     _lib.check(rc, "mb_attn_hd64_decode")
     return out
 

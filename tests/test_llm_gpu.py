@@ -224,3 +224,28 @@ def test_generate_image_vs_reference(tiny_model, cuda_device, name, forced):
         assert e_i < 3e-2, e_i            # pixel decoder on features of the reference trajectory
     else:
         assert img.shape == torch.from_numpy(g[f"{name}_image"])[0:1].shape and bool(torch.isfinite(img.float()).all())
+
+
+@pytest.mark.parametrize("name", ["t2i", "edit"])
+def test_generate_image_cuda_graph_equals_eager(tiny_model, cuda_device, name):
+    """The one-graph-replay-per-token fast path (device-side cache positions, static buffers) must reproduce the eager
+    kernel-by-kernel loop bit for bit, and be replayable for a second image."""
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    noises = [torch.from_numpy(n) for n in g[f"{name}_noises"]]
+    um = torch.from_numpy(g[f"{name}_uncond"]).to(cuda_device)
+    tm = torch.from_numpy(g[f"{name}_text_uncond"]).to(cuda_device)
+    llm = tiny_model.model
+    outs = {}
+    for mode in ("eager", "graph", "graph2"):
+        llm.use_cuda_graph = mode != "eager"
+        img, fmask = tiny_model.generate_image_from_prompt(ids, uncond_attention_mask=um, text_uncond_attention_mask=tm,
+                                                           image_gen_temperature=0.9, noises=noises)
+        outs[mode] = (img.float().cpu(), fmask.cpu(), tiny_model.past_key_values.get_seq_length(),
+                      tiny_model.past_key_values.k[0][0, :, :tiny_model.past_key_values.get_seq_length()].float().cpu())
+    llm.use_cuda_graph = True
+    for mode in ("graph", "graph2"):
+        assert torch.equal(outs[mode][0], outs["eager"][0]), mode
+        assert torch.equal(outs[mode][1], outs["eager"][1])
+        assert outs[mode][2] == outs["eager"][2] == int(g[f"{name}_cache_len"])
+        assert torch.equal(outs[mode][3], outs["eager"][3])
