@@ -202,14 +202,22 @@ int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* im
                    float* weights, int T, int E, int k, int renorm, void* stream);
 /* moe_infer (:608-639) for small token counts: counting sort of the (token, slot) pairs by expert, expert gate/up +
  * SwiGLU on the sorted pairs (Wgu[E][2I][D]: gate rows then up rows), expert down projection (Wd[E][D][I]) written
- * back in (token, slot) order, and the fp32 weighted combine + shared-expert add + layer residual. */
-int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E, void* stream);
+ * back in (token, slot) order, and the fp32 weighted combine + shared-expert add + layer residual.
+ * E is the number of LOCAL experts and e_begin the first one (E = all, e_begin = 0 without expert parallelism). */
+int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E, int e_begin,
+                void* stream);
 int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
                    void* hid, int T, int k, int E, int D, int I, void* stream);
 int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
                 void* out_pairs, int T, int k, int E, int D, int I, void* stream);
 int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual, void* y,
-                   int T, int k, int D, void* stream);
+                   float* y_partial, int T, int k, int D, void* stream);
+/* Expert parallelism (no reference implementation — the reference keeps all experts on one device):
+ * rank r owns experts [e_begin, e_begin + E) — mb_moe_sort lists only the pairs routed to them, mb_moe_gate_up /
+ * mb_moe_down run on the local slabs, mb_moe_combine with y_partial != NULL writes this rank's fp32 share of the
+ * weighted sum (non-local pairs contribute zeros), the ranks all-reduce the [T, D] fp32 partials over NCCL, and
+ * mb_moe_finalize applies the reference's rounding chain: bf16(bf16(bf16(sum) + shared) + residual). */
+int mb_moe_finalize(const float* y_sum, const void* shared, const void* residual, void* y, int T, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,10 +30,11 @@ SIGNATURES = {
     "mb_rope_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
     "mb_attn_decode_gqa": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
     "mb_router_topk": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_finalize": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
     "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],

@@ -125,9 +125,11 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
                           const __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ key_mask,
                           int64_t mask_stride, __nv_bfloat16* __restrict__ out, int B, int H, int Hkv, int Tmax,
                           const int32_t* __restrict__ t_dev, int t_host, float scale) {
-  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= B * H) return;
-  const int b = wid / H, h = wid % H, hk = h / (H / Hkv);
+  // one CTA (4 warps) per (batch row, q head): the warps take interleaved groups of 4 keys, then merge their partial
+  // (max, sum, output) triples through shared memory — 4x shorter dependent chain than one warp per head
+  __shared__ float s_m[4], s_l[4], s_o[4][128];
+  const int bh = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = bh / H, h = bh % H, hk = h / (H / Hkv);
   const int T = (t_dev ? *t_dev : 0) + t_host;
   const uint2 qq = *reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4);
   const float2 q0 = unpack_bf16x2(qq.x), q1 = unpack_bf16x2(qq.y);
@@ -135,7 +137,7 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
   const __nv_bfloat16* vc = vcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;
   const int32_t* mk = key_mask ? key_mask + static_cast<int64_t>(b) * mask_stride : nullptr;
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-  for (int j0 = 0; j0 < T; j0 += 4) {
+  for (int j0 = warp * 4; j0 < T; j0 += 16) {
     uint2 kk[4], vv[4];
     bool ok[4];
 #pragma unroll
@@ -162,11 +164,26 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
       m = m_new;
     }
   }
-  const float inv = l > 0.f ? 1.f / l : 0.f;
-  uint2 r;
-  r.x = pack_bf16x2(o0 * inv, o1 * inv);
-  r.y = pack_bf16x2(o2 * inv, o3 * inv);
-  *reinterpret_cast<uint2*>(out + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4) = r;
+  if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+  s_o[warp][lane * 4 + 0] = o0; s_o[warp][lane * 4 + 1] = o1;
+  s_o[warp][lane * 4 + 2] = o2; s_o[warp][lane * 4 + 3] = o3;
+  __syncthreads();
+  if (warp == 0) {
+    const float mm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float c = (s_m[w] == -INFINITY) ? 0.f : __expf(s_m[w] - mm);
+      lt += s_l[w] * c;
+      r0 += s_o[w][lane * 4 + 0] * c; r1 += s_o[w][lane * 4 + 1] * c;
+      r2 += s_o[w][lane * 4 + 2] * c; r3 += s_o[w][lane * 4 + 3] * c;
+    }
+    const float inv = lt > 0.f ? 1.f / lt : 0.f;
+    uint2 r;
+    r.x = pack_bf16x2(r0 * inv, r1 * inv);
+    r.y = pack_bf16x2(r2 * inv, r3 * inv);
+    *reinterpret_cast<uint2*>(out + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4) = r;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -232,13 +249,17 @@ router_topk_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 moe_sort_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ expert_offsets,
-                int32_t* __restrict__ sorted_pair, int npairs, int E) {
+                int32_t* __restrict__ sorted_pair, int npairs, int E, int e_begin) {
+  // E = number of LOCAL experts [e_begin, e_begin + E); pairs routed elsewhere (expert parallelism) are not listed
   extern __shared__ int32_t sm[];  // counts[E], cursor[E]
   int32_t* counts = sm;
   int32_t* cursor = sm + E;
   for (int e = threadIdx.x; e < E; e += blockDim.x) counts[e] = 0;
   __syncthreads();
-  for (int p = threadIdx.x; p < npairs; p += blockDim.x) atomicAdd(&counts[idx[p]], 1);
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    const int e = idx[p] - e_begin;
+    if (e >= 0 && e < E) atomicAdd(&counts[e], 1);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -256,66 +277,25 @@ moe_sort_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ expert_of
     int c = cursor[e];
     if (counts[e] == 0) continue;
     for (int p = 0; p < npairs; ++p)
-      if (idx[p] == e) sorted_pair[c++] = p;
+      if (idx[p] - e_begin == e) sorted_pair[c++] = p;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Routed experts, small-token regime.  grid = (X column blocks, E experts).  For its expert a CTA walks the expert's
-// pairs in chunks of <= 8 rows: stages the rows in shared memory, then every warp streams weight rows (16-byte loads,
-// K split over the lanes) and accumulates all staged rows at once, so an expert's weights are read once per chunk.
+// Routed experts, small-token regime.  grid = (X row-tile blocks, E experts).  For its expert a CTA walks the expert's
+// pairs in chunks of <= 8 rows (= the 8 columns of mma.m16n8k16): stages the rows in shared memory, then every warp
+// streams 16-row weight tiles straight from global memory into tensor-core A fragments (same permuted-K scheme as
+// gemv.cu: lane (g, t) loads 16 bytes of rows g and g + 8 at K offset 32 kg + 8 t; the activation fragment uses the
+// same K permutation), so an expert's weights are read once per chunk at ~4 instructions per KB.
 //   PHASE 0: hid[p, i]  = bf16(bf16(silu(bf16(x[tok(p)] . Wg[e][i]))) * bf16(x[tok(p)] . Wu[e][i]))     (gate/up + SwiGLU)
 //   PHASE 1: out[pair(p), n] = bf16(hid[p] . Wd[e][n])                                                   (down)
 // ------------------------------------------------------------------------------------------------------------
-template <int MT, int PHASE>
-__device__ __forceinline__ void moe_rows(const uint4* __restrict__ sA, int kchunks, const __nv_bfloat16* __restrict__ We,
-                                         int n_cols, int K, int col0, int col_step, int lane, int cnt,
-                                         __nv_bfloat16* __restrict__ dst, int64_t dst_ld, const int32_t* dst_rows,
-                                         int p0) {
-  for (int n = col0; n < n_cols; n += col_step) {
-    const uint4* w0 = reinterpret_cast<const uint4*>(We + static_cast<int64_t>(n) * K);
-    const uint4* w1 = reinterpret_cast<const uint4*>(We + static_cast<int64_t>(n + n_cols) * K);  // PHASE 0: up row
-    float a0[MT], a1[MT];
-#pragma unroll
-    for (int m = 0; m < MT; ++m) a0[m] = a1[m] = 0.f;
-    for (int c0 = lane; c0 < kchunks; c0 += 32 * 4) {
-      uint4 wa[4], wb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + 32 * u;
-        wa[u] = c < kchunks ? ldg_stream16(w0 + c) : make_uint4(0, 0, 0, 0);
-        if (PHASE == 0) wb[u] = c < kchunks ? ldg_stream16(w1 + c) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + 32 * u;
-        if (c < kchunks) {
-#pragma unroll
-          for (int m = 0; m < MT; ++m) {
-            const uint4 a = sA[m * kchunks + c];
-            a0[m] += dot8f(wa[u], a);
-            if (PHASE == 0) a1[m] += dot8f(wb[u], a);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      a0[m] = warp_sum_f(a0[m]);
-      if (PHASE == 0) a1[m] = warp_sum_f(a1[m]);
-    }
-#pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      if (lane == m && m < cnt) {
-        if (PHASE == 0) {
-          const float g = bf16_round(a0[m]), u = bf16_round(a1[m]);
-          dst[static_cast<int64_t>(p0 + m) * dst_ld + n] = __float2bfloat16_rn(bf16_round(silu(g)) * u);
-        } else {
-          dst[static_cast<int64_t>(dst_rows[p0 + m]) * dst_ld + n] = __float2bfloat16_rn(a0[m]);
-        }
-      }
-    }
-  }
+__device__ __forceinline__ void mma16816_f(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                           uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
 template <int PHASE>
@@ -323,30 +303,86 @@ __global__ void __launch_bounds__(256)
 moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                   const int32_t* __restrict__ expert_offsets, const int32_t* __restrict__ sorted_pair,
                   __nv_bfloat16* __restrict__ dst, int topk, int K, int n_cols, int64_t expert_stride) {
+  constexpr int kTiles = (PHASE == 0) ? 2 : 1;
+  constexpr int kUnroll = (PHASE == 0) ? 4 : 8;
   extern __shared__ __align__(16) uint8_t moe_smem[];
-  uint4* sA = reinterpret_cast<uint4*>(moe_smem);  // [8][K/8]
   const int e = blockIdx.y;
   const int beg = expert_offsets[e], end = expert_offsets[e + 1];
   if (beg == end) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int kchunks = K >> 3;
+  const int kgroups = (kchunks + 3) >> 2;
+  const int row_bytes = kgroups * 64 + 64;
   const __nv_bfloat16* We = W + static_cast<int64_t>(e) * expert_stride;
-  const int col0 = blockIdx.x * 8 + warp, col_step = gridDim.x * 8;
+  const int n_items = (n_cols + 15) / 16;
   for (int p0 = beg; p0 < end; p0 += 8) {
     const int cnt = min(8, end - p0);
     __syncthreads();  // previous chunk fully consumed
-    for (int i = tid; i < cnt * kchunks; i += 256) {
-      const int m = i / kchunks, c = i % kchunks;
-      // PHASE 0 gathers token rows of x; PHASE 1 reads the (already expert-sorted) hidden rows
-      const int64_t src_row = (PHASE == 0) ? (sorted_pair[p0 + m] / topk) : (p0 + m);
-      sA[m * kchunks + c] = *reinterpret_cast<const uint4*>(A + src_row * K + c * 8);
+    for (int i = tid; i < (cnt + 1) * (row_bytes / 16); i += 256) {
+      const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < cnt && c < kchunks) {
+        // PHASE 0 gathers token rows of x; PHASE 1 reads the (already expert-sorted) hidden rows
+        const int64_t src_row = (PHASE == 0) ? (sorted_pair[p0 + m] / topk) : (p0 + m);
+        v = *reinterpret_cast<const uint4*>(A + src_row * K + c * 8);
+      }
+      *reinterpret_cast<uint4*>(moe_smem + m * row_bytes + c * 16) = v;
     }
     __syncthreads();
-    const int64_t dst_ld = (PHASE == 0) ? n_cols : n_cols;
-    if (cnt == 1) moe_rows<1, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
-    else if (cnt == 2) moe_rows<2, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
-    else if (cnt <= 4) moe_rows<4, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
-    else moe_rows<8, PHASE>(sA, kchunks, We, n_cols, K, col0, col_step, lane, cnt, dst, dst_ld, sorted_pair, p0);
+    const uint8_t* xrow = moe_smem + min(g, cnt) * row_bytes + t * 16;
+    for (int item = blockIdx.x * 8 + warp; item < n_items; item += gridDim.x * 8) {
+      const int n0 = item * 16;
+      const __nv_bfloat16* wr[kTiles][2];
+#pragma unroll
+      for (int tl = 0; tl < kTiles; ++tl) {
+        const int base = tl * n_cols;  // PHASE 0: up rows follow the gate rows inside the expert slab
+        wr[tl][0] = We + static_cast<int64_t>(base + min(n0 + g, n_cols - 1)) * K + t * 8;
+        wr[tl][1] = We + static_cast<int64_t>(base + min(n0 + g + 8, n_cols - 1)) * K + t * 8;
+      }
+      float acc[kTiles][4];
+#pragma unroll
+      for (int tl = 0; tl < kTiles; ++tl) acc[tl][0] = acc[tl][1] = acc[tl][2] = acc[tl][3] = 0.f;
+      for (int kg0 = 0; kg0 < kgroups; kg0 += kUnroll) {
+        uint4 w[kTiles][2][kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int kg = kg0 + u;
+          const bool ok = kg < kgroups && (kg * 4 + t) < kchunks;
+#pragma unroll
+          for (int tl = 0; tl < kTiles; ++tl) {
+            w[tl][0][u] = ok ? ldg_stream16(reinterpret_cast<const uint4*>(wr[tl][0] + kg * 32)) : make_uint4(0, 0, 0, 0);
+            w[tl][1][u] = ok ? ldg_stream16(reinterpret_cast<const uint4*>(wr[tl][1] + kg * 32)) : make_uint4(0, 0, 0, 0);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const int kg = kg0 + u;
+          if (kg < kgroups) {
+            const uint4 xb = *reinterpret_cast<const uint4*>(xrow + kg * 64);
+#pragma unroll
+            for (int tl = 0; tl < kTiles; ++tl) {
+              mma16816_f(acc[tl], w[tl][0][u].x, w[tl][1][u].x, w[tl][0][u].y, w[tl][1][u].y, xb.x, xb.y);
+              mma16816_f(acc[tl], w[tl][0][u].z, w[tl][1][u].z, w[tl][0][u].w, w[tl][1][u].w, xb.z, xb.w);
+            }
+          }
+        }
+      }
+      // accumulator element ei: weight row n0 + g + 8 (ei >> 1), chunk row (token) 2 t + (ei & 1)
+#pragma unroll
+      for (int ei = 0; ei < 4; ++ei) {
+        const int n = n0 + g + 8 * (ei >> 1);
+        const int m = 2 * t + (ei & 1);
+        if (n < n_cols && m < cnt) {
+          if (PHASE == 0) {
+            const float gg = bf16_round(acc[0][ei]), uu = bf16_round(acc[kTiles - 1][ei]);
+            dst[static_cast<int64_t>(p0 + m) * n_cols + n] = __float2bfloat16_rn(bf16_round(silu(gg)) * uu);
+          } else {
+            dst[static_cast<int64_t>(sorted_pair[p0 + m]) * n_cols + n] = __float2bfloat16_rn(acc[0][ei]);
+          }
+        }
+      }
+    }
   }
 }
 
@@ -354,7 +390,7 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
 // (moe_infer's fp32 weighted sum :632-638, `y + shared_experts(identity)` :604-605, layer residual :1226)
 __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ out_pairs, const float* __restrict__ w,
                                    const __nv_bfloat16* __restrict__ shared, const __nv_bfloat16* __restrict__ residual,
-                                   __nv_bfloat16* __restrict__ y, int T, int k, int D) {
+                                   __nv_bfloat16* __restrict__ y, float* __restrict__ y_partial, int T, int k, int D) {
   const int64_t total = static_cast<int64_t>(T) * D;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -362,7 +398,23 @@ __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ out_pairs, 
     const int d = static_cast<int>(i % D);
     float acc = 0.f;
     for (int j = 0; j < k; ++j) acc += w[t * k + j] * __bfloat162float(out_pairs[(t * k + j) * D + d]);
+    if (y_partial != nullptr) {  // expert-parallel: this rank's share of the fp32 sum; finalised after the all-reduce
+      y_partial[i] = acc;
+      continue;
+    }
     float v = bf16_round(acc);
+    if (shared) v = bf16_round(v + __bfloat162float(shared[i]));
+    if (residual) v = v + __bfloat162float(residual[i]);
+    y[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void moe_finalize_kernel(const float* __restrict__ y_sum, const __nv_bfloat16* __restrict__ shared,
+                                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ y,
+                                    int64_t total) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float v = bf16_round(y_sum[i]);
     if (shared) v = bf16_round(v + __bfloat162float(shared[i]));
     if (residual) v = v + __bfloat162float(residual[i]);
     y[i] = __float2bfloat16_rn(v);
@@ -413,7 +465,7 @@ extern "C" int mb_attn_decode_gqa(const void* q, const void* kcache, const void*
   MB_CHECK_ARG(hd == 128 && H % Hkv == 0, MB_ERR_SHAPE, "mb_attn_decode_gqa: head_dim must be 128 and H %% Hkv == 0");
   MB_CHECK_ARG(t_dev != nullptr || (t_host >= 0 && t_host <= Tmax), MB_ERR_SHAPE, "mb_attn_decode_gqa: bad length");
   if (B == 0) return MB_OK;
-  attn_decode_gqa128_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(
+  attn_decode_gqa128_kernel<<<B * H, 128, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
       static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
       Tmax, t_dev, t_host, scale);
@@ -435,19 +487,19 @@ extern "C" int mb_router_topk(const void* logits, const void* logits_img, const 
 }
 
 extern "C" int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E,
-                           void* stream_) {
+                           int e_begin, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_sort: no sm_100 device");
-  MB_CHECK_ARG(E >= 1 && E <= 4096, MB_ERR_SHAPE, "mb_moe_sort: bad expert count");
-  moe_sort_kernel<<<1, 256, 2 * E * sizeof(int32_t), stream>>>(idx, expert_offsets, sorted_pair, T * k, E);
+  MB_CHECK_ARG(E >= 1 && E <= 4096 && e_begin >= 0, MB_ERR_SHAPE, "mb_moe_sort: bad expert range");
+  moe_sort_kernel<<<1, 256, 2 * E * sizeof(int32_t), stream>>>(idx, expert_offsets, sorted_pair, T * k, E, e_begin);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }
 
 static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
                             void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(8) * K * 2;
-  MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= 10240");
+  const size_t smem = static_cast<size_t>(9) * (((K / 8 + 3) / 4) * 64 + 64);
+  MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= 8192");
   static bool attr_set[2] = {false, false};
   if (!attr_set[phase]) {
     if (phase == 0)
@@ -456,7 +508,7 @@ static int launch_moe_phase(int phase, const void* A, const void* W, const int32
       MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[phase] = true;
   }
-  int xblocks = (n_cols + 8 * 11 - 1) / (8 * 11);  // ~11 columns per warp
+  int xblocks = ((n_cols + 15) / 16 + 7) / 8;  // one 16-row weight tile per warp
   if (xblocks < 1) xblocks = 1;
   dim3 grid(xblocks, E);
   if (phase == 0)
@@ -487,8 +539,23 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
                           static_cast<cudaStream_t>(stream_));
 }
 
+extern "C" int mb_moe_finalize(const float* y_sum, const void* shared, const void* residual, void* y, int T, int D,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_finalize: no sm_100 device");
+  const int64_t total = static_cast<int64_t>(T) * D;
+  if (total == 0) return MB_OK;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms() * 8) grid = num_sms() * 8;
+  moe_finalize_kernel<<<grid, 256, 0, stream>>>(y_sum, static_cast<const __nv_bfloat16*>(shared),
+                                                static_cast<const __nv_bfloat16*>(residual),
+                                                static_cast<__nv_bfloat16*>(y), total);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
 extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual,
-                              void* y, int T, int k, int D, void* stream_) {
+                              void* y, float* y_partial, int T, int k, int D, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_combine: no sm_100 device");
   const int64_t total = static_cast<int64_t>(T) * D;
@@ -498,7 +565,7 @@ extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const
   moe_combine_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out_pairs), weights,
                                                static_cast<const __nv_bfloat16*>(shared),
                                                static_cast<const __nv_bfloat16*>(residual),
-                                               static_cast<__nv_bfloat16*>(y), T, k, D);
+                                               static_cast<__nv_bfloat16*>(y), y_partial, T, k, D);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

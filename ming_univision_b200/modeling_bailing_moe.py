@@ -121,6 +121,14 @@ class BailingMoeSparseMoeBlock(nn.Module):
         if config.num_shared_experts is not None and config.num_shared_experts > 0:
             self.shared_experts = BailingMoeMLP(config, config.moe_intermediate_size * config.num_shared_experts)
         self._pk = None
+        # expert parallelism: this rank keeps experts [ep_rank * E / ep_size, (ep_rank + 1) * E / ep_size)
+        self.ep_group, self.ep_rank, self.ep_size = None, 0, 1
+
+    def set_expert_parallel(self, group, rank: int, size: int) -> None:
+        if self.config.num_experts % size != 0:
+            raise ValueError("num_experts must be divisible by the expert-parallel world size")
+        self.ep_group, self.ep_rank, self.ep_size = (group if size > 1 else None), rank, size
+        self._pk = None
 
     def _pack(self):
         dev = self.gate.weight.device
@@ -130,9 +138,12 @@ class BailingMoeSparseMoeBlock(nn.Module):
             if self.multi_gate:
                 pk["image_gate"] = d(self.image_gate.weight)
             # per-expert slabs: Wgu[e] = [gate_proj; up_proj] ([2I, D]), Wd[e] = down_proj ([D, I])
+            n_local = len(self.experts) // self.ep_size
+            pk["e_begin"] = self.ep_rank * n_local
+            local = list(self.experts)[pk["e_begin"]:pk["e_begin"] + n_local]
             pk["Wgu"] = torch.stack([torch.cat([d(e.gate_proj.weight), d(e.up_proj.weight)], dim=0)
-                                     for e in self.experts]).contiguous()
-            pk["Wd"] = torch.stack([d(e.down_proj.weight) for e in self.experts]).contiguous()
+                                     for e in local]).contiguous()
+            pk["Wd"] = torch.stack([d(e.down_proj.weight) for e in local]).contiguous()
             if hasattr(self, "shared_experts"):
                 s = self.shared_experts
                 pk["s12"] = torch.cat([d(s.gate_proj.weight), d(s.up_proj.weight)], dim=0).contiguous()
@@ -164,7 +175,7 @@ class BailingMoeSparseMoeBlock(nn.Module):
                 shared = ops.gemv(ops.gemv(x2d, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
             else:
                 shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
-        y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual)
+        y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual, pk["e_begin"], self.ep_group)
         return y, logits, idx
 
     @torch.no_grad()
@@ -264,6 +275,18 @@ class BailingMoeModel(nn.Module):
                                    dense_w=d(a.dense.weight), dense_b=d(a.dense.bias)))
             self._pk = dict(dev=dev, layers=layers, norm=d(self.norm.weight), emb=d(self.word_embeddings.weight))
         return self._pk
+
+    def set_expert_parallel(self, group=None) -> None:
+        """Shards the routed experts of every layer over the ranks of `group` (default: the world group); attention,
+        gates, shared experts and norms stay replicated.  One process per GPU; NCCL over NVLink."""
+        import torch.distributed as dist
+
+        size = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        for lyr in self.layers:
+            lyr.mlp.set_expert_parallel(group if group is not None else (dist.group.WORLD if size > 1 else None),
+                                        rank, size)
+        self.ep_size = size
 
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:
         """word_embeddings lookup (row gather of the packed bf16 table; pure indexing, no arithmetic)."""
@@ -435,7 +458,8 @@ class BailingMoeForCausalLM(nn.Module):
         if B > 1:
             input_embeds = input_embeds.repeat((B, 1, 1))
             cache.repeat_rows(B)
-        if self.use_cuda_graph and self._graphable(latent_to_sem_func, linear_proj):
+        if self.use_cuda_graph and getattr(self.model, "ep_size", 1) == 1 and \
+                self._graphable(latent_to_sem_func, linear_proj):
             return self._generate_image_graphed(input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func,
                                                 linear_proj, sem_to_pix_func, image_gen_temperature, noises)
         # key mask buffer for the whole generation: prompt part now, one more "1" column per generated token

@@ -396,8 +396,13 @@ def router_topk(logits: torch.Tensor, k: int, renorm: bool, logits_img: torch.Te
 
 
 def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor,
-                shared: torch.Tensor | None, residual: torch.Tensor | None) -> torch.Tensor:
-    """moe_infer + shared-expert add + residual: x [T, D]; Wgu [E, 2I, D]; Wd [E, D, I]; idx int32 [T, k]; w fp32."""
+                shared: torch.Tensor | None, residual: torch.Tensor | None, e_begin: int = 0,
+                ep_group=None) -> torch.Tensor:
+    """moe_infer + shared-expert add + residual: x [T, D]; Wgu [E_local, 2I, D]; Wd [E_local, D, I]; idx int32 [T, k]
+    (GLOBAL expert ids); w fp32.  With `ep_group` the slabs hold only experts [e_begin, e_begin + E_local): each rank
+    computes the fp32 weighted sum of its experts, the partials are all-reduced over NCCL (torch.distributed is the
+    plumbing; the tokens of this path are replicated on every rank, so there is no dispatch exchange), and the
+    reference's rounding chain is applied after the reduction."""
     _check_bf16(x, Wgu, Wd, shared, residual)
     lib = _lib.load()
     T, D = x.shape
@@ -408,14 +413,26 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
     offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
     sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
     hid = torch.empty((T * k, I), dtype=BF16, device=dev)
-    out_pairs = torch.empty((T * k, D), dtype=BF16, device=dev)
+    ep = ep_group is not None
+    out_pairs = (torch.zeros if ep else torch.empty)((T * k, D), dtype=BF16, device=dev)
     y = torch.empty((T, D), dtype=BF16, device=dev)
     s = _stream()
-    _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, s), "mb_moe_sort")
+    _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
+               "mb_moe_sort")
     _lib.check(lib.mb_moe_gate_up(x.contiguous().data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
                                   hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
     _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
                                out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
-    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, k,
+    if not ep:
+        _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(),
+                                      None, T, k, D, s), "mb_moe_combine")
+        return y
+    import torch.distributed as dist
+
+    part = torch.empty((T, D), dtype=torch.float32, device=dev)
+    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), part.data_ptr(), T, k,
                                   D, s), "mb_moe_combine")
+    dist.all_reduce(part, op=dist.ReduceOp.SUM, group=ep_group)
+    _lib.check(lib.mb_moe_finalize(part.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, D, s),
+               "mb_moe_finalize")
     return y

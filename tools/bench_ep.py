@@ -1,0 +1,66 @@
+"""Expert-parallel decode step of ONE full-size Bailing-MoE MoE layer (64 experts top-6 + 2 shared, D = 2048) under
+torchrun: experts sharded over the ranks, tokens (B = 2 CFG rows) replicated, fp32 partial sums all-reduced with NCCL.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_ep.py
+Prints per-layer latency (CUDA events, max over ranks) for EP = N next to the unsharded layer on rank 0."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ming_univision_b200 import synthetic  # noqa: E402
+from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig, BailingMoeSparseMoeBlock  # noqa: E402
+
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+if world > 1:
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+cfg = BailingMoeConfig(**synthetic.LLM_CONFIG)
+torch.manual_seed(0)
+torch.set_default_dtype(torch.bfloat16)
+with torch.device(dev):
+    blk = BailingMoeSparseMoeBlock(cfg)
+torch.set_default_dtype(torch.float32)
+with torch.no_grad():
+    for p in blk.parameters():
+        p.copy_(torch.randn(p.shape, device=dev, dtype=torch.float32) / p.shape[-1] ** 0.5)
+x = torch.randn((2, 2048), device=dev).to(torch.bfloat16)
+res = torch.randn((2, 2048), device=dev).to(torch.bfloat16)
+if world > 1:
+    dist.broadcast(x, 0)
+    dist.broadcast(res, 0)
+    for p in blk.parameters():
+        dist.broadcast(p.data, 0)
+
+
+def timeit(fn, iters=50):
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / iters], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+y_single, _, _ = blk._run(x, res, None)
+ms_single = timeit(lambda: blk._run(x, res, None))
+out = {"world": world, "ms_layer_unsharded": round(ms_single, 4)}
+if world > 1:
+    blk.set_expert_parallel(dist.group.WORLD, rank, world)
+    y_ep, _, _ = blk._run(x, res, None)
+    out["rel_err_vs_unsharded"] = float(((y_ep.float() - y_single.float()).norm() / y_single.float().norm()).item())
+    out["ms_layer_ep"] = round(timeit(lambda: blk._run(x, res, None)), 4)
+if rank == 0:
+    print(json.dumps(out), flush=True)
+if world > 1:
+    dist.destroy_process_group()
