@@ -216,6 +216,24 @@ __global__ void unpatchify_clamp_kernel(const __nv_bfloat16* __restrict__ x, voi
   }
 }
 
+// stats[r] = (sum_c x[r, c], sum_c x[r, c]^2)   one warp per row — seeds the LayerNorm-folded GEMM chain of a stage
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restrict__ stats, int rows, int dim) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * ldx;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = lane * 8; c < dim; c += 256) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) { stats[2 * row] = s1; stats[2 * row + 1] = s2; }
+}
+
 static inline int grid_for(int64_t n, int block) {
   int64_t g = (n + block - 1) / block;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -256,6 +274,16 @@ extern "C" int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const
   else if (nv <= 12) MB_LN(12);
   else MB_LN(16);
 #undef MB_LN
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_row_stats(const void* x, int64_t ldx, float* stats, int rows, int dim, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_row_stats: no sm_100 device");
+  MB_CHECK_ARG(dim % 8 == 0 && ldx % 8 == 0, MB_ERR_ALIGN, "mb_row_stats: dim and ldx must be multiples of 8");
+  if (rows == 0) return MB_OK;
+  row_stats_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx, stats, rows, dim);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

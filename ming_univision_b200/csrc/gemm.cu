@@ -42,6 +42,13 @@ struct GemmParams {
   int out_row_group;
   int out_row_pad;
   int tma_epi;  // 1: epilogue goes through shared-memory staging + TMA store (and TMA load of the residual)
+  // LayerNorm folded into this GEMM (see mb_gemm_bf16_ex): A holds the UN-normalised rows, W already carries gamma,
+  //   out = rstd[r] * (acc - mean[r] * csum[n]) + bias_f32[n]
+  const float* ln_stats_in;   // [M][2] per-row (sum, sum of squares) of A, or NULL
+  const float* ln_csum;       // [N]    row sums of the gamma-scaled weight (fp32)
+  const float* ln_bias;       // [N]    bias + W . beta (fp32)
+  float ln_inv_dim, ln_eps;
+  float* ln_stats_out;        // [M][2] RESIDUAL epilogue: accumulates (sum, sumsq) of the rows it writes, or NULL
 };
 
 template <int BN, int CG>
@@ -101,34 +108,67 @@ __device__ __forceinline__ void load_bias32(const __nv_bfloat16* bias, int col0,
 
 // Accumulator chunk (this warp's 32 rows x 32 columns starting at tile column tc) -> bias / activation, fp32 in v[].
 // For MB_EPI_RESIDUAL the residual is added by the caller (it arrives either by TMA or by direct loads).
+// acc[i] -> rstd * (acc[i] - mean * csum[col + i]) + bias_f32[col + i]   (LayerNorm folded into the GEMM)
+__device__ __forceinline__ void ln_fold32(const GemmParams& p, int col, int ncols_valid, float mean, float rstd,
+                                          const uint32_t (&a)[32], float (&v)[32]) {
+  if (ncols_valid >= 32) {
+    const float4* cs = reinterpret_cast<const float4*>(p.ln_csum + col);
+    const float4* bs = reinterpret_cast<const float4*>(p.ln_bias + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 c = __ldg(cs + i), b = __ldg(bs + i);
+      v[4 * i + 0] = fmaf(rstd, __uint_as_float(a[4 * i + 0]) - mean * c.x, b.x);
+      v[4 * i + 1] = fmaf(rstd, __uint_as_float(a[4 * i + 1]) - mean * c.y, b.y);
+      v[4 * i + 2] = fmaf(rstd, __uint_as_float(a[4 * i + 2]) - mean * c.z, b.z);
+      v[4 * i + 3] = fmaf(rstd, __uint_as_float(a[4 * i + 3]) - mean * c.w, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      v[i] = (i < ncols_valid) ? fmaf(rstd, __uint_as_float(a[i]) - mean * p.ln_csum[col + i], p.ln_bias[col + i]) : 0.f;
+  }
+}
+
 template <int BN, int EPI>
 __device__ __forceinline__ void epi_math(const GemmParams& p, uint32_t t_row, int tc, int n_tile, int out_col,
-                                         int ncols_valid, float (&v)[32]) {
+                                         int ncols_valid, float ln_mean, float ln_rstd, float (&v)[32]) {
   if constexpr (EPI == MB_EPI_SWIGLU) {
     uint32_t g[32], u[32];
     tmem_ld_32x32b_x32(t_row + tc, g);
     tmem_ld_32x32b_x32(t_row + BN / 2 + tc, u);
     tmem_ld_wait();
-    {
-      float bg[32];
-      load_bias32(p.bias, n_tile * BN + tc, 32, bg);
+    if (p.ln_stats_in != nullptr) {
+      float x1[32];
+      ln_fold32(p, n_tile * BN + tc, 32, ln_mean, ln_rstd, g, x1);
+      ln_fold32(p, n_tile * BN + BN / 2 + tc, 32, ln_mean, ln_rstd, u, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
-    }
-    {
-      float bu[32];
-      load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
+      for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(x1[i]))) * bf16_round(v[i]);
+    } else {
+      {
+        float bg[32];
+        load_bias32(p.bias, n_tile * BN + tc, 32, bg);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
+        for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
+      }
+      {
+        float bu[32];
+        load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
+      }
     }
   } else {
     uint32_t a[32];
     tmem_ld_32x32b_x32(t_row + tc, a);
     tmem_ld_wait();
-    float b[32];
-    load_bias32(p.bias, out_col, ncols_valid, b);
+    if (p.ln_stats_in != nullptr) {
+      ln_fold32(p, out_col, ncols_valid, ln_mean, ln_rstd, a, v);
+    } else {
+      float b[32];
+      load_bias32(p.bias, out_col, ncols_valid, b);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
+    }
     if constexpr (EPI == MB_EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
@@ -284,6 +324,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (p.out_row_group > 0) out_row += static_cast<int64_t>(row / p.out_row_group) * p.out_row_pad;
       const int64_t res_row = (p.res_row_mod > 0) ? (row % p.res_row_mod) : row;
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats_in != nullptr && row_ok) {
+        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats_in) + row);
+        ln_mean = st.x * p.ln_inv_dim;
+        ln_rstd = rsqrtf(fmaxf(st.y * p.ln_inv_dim - ln_mean * ln_mean, 0.f) + p.ln_eps);
+      }
+      float st_sum = 0.f, st_sq = 0.f;
 
       if (p.tma_epi) {
         // ---- staged path: registers -> 128B-swizzled smem box (32 rows x 64 cols) -> one TMA store per box; the
@@ -308,7 +355,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int cc = 0; cc < 2; ++cc) {
             const int tc = box_tc + cc * 32;
             float v[32];
-            epi_math<BN, EPI>(p, t_row, tc, n_tile, n_tile * kOutTileN + tc, n_out_total - (n_tile * kOutTileN + tc), v);
+            epi_math<BN, EPI>(p, t_row, tc, n_tile, n_tile * kOutTileN + tc, n_out_total - (n_tile * kOutTileN + tc),
+                              ln_mean, ln_rstd, v);
             if constexpr (EPI == MB_EPI_RESIDUAL) {
               if (cc == 0) mbar_wait(&epi_bar[ew], epi_phase);
 #pragma unroll
@@ -320,6 +368,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 v[8 * j + 2] = bf16_round(v[8 * j + 2]) + f1.x; v[8 * j + 3] = bf16_round(v[8 * j + 3]) + f1.y;
                 v[8 * j + 4] = bf16_round(v[8 * j + 4]) + f2.x; v[8 * j + 5] = bf16_round(v[8 * j + 5]) + f2.y;
                 v[8 * j + 6] = bf16_round(v[8 * j + 6]) + f3.x; v[8 * j + 7] = bf16_round(v[8 * j + 7]) + f3.y;
+              }
+            }
+            if constexpr (EPI == MB_EPI_RESIDUAL) {
+              if (p.ln_stats_out != nullptr) {  // statistics of the rows as stored (bf16), for the LayerNorm that follows
+                const int nv = n_out_total - (n_tile * kOutTileN + tc);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float r = (i < nv) ? bf16_round(v[i]) : 0.f;
+                  st_sum += r;
+                  st_sq = fmaf(r, r, st_sq);
+                }
               }
             }
 #pragma unroll
@@ -347,7 +406,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int out_col = n_tile * kOutTileN + tc;  // global output column
           const int ncols_valid = n_out_total - out_col;
           float v[32];
-          epi_math<BN, EPI>(p, t_row, tc, n_tile, out_col, ncols_valid, v);
+          epi_math<BN, EPI>(p, t_row, tc, n_tile, out_col, ncols_valid, ln_mean, ln_rstd, v);
           if constexpr (EPI == MB_EPI_RESIDUAL) {
             if (row_ok && ncols_valid > 0) {
               const __nv_bfloat16* rp = p.residual + res_row * p.ldr + out_col;
@@ -371,6 +430,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
+        }
+      }
+      if constexpr (EPI == MB_EPI_RESIDUAL) {
+        if (p.ln_stats_out != nullptr && p.tma_epi && row_ok) {
+          atomicAdd(p.ln_stats_out + 2 * row, st_sum);
+          atomicAdd(p.ln_stats_out + 2 * row + 1, st_sq);
         }
       }
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
@@ -465,6 +530,15 @@ extern "C" int mb_gemm_force_tile(int cta_group, int bn) {
 extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
                             int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
                             int res_row_mod, int out_row_group, int out_row_pad, void* stream_) {
+  return mb_gemm_bf16_ex(A, lda, W, ldw, bias, out, ldo, M, N, K, epi, residual, ldr, res_row_mod, out_row_group,
+                         out_row_pad, nullptr, nullptr, nullptr, 0.f, nullptr, stream_);
+}
+
+extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                               int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
+                               int res_row_mod, int out_row_group, int out_row_pad, const float* ln_stats_in,
+                               const float* ln_csum, const float* ln_bias_f32, float ln_eps, float* ln_stats_out,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_gemm_bf16: no sm_100 device");
   MB_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, MB_ERR_SHAPE, "mb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -507,6 +581,21 @@ extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   const bool tma_epi = !g_no_tma_epi && out_row_group == 0 && res_row_mod == 0 && n_out >= 64 &&
                        (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
   p.tma_epi = tma_epi ? 1 : 0;
+  p.ln_stats_in = ln_stats_in;
+  p.ln_csum = ln_csum;
+  p.ln_bias = ln_bias_f32;
+  p.ln_inv_dim = 1.0f / static_cast<float>(K);
+  p.ln_eps = ln_eps;
+  p.ln_stats_out = ln_stats_out;
+  if (ln_stats_in != nullptr)
+    MB_CHECK_ARG(ln_csum != nullptr && ln_bias_f32 != nullptr && epi != MB_EPI_RESIDUAL &&
+                     (reinterpret_cast<uintptr_t>(ln_csum) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_bias_f32) & 15) == 0,
+                 MB_ERR_SHAPE, "mb_gemm_bf16_ex: LayerNorm fold needs 16-byte aligned csum / bias_f32 and a non-residual epilogue");
+  if (ln_stats_out != nullptr) {
+    MB_CHECK_ARG(epi == MB_EPI_RESIDUAL && tma_epi, MB_ERR_SHAPE,
+                 "mb_gemm_bf16_ex: row statistics are produced by the dense RESIDUAL epilogue only");
+    MB_CHECK_CUDA(cudaMemsetAsync(ln_stats_out, 0, static_cast<size_t>(M) * 2 * sizeof(float), stream));
+  }
   CUtensorMap to = ta, tr = ta;  // valid placeholders when unused
   if (tma_epi) {
     if (!make_tmap_2d_bf16(&to, out, n_out, M, ldo, 64, 32)) return MB_ERR_CUDA;

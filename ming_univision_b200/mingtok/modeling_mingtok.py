@@ -159,7 +159,7 @@ def _dev_bf16(t: torch.Tensor, device) -> torch.Tensor:
 
 class _PackedBlock:
     __slots__ = ("n1w", "n1b", "qkv_w", "qkv_b", "proj_w", "proj_b", "n2w", "n2b", "ffn", "w1", "b1", "w2", "b2",
-                 "w12_ref", "b12_ref", "w3_ref")
+                 "w12_ref", "b12_ref", "w3_ref", "qkv_f", "w1_f")
 
     def __init__(self, blk: _Block, device):
         d = lambda t: _dev_bf16(t, device)  # noqa: E731
@@ -177,6 +177,46 @@ class _PackedBlock:
             self.ffn = "gelu"
             self.w1, self.b1 = d(blk.mlp.fc1.weight), d(blk.mlp.fc1.bias)
             self.w2, self.b2 = d(blk.mlp.fc2.weight), d(blk.mlp.fc2.bias)
+        # LayerNorm-folded packs for the full-sequence path: norm1 -> qkv, norm2 -> w12 / fc1 (ops.fold_layernorm)
+        self.qkv_f = ops.fold_layernorm(self.qkv_w, self.qkv_b, self.n1w, self.n1b)
+        if self.ffn == "swiglu":
+            H = self.w12_ref.shape[0] // 2
+            wf, cs, bf = ops.fold_layernorm(self.w12_ref, self.b12_ref, self.n2w, self.n2b)
+            wp, _, hp = ops.pack_swiglu(wf, None)
+            self.w1_f = (wp, ops.pack_swiglu_f32(cs, H, hp), ops.pack_swiglu_f32(bf, H, hp))
+        else:
+            self.w1_f = ops.fold_layernorm(self.w1, self.b1, self.n2w, self.n2b)
+
+
+LN_EPS = 1e-6
+FOLD_LAYERNORM = True  # full-sequence blocks: LayerNorms folded into the GEMMs (no LayerNorm kernels, see _run_block_folded)
+
+
+def _run_block_folded(pb: _PackedBlock, x: torch.Tensor, B: int, S: int, H: int, causal: bool,
+                      stats: torch.Tensor) -> torch.Tensor:
+    """The same block with both LayerNorms folded into the GEMMs that consume them: `stats` [rows, 2] holds the per-row
+    (sum, sum of squares) of x on entry (left there by the previous block's last GEMM or by ops.row_stats); the proj
+    and w3 / fc2 epilogues refresh it while they write the residual stream.  4 GEMMs + attention per block, no
+    LayerNorm kernel, no normalised copy of the activations in HBM / L2.  Returns the statistics of the new x."""
+    qkv = ops.linear(x, pb.qkv_f[0], None, ln_fold=(stats, pb.qkv_f[1], pb.qkv_f[2], LN_EPS))
+    a = ops.attention_hd64(qkv, B, S, H, causal)
+    st_mid = torch.empty_like(stats)
+    ops.linear(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x, stats_out=st_mid)
+    hid = ops.linear(x, pb.w1_f[0], None, epi=ops.EPI_SWIGLU if pb.ffn == "swiglu" else ops.EPI_GELU,
+                     ln_fold=(st_mid, pb.w1_f[1], pb.w1_f[2], LN_EPS))
+    ops.linear(hid, pb.w2, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x, stats_out=stats)
+    return stats
+
+
+def _run_blocks(blocks, x: torch.Tensor, B: int, S: int, H: int, causal: bool) -> torch.Tensor:
+    if not FOLD_LAYERNORM:
+        for pb in blocks:
+            _run_block(pb, x, B, S, H, causal)
+        return x
+    stats = ops.row_stats(x)
+    for pb in blocks:
+        _run_block_folded(pb, x, B, S, H, causal, stats)
+    return x
 
 
 def _run_block(pb: _PackedBlock, x: torch.Tensor, B: int, S: int, H: int, causal: bool) -> torch.Tensor:
@@ -337,8 +377,7 @@ class MingTok(PreTrainedModel):
         ops.linear(rows, pk.pe_w, pk.pe_b, epi=ops.EPI_RESIDUAL, residual=patch_pos, res_row_mod=n, out=t,
                    out_row_group=n, out_row_pad=1)
         ops.fill_cls_row(t, pk.cls, cls_pos)
-        for pb in pk.enc_blocks:
-            _run_block(pb, t, B, n + 1, enc.num_heads, False)
+        _run_blocks(pk.enc_blocks, t, B, n + 1, enc.num_heads, False)
         shortcut = ops.group_mean(t, enc.out_dim)
         hgelu = ops.layernorm(t, pk.out_nw, pk.out_nb, act=1)
         return ops.linear(hgelu, pk.out_w, pk.out_b, epi=ops.EPI_RESIDUAL, residual=shortcut)
@@ -351,8 +390,7 @@ class MingTok(PreTrainedModel):
         sem = self.semantic_decoder
         B, N, _ = latent.shape
         x = ops.inproj_repeat(latent, pk.in_w, pk.in_b)
-        for pb in pk.sem_blocks:
-            _run_block(pb, x, B, N, sem.num_heads, True)
+        _run_blocks(pk.sem_blocks, x, B, N, sem.num_heads, True)
         return ops.layernorm(x, pk.sem_nw, pk.sem_nb, drop_last_token=N > 1)
 
     # -- reference API -----------------------------------------------------------------------------------------
@@ -429,8 +467,7 @@ class MingTok(PreTrainedModel):
         s = ops.linear(x, pk.s2p_w, pk.s2p_b)
         t = ops.pixel_shuffle(s, g, f, pix.embed_dim)
         S = g * f * g * f
-        for pb in pk.pix_blocks:
-            _run_block(pb, t, B, S, pix.num_heads, False)
+        _run_blocks(pk.pix_blocks, t, B, S, pix.num_heads, False)
         hn = ops.layernorm(t, pk.pix_nw, pk.pix_nb)
         y = ops.linear(hn, pk.head_w, pk.head_b)
         return ops.unpatchify_clamp(y, g * f, pix.patch_size, out_dtype)

@@ -48,8 +48,12 @@ def round_up(x: int, m: int) -> int:
 # ---------------------------------------------------------------------------------------------------------------
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, *, epi: int = EPI_BIAS,
            residual: torch.Tensor | None = None, res_row_mod: int = 0, out: torch.Tensor | None = None,
-           out_row_group: int = 0, out_row_pad: int = 0) -> torch.Tensor:
-    """out = epilogue(x @ weight.T + bias) on the tcgen05 GEMM.  x: [..., K], weight: [N, K] (nn.Linear layout)."""
+           out_row_group: int = 0, out_row_pad: int = 0, ln_fold: tuple | None = None,
+           stats_out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = epilogue(x @ weight.T + bias) on the tcgen05 GEMM.  x: [..., K], weight: [N, K] (nn.Linear layout).
+    ln_fold = (stats [M, 2] fp32, csum [N] fp32, bias_f32 [N] fp32, eps): LayerNorm of x folded into the epilogue
+    (weight must be the gamma-scaled pack, see fold_layernorm); stats_out [M, 2] fp32: the RESIDUAL epilogue leaves the
+    per-row (sum, sum of squares) of what it wrote there for the next folded GEMM."""
     _check_bf16(x, weight, bias, residual, out)
     lib = _lib.load()
     a = _rows2d(x)
@@ -78,14 +82,60 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    rc = lib.mb_gemm_bf16(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
-                          out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod, out_row_group,
-                          out_row_pad, _stream())
+    if ln_fold is None and stats_out is None:
+        rc = lib.mb_gemm_bf16(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
+                              out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod,
+                              out_row_group, out_row_pad, _stream())
+    else:
+        st_in = cs = bf = None
+        eps = 0.0
+        if ln_fold is not None:
+            st_in, cs, bf, eps = ln_fold
+            if st_in.dtype != torch.float32 or cs.dtype != torch.float32 or bf.dtype != torch.float32:
+                raise TypeError("ln_fold tensors must be fp32")
+        rc = lib.mb_gemm_bf16_ex(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
+                                 out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod,
+                                 out_row_group, out_row_pad, _ptr(st_in), _ptr(cs), _ptr(bf), float(eps),
+                                 _ptr(stats_out), _stream())
     if prof is not None:
         ev1.record()
         prof.append(((M, N, K, epi), 2.0 * M * N * K, ev0, ev1))
     _lib.check(rc, "mb_gemm_bf16")
     return ret
+
+
+def row_stats(x: torch.Tensor) -> torch.Tensor:
+    """[rows, D] bf16 -> [rows, 2] fp32 (sum, sum of squares): seeds a chain of LayerNorm-folded GEMMs."""
+    _check_bf16(x)
+    lib = _lib.load()
+    x2 = _rows2d(x)
+    st = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+    _lib.check(lib.mb_row_stats(x2.data_ptr(), x2.stride(0), st.data_ptr(), x2.shape[0], x2.shape[1], _stream()),
+               "mb_row_stats")
+    return st
+
+
+def fold_layernorm(w: torch.Tensor, b: torch.Tensor | None, gamma: torch.Tensor, beta: torch.Tensor):
+    """Load-time pack for a LayerNorm folded into the Linear that follows it:
+    LN(x) W^T + b = rstd (x W'^T - mean csum) + b'   with W' = bf16(W * gamma), csum = rowsum(W') and
+    b' = b + W beta (both fp32).  Returns (W' bf16 [N, K], csum fp32 [N], b' fp32 [N])."""
+    wf = w.float()
+    wp = (wf * gamma.float()[None, :]).to(BF16).contiguous()
+    csum = wp.float().sum(dim=1).contiguous()
+    bp = (wf @ beta.float()) + (b.float() if b is not None else 0.0)
+    return wp, csum, bp.contiguous()
+
+
+def pack_swiglu_f32(v12: torch.Tensor, H: int, Hp: int) -> torch.Tensor:
+    """The row interleave of pack_swiglu for an fp32 per-row vector [2H] -> [2Hp] (folded csum / bias)."""
+    out = torch.zeros((2 * Hp,), dtype=torch.float32, device=v12.device)
+    o = out.view(Hp // 128, 2, 128)
+    g = torch.zeros((Hp,), dtype=torch.float32, device=v12.device)
+    u = torch.zeros((Hp,), dtype=torch.float32, device=v12.device)
+    g[:H], u[:H] = v12[:H], v12[H:]
+    o[:, 0, :] = g.view(-1, 128)
+    o[:, 1, :] = u.view(-1, 128)
+    return out
 
 
 def pack_swiglu(w12: torch.Tensor, b12: torch.Tensor | None) -> tuple[torch.Tensor, torch.Tensor | None, int]:

@@ -243,3 +243,61 @@ def test_mingtok_data_movement(cuda_device):
     ops.fill_cls_row(xx, cls, pos)
     assert torch.equal(xx[:, 4], (cls.float() + pos.float()).to(BF16).expand(B, -1))
     assert (xx[:, :4] == 0).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(4160, 2304, 768), (300, 1000, 264), (16384, 1024, 1024)])
+@pytest.mark.parametrize("epi", ["bias", "gelu", "swiglu"])
+def test_gemm_layernorm_fold(cuda_device, tile, M, N, K, epi):
+    """LayerNorm folded into the GEMM epilogue == F.layer_norm followed by the Linear (+ activation)."""
+    from ming_univision_b200 import ops
+
+    if tile in ("pair128", "single128", "single128-direct") and epi == "swiglu":
+        pytest.skip("SwiGLU uses 256-wide tiles")
+    x = (_rand((M, K), cuda_device, 1.5, 50).float() + 0.7).to(BF16)  # non-zero mean exercises the mean * csum term
+    gamma = (_rand((K,), cuda_device, 0.1, 51).float() + 1).to(BF16)
+    beta = _rand((K,), cuda_device, 0.1, 52)
+    ln = F.layer_norm(x.float(), (K,), gamma.float(), beta.float(), 1e-6)
+    stats = ops.row_stats(x)
+    assert torch.allclose(stats[:, 0], x.float().sum(1), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (x.float() ** 2).sum(1), rtol=1e-5, atol=1e-2)
+    if epi == "swiglu":
+        H = 344 if N == 1000 else N // 2
+        w12 = _rand((2 * H, K), cuda_device, 1.0 / math.sqrt(K), 53)
+        b12 = _rand((2 * H,), cuda_device, 0.2, 54)
+        wf, cs, bf = ops.fold_layernorm(w12, b12, gamma, beta)
+        wp, _, Hp = ops.pack_swiglu(wf, None)
+        out = ops.linear(x, wp, None, epi=ops.EPI_SWIGLU,
+                         ln_fold=(stats, ops.pack_swiglu_f32(cs, H, Hp), ops.pack_swiglu_f32(bf, H, Hp), 1e-6))
+        x12 = ln @ w12.float().t() + b12.float()
+        ref = F.silu(x12[:, :H]) * x12[:, H:]
+        got = out[:, :H]
+        assert (out[:, H:].float() == 0).all()
+    else:
+        w = _rand((N, K), cuda_device, 1.0 / math.sqrt(K), 55)
+        b = _rand((N,), cuda_device, 0.5, 56)
+        wf, cs, bf = ops.fold_layernorm(w, b, gamma, beta)
+        out = ops.linear(x, wf, None, epi=ops.EPI_GELU if epi == "gelu" else ops.EPI_BIAS, ln_fold=(stats, cs, bf, 1e-6))
+        ref = ln @ w.float().t() + b.float()
+        if epi == "gelu":
+            ref = F.gelu(ref)
+        got = out
+    # bf16 operands (x and gamma-scaled W) + bf16 output: same error budget as LN -> bf16 -> GEMM
+    assert _rel_err(got, ref) < 1e-2
+    assert ((got.float() - ref).abs() <= 3e-2 * ref.abs() + 5e-2).all()
+
+
+def test_gemm_residual_row_stats(cuda_device, tile):
+    """The RESIDUAL epilogue leaves (sum, sum of squares) of every row it wrote — the input of the next folded GEMM."""
+    from ming_univision_b200 import ops
+
+    if tile.endswith("-direct"):
+        pytest.skip("row statistics come from the staged (TMA) epilogue")
+    M, N, K = 4160, 1024, 1024
+    x = _rand((M, K), cuda_device, 1.0, 60)
+    w = _rand((N, K), cuda_device, 1.0 / math.sqrt(K), 61)
+    b = _rand((N,), cuda_device, 0.5, 62)
+    stream = _rand((M, N), cuda_device, 1.0, 63)
+    stats = torch.full((M, 2), 123.0, dtype=torch.float32, device=cuda_device)
+    ops.linear(x, w, b, epi=ops.EPI_RESIDUAL, residual=stream, out=stream, stats_out=stats)
+    assert torch.allclose(stats[:, 0], stream.float().sum(1), rtol=1e-4, atol=5e-2)
+    assert torch.allclose(stats[:, 1], (stream.float() ** 2).sum(1), rtol=1e-4, atol=5e-2)
