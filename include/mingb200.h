@@ -74,18 +74,20 @@ int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const v
 /* The same GEMM with a LayerNorm FOLDED into it (removes the LayerNorm kernel and its read + write of the activation
  * tensor between a residual GEMM and the qkv / w12 / fc1 GEMM that consumes the normalised rows;
  * block.py:80-105: x + attn(norm1(x)), x + mlp(norm2(x))):
- *   producer side  (epi = MB_EPI_RESIDUAL, ln_stats_out != NULL): while writing its rows the epilogue accumulates, per
- *       row, (sum, sum of squares) of the bf16 values it stores into ln_stats_out[M][2] (zeroed by this call);
+ *   producer side  (epi = MB_EPI_RESIDUAL, ln_stats_out != NULL): while writing its rows the epilogue stores, per row
+ *       and per 64-column box, (sum, sum of squares) of the bf16 values it writes into
+ *       ln_stats_out[M][ceil(N / 64)][2] — every slot written exactly once, no atomics, bitwise reproducible;
  *   consumer side  (ln_stats_in != NULL): A holds the UN-normalised rows; W must be pre-scaled by gamma
  *       (W' = bf16(W * gamma)), ln_csum[n] = sum_k W'[n, k] and ln_bias_f32[n] = bias[n] + sum_k W[n, k] beta[k] (fp32,
  *       packed at load time); the epilogue computes  rstd_r * (acc - mean_r * csum[n]) + bias_f32[n]  with
- *       mean / rstd from ln_stats_in, which equals  LN(A) W^T + bias  with fp32 statistics and no intermediate bf16
- *       rounding of the normalised activations.  `bias` is ignored on the consumer side.
+ *       mean / rstd from the ln_slots_in partial sums of ln_stats_in[M][ln_slots_in][2] (added in slot order), which
+ *       equals  LN(A) W^T + bias  with fp32 statistics and no intermediate bf16 rounding of the normalised
+ *       activations.  `bias` is ignored on the consumer side.
  * mb_row_stats seeds the chain for the first block of a stage. */
 int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                     int M, int N, int K, int epi, const void* residual, int64_t ldr, int res_row_mod,
-                    int out_row_group, int out_row_pad, const float* ln_stats_in, const float* ln_csum,
-                    const float* ln_bias_f32, float ln_eps, float* ln_stats_out, void* stream);
+                    int out_row_group, int out_row_pad, const float* ln_stats_in, int ln_slots_in,
+                    const float* ln_csum, const float* ln_bias_f32, float ln_eps, float* ln_stats_out, void* stream);
 int mb_row_stats(const void* x, int64_t ldx, float* stats, int rows, int dim, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -21,8 +21,8 @@ SIGNATURES = {
     "mb_device_ok": [],
     "mb_num_sms": [],
     "mb_gemm_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp],
-    "mb_gemm_bf16_ex": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _f,
-                        _vp, _vp],
+    "mb_gemm_bf16_ex": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _i, _i, _i, _vp, _i, _vp, _vp,
+                        _f, _vp, _vp],
     "mb_row_stats": [_vp, _i64, _vp, _i, _i, _vp],
     "mb_gemm_force_tile": [_i, _i],
     "mb_gemv_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],

@@ -161,20 +161,41 @@ __global__ void affine_kernel(const void* __restrict__ x_, __nv_bfloat16* __rest
   }
 }
 
-__global__ void inproj_repeat_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
-                                     const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, int rows,
-                                     int in_dim, int dim) {
-  __shared__ float xs[64];
-  const int r = blockIdx.x;
-  if (threadIdx.x < in_dim) xs[threadIdx.x] = __bfloat162float(x[static_cast<int64_t>(r) * in_dim + threadIdx.x]);
+// in_proj (K = in_dim <= 64) + repeat shortcut.  The whole weight ([dim, in_dim] bf16, 64 KB for 1024 x 32) is staged
+// TRANSPOSED in shared memory once per CTA and reused for kRowsPerCta rows, so it is read from L2 ~130 times per call
+// instead of once per row (the first version spent 256 us re-reading it 4160 times).
+constexpr int kInprojRows = 32;
+__global__ void __launch_bounds__(256)
+inproj_repeat_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ W,
+                     const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ out, int rows, int in_dim,
+                     int dim) {
+  extern __shared__ __align__(16) uint8_t inproj_smem[];
+  __nv_bfloat16* sWt = reinterpret_cast<__nv_bfloat16*>(inproj_smem);               // [in_dim][dim]  (k-major)
+  float* sx = reinterpret_cast<float*>(inproj_smem + static_cast<size_t>(in_dim) * dim * 2);  // [kInprojRows][in_dim]
+  for (int i = threadIdx.x; i < in_dim * dim; i += blockDim.x) {
+    const int j = i / in_dim, k = i % in_dim;  // coalesced read of W[j][k]
+    sWt[k * dim + j] = W[i];
+  }
+  const int r0 = blockIdx.x * kInprojRows;
+  const int nr = min(kInprojRows, rows - r0);
+  for (int i = threadIdx.x; i < nr * in_dim; i += blockDim.x)
+    sx[i] = __bfloat162float(x[static_cast<int64_t>(r0) * in_dim + i]);
   __syncthreads();
   const int rep = dim / in_dim;
   for (int j = threadIdx.x; j < dim; j += blockDim.x) {
-    const __nv_bfloat16* w = W + static_cast<int64_t>(j) * in_dim;
-    float acc = 0.f;
-    for (int k = 0; k < in_dim; ++k) acc += __bfloat162float(w[k]) * xs[k];
-    const float lin = bf16_round(acc + (b ? __bfloat162float(b[j]) : 0.f));
-    out[static_cast<int64_t>(r) * dim + j] = __float2bfloat16_rn(lin + xs[j / rep]);
+    const float bj = b ? __bfloat162float(b[j]) : 0.f;
+    float wj[64];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) wj[k] = (k < in_dim) ? __bfloat162float(sWt[k * dim + j]) : 0.f;
+    for (int r = 0; r < nr; ++r) {
+      const float* xr = sx + r * in_dim;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+        if (k < in_dim) acc = fmaf(wj[k], xr[k], acc);
+      const float lin = bf16_round(acc + bj);
+      out[static_cast<int64_t>(r0 + r) * dim + j] = __float2bfloat16_rn(lin + xr[j / rep]);
+    }
   }
 }
 
@@ -197,22 +218,27 @@ __global__ void pixel_shuffle_kernel(const __nv_bfloat16* __restrict__ in, __nv_
 
 template <bool kFp32Out>
 __global__ void unpatchify_clamp_kernel(const __nv_bfloat16* __restrict__ x, void* __restrict__ img_, int B, int g,
-                                        int p, int64_t total) {
+                                        int p, int64_t total_pix) {
+  // one thread per output pixel: its 3 channels are adjacent in x (channel-last inside the patch) and go to the 3
+  // planes of the NCHW image; consecutive threads walk along the image row, so both sides are coalesced
   const int HW = g * p;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total_pix;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int xw = static_cast<int>(idx % HW);
     const int yh = static_cast<int>((idx / HW) % HW);
-    const int c = static_cast<int>((idx / (static_cast<int64_t>(HW) * HW)) % 3);
-    const int b = static_cast<int>(idx / (static_cast<int64_t>(HW) * HW * 3));
+    const int b = static_cast<int>(idx / (static_cast<int64_t>(HW) * HW));
     const int h = yh / p, pp = yh % p, w = xw / p, q = xw % p;
-    const int64_t src = ((static_cast<int64_t>(b) * g * g + h * g + w) * (p * p) + pp * p + q) * 3 + c;
-    float v = __bfloat162float(x[src]);
-    v = fminf(fmaxf(v, -1.f), 1.f);
-    if (kFp32Out)
-      static_cast<float*>(img_)[idx] = v;
-    else
-      static_cast<__nv_bfloat16*>(img_)[idx] = __float2bfloat16_rn(v);
+    const int64_t src = ((static_cast<int64_t>(b) * g * g + h * g + w) * (p * p) + pp * p + q) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = __bfloat162float(x[src + c]);
+      v = fminf(fmaxf(v, -1.f), 1.f);
+      const int64_t dst = ((static_cast<int64_t>(b) * 3 + c) * HW + yh) * HW + xw;
+      if (kFp32Out)
+        static_cast<float*>(img_)[dst] = v;
+      else
+        static_cast<__nv_bfloat16*>(img_)[dst] = __float2bfloat16_rn(v);
+    }
   }
 }
 
@@ -347,7 +373,14 @@ extern "C" int mb_inproj_repeat(const void* x, const void* W, const void* b, voi
   MB_CHECK_ARG(in_dim >= 1 && in_dim <= 64 && dim % in_dim == 0, MB_ERR_SHAPE,
                "mb_inproj_repeat: need in_dim <= 64 and dim %% in_dim == 0 (in_dim=%d dim=%d)", in_dim, dim);
   if (rows == 0) return MB_OK;
-  inproj_repeat_kernel<<<rows, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
+  const size_t smem = static_cast<size_t>(in_dim) * dim * 2 + static_cast<size_t>(kInprojRows) * in_dim * 4;
+  MB_CHECK_ARG(smem <= 200 * 1024, MB_ERR_SHAPE, "mb_inproj_repeat: in_dim * dim too large");
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(inproj_repeat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  inproj_repeat_kernel<<<(rows + kInprojRows - 1) / kInprojRows, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(x),
                                                  static_cast<const __nv_bfloat16*>(W),
                                                  static_cast<const __nv_bfloat16*>(b),
                                                  static_cast<__nv_bfloat16*>(out), rows, in_dim, dim);
@@ -370,7 +403,7 @@ extern "C" int mb_pixel_shuffle(const void* in, void* out, int B, int g, int f, 
 extern "C" int mb_unpatchify_clamp(const void* x, void* img, int out_is_fp32, int B, int g, int p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_unpatchify_clamp: no sm_100 device");
-  const int64_t total = static_cast<int64_t>(B) * 3 * g * p * g * p;
+  const int64_t total = static_cast<int64_t>(B) * g * p * g * p;  // pixels; each thread writes the 3 channels
   if (total == 0) return MB_OK;
   if (out_is_fp32)
     unpatchify_clamp_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), img,

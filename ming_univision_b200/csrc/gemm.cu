@@ -44,11 +44,13 @@ struct GemmParams {
   int tma_epi;  // 1: epilogue goes through shared-memory staging + TMA store (and TMA load of the residual)
   // LayerNorm folded into this GEMM (see mb_gemm_bf16_ex): A holds the UN-normalised rows, W already carries gamma,
   //   out = rstd[r] * (acc - mean[r] * csum[n]) + bias_f32[n]
-  const float* ln_stats_in;   // [M][2] per-row (sum, sum of squares) of A, or NULL
+  const float* ln_stats_in;   // [M][ln_slots_in][2] per-row partial (sum, sum of squares) of A, or NULL
+  int ln_slots_in;
   const float* ln_csum;       // [N]    row sums of the gamma-scaled weight (fp32)
   const float* ln_bias;       // [N]    bias + W . beta (fp32)
   float ln_inv_dim, ln_eps;
-  float* ln_stats_out;        // [M][2] RESIDUAL epilogue: accumulates (sum, sumsq) of the rows it writes, or NULL
+  float* ln_stats_out;        // [M][ceil(N/64)][2] RESIDUAL epilogue: (sum, sumsq) of every 64-column box it writes
+  int ln_slots_out;           //   (one slot per box, each written exactly once: deterministic, no atomics)
 };
 
 template <int BN, int CG>
@@ -326,11 +328,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(quad * 32) << 16);
       float ln_mean = 0.f, ln_rstd = 1.f;
       if (p.ln_stats_in != nullptr && row_ok) {
-        const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats_in) + row);
-        ln_mean = st.x * p.ln_inv_dim;
-        ln_rstd = rsqrtf(fmaxf(st.y * p.ln_inv_dim - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        const float2* sp = reinterpret_cast<const float2*>(p.ln_stats_in) + static_cast<int64_t>(row) * p.ln_slots_in;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < p.ln_slots_in; ++i) {  // fixed order -> bitwise reproducible
+          const float2 st = __ldg(sp + i);
+          s1 += st.x;
+          s2 += st.y;
+        }
+        ln_mean = s1 * p.ln_inv_dim;
+        ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_dim - ln_mean * ln_mean, 0.f) + p.ln_eps);
       }
-      float st_sum = 0.f, st_sq = 0.f;
 
       if (p.tma_epi) {
         // ---- staged path: registers -> 128B-swizzled smem box (32 rows x 64 cols) -> one TMA store per box; the
@@ -343,6 +350,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int box_tc = half * kColsPerWarp + bx * 64;   // first column of the box inside the output tile
           const int box_col = n_tile * kOutTileN + box_tc;    // global output column
           if (box_col >= n_out_total || row0 >= p.M) continue;  // warp-uniform
+          float st_sum = 0.f, st_sq = 0.f;
           if (lane == 0) tma_store_wait_read<0>();            // previous box fully read out of the staging buffer
           __syncwarp();
           if constexpr (EPI == MB_EPI_RESIDUAL) {
@@ -391,7 +399,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4)) = q;
             }
           }
-          if constexpr (EPI == MB_EPI_RESIDUAL) epi_phase ^= 1;
+          if constexpr (EPI == MB_EPI_RESIDUAL) {
+            epi_phase ^= 1;
+            if (p.ln_stats_out != nullptr && row_ok)
+              reinterpret_cast<float2*>(p.ln_stats_out)[static_cast<int64_t>(row) * p.ln_slots_out + (box_col >> 6)] =
+                  make_float2(st_sum, st_sq);
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -430,12 +443,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
-        }
-      }
-      if constexpr (EPI == MB_EPI_RESIDUAL) {
-        if (p.ln_stats_out != nullptr && p.tma_epi && row_ok) {
-          atomicAdd(p.ln_stats_out + 2 * row, st_sum);
-          atomicAdd(p.ln_stats_out + 2 * row + 1, st_sq);
         }
       }
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
@@ -531,14 +538,14 @@ extern "C" int mb_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
                             int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
                             int res_row_mod, int out_row_group, int out_row_pad, void* stream_) {
   return mb_gemm_bf16_ex(A, lda, W, ldw, bias, out, ldo, M, N, K, epi, residual, ldr, res_row_mod, out_row_group,
-                         out_row_pad, nullptr, nullptr, nullptr, 0.f, nullptr, stream_);
+                         out_row_pad, nullptr, 0, nullptr, nullptr, 0.f, nullptr, stream_);
 }
 
 extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
                                int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
                                int res_row_mod, int out_row_group, int out_row_pad, const float* ln_stats_in,
-                               const float* ln_csum, const float* ln_bias_f32, float ln_eps, float* ln_stats_out,
-                               void* stream_) {
+                               int ln_slots_in, const float* ln_csum, const float* ln_bias_f32, float ln_eps,
+                               float* ln_stats_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_gemm_bf16: no sm_100 device");
   MB_CHECK_ARG(M >= 0 && N >= 1 && K >= 1, MB_ERR_SHAPE, "mb_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
@@ -582,19 +589,20 @@ extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_
                        (reinterpret_cast<uintptr_t>(residual) & 15) == 0;
   p.tma_epi = tma_epi ? 1 : 0;
   p.ln_stats_in = ln_stats_in;
+  p.ln_slots_in = ln_slots_in;
+  p.ln_slots_out = (n_out + 63) / 64;
   p.ln_csum = ln_csum;
   p.ln_bias = ln_bias_f32;
   p.ln_inv_dim = 1.0f / static_cast<float>(K);
   p.ln_eps = ln_eps;
   p.ln_stats_out = ln_stats_out;
   if (ln_stats_in != nullptr)
-    MB_CHECK_ARG(ln_csum != nullptr && ln_bias_f32 != nullptr && epi != MB_EPI_RESIDUAL &&
+    MB_CHECK_ARG(ln_csum != nullptr && ln_bias_f32 != nullptr && epi != MB_EPI_RESIDUAL && ln_slots_in >= 1 &&
                      (reinterpret_cast<uintptr_t>(ln_csum) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_bias_f32) & 15) == 0,
                  MB_ERR_SHAPE, "mb_gemm_bf16_ex: LayerNorm fold needs 16-byte aligned csum / bias_f32 and a non-residual epilogue");
   if (ln_stats_out != nullptr) {
     MB_CHECK_ARG(epi == MB_EPI_RESIDUAL && tma_epi, MB_ERR_SHAPE,
                  "mb_gemm_bf16_ex: row statistics are produced by the dense RESIDUAL epilogue only");
-    MB_CHECK_CUDA(cudaMemsetAsync(ln_stats_out, 0, static_cast<size_t>(M) * 2 * sizeof(float), stream));
   }
   CUtensorMap to = ta, tr = ta;  // valid placeholders when unused
   if (tma_epi) {

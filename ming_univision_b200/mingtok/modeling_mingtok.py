@@ -200,12 +200,14 @@ def _run_block_folded(pb: _PackedBlock, x: torch.Tensor, B: int, S: int, H: int,
     LayerNorm kernel, no normalised copy of the activations in HBM / L2.  Returns the statistics of the new x."""
     qkv = ops.linear(x, pb.qkv_f[0], None, ln_fold=(stats, pb.qkv_f[1], pb.qkv_f[2], LN_EPS))
     a = ops.attention_hd64(qkv, B, S, H, causal)
-    st_mid = torch.empty_like(stats)
+    rows, D = x.shape[0] * x.shape[1], x.shape[-1]
+    st_mid = torch.empty((rows, (D + 63) // 64, 2), dtype=torch.float32, device=x.device)
     ops.linear(a, pb.proj_w, pb.proj_b, epi=ops.EPI_RESIDUAL, residual=x, out=x, stats_out=st_mid)
     hid = ops.linear(x, pb.w1_f[0], None, epi=ops.EPI_SWIGLU if pb.ffn == "swiglu" else ops.EPI_GELU,
                      ln_fold=(st_mid, pb.w1_f[1], pb.w1_f[2], LN_EPS))
-    ops.linear(hid, pb.w2, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x, stats_out=stats)
-    return stats
+    st_out = torch.empty_like(st_mid)
+    ops.linear(hid, pb.w2, pb.b2, epi=ops.EPI_RESIDUAL, residual=x, out=x, stats_out=st_out)
+    return st_out
 
 
 def _run_blocks(blocks, x: torch.Tensor, B: int, S: int, H: int, causal: bool) -> torch.Tensor:
@@ -215,7 +217,7 @@ def _run_blocks(blocks, x: torch.Tensor, B: int, S: int, H: int, causal: bool) -
         return x
     stats = ops.row_stats(x)
     for pb in blocks:
-        _run_block_folded(pb, x, B, S, H, causal, stats)
+        stats = _run_block_folded(pb, x, B, S, H, causal, stats)
     return x
 
 

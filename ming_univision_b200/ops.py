@@ -51,9 +51,9 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
            out_row_group: int = 0, out_row_pad: int = 0, ln_fold: tuple | None = None,
            stats_out: torch.Tensor | None = None) -> torch.Tensor:
     """out = epilogue(x @ weight.T + bias) on the tcgen05 GEMM.  x: [..., K], weight: [N, K] (nn.Linear layout).
-    ln_fold = (stats [M, 2] fp32, csum [N] fp32, bias_f32 [N] fp32, eps): LayerNorm of x folded into the epilogue
-    (weight must be the gamma-scaled pack, see fold_layernorm); stats_out [M, 2] fp32: the RESIDUAL epilogue leaves the
-    per-row (sum, sum of squares) of what it wrote there for the next folded GEMM."""
+    ln_fold = (stats [M, S, 2] fp32, csum [N] fp32, bias_f32 [N] fp32, eps): LayerNorm of x folded into the epilogue
+    (weight must be the gamma-scaled pack, see fold_layernorm); stats_out [M, ceil(N/64), 2] fp32: the RESIDUAL
+    epilogue leaves per-row, per-64-column-box (sum, sum of squares) of what it wrote for the next folded GEMM."""
     _check_bf16(x, weight, bias, residual, out)
     lib = _lib.load()
     a = _rows2d(x)
@@ -88,14 +88,20 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
                               out_row_group, out_row_pad, _stream())
     else:
         st_in = cs = bf = None
-        eps = 0.0
+        eps, slots = 0.0, 0
         if ln_fold is not None:
             st_in, cs, bf, eps = ln_fold
             if st_in.dtype != torch.float32 or cs.dtype != torch.float32 or bf.dtype != torch.float32:
                 raise TypeError("ln_fold tensors must be fp32")
+            if st_in.dim() != 3 or st_in.shape[0] != M or st_in.shape[2] != 2 or not st_in.is_contiguous():
+                raise ValueError("ln_fold statistics must be a contiguous [M, S, 2] tensor")
+            slots = st_in.shape[1]
+        if stats_out is not None and (tuple(stats_out.shape) != (M, (n_out + 63) // 64, 2) or
+                                      stats_out.dtype != torch.float32 or not stats_out.is_contiguous()):
+            raise ValueError(f"stats_out must be a contiguous fp32 [{M}, {(n_out + 63) // 64}, 2] tensor")
         rc = lib.mb_gemm_bf16_ex(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
                                  out2.data_ptr(), out2.stride(0), M, N, K, epi, _ptr(r2), ldr, res_row_mod,
-                                 out_row_group, out_row_pad, _ptr(st_in), _ptr(cs), _ptr(bf), float(eps),
+                                 out_row_group, out_row_pad, _ptr(st_in), slots, _ptr(cs), _ptr(bf), float(eps),
                                  _ptr(stats_out), _stream())
     if prof is not None:
         ev1.record()
@@ -105,11 +111,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
 
 
 def row_stats(x: torch.Tensor) -> torch.Tensor:
-    """[rows, D] bf16 -> [rows, 2] fp32 (sum, sum of squares): seeds a chain of LayerNorm-folded GEMMs."""
+    """[rows, D] bf16 -> [rows, 1, 2] fp32 (sum, sum of squares): seeds a chain of LayerNorm-folded GEMMs."""
     _check_bf16(x)
     lib = _lib.load()
     x2 = _rows2d(x)
-    st = torch.empty((x2.shape[0], 2), dtype=torch.float32, device=x.device)
+    st = torch.empty((x2.shape[0], 1, 2), dtype=torch.float32, device=x.device)
     _lib.check(lib.mb_row_stats(x2.data_ptr(), x2.stride(0), st.data_ptr(), x2.shape[0], x2.shape[1], _stream()),
                "mb_row_stats")
     return st
