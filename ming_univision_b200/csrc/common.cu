@@ -2,6 +2,7 @@
 #include "common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mb {
@@ -54,6 +55,15 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint6
     return false;
   }
   return true;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MB_NO_PDL");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int num_sms() {

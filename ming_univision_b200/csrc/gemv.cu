@@ -74,6 +74,48 @@ gemv_bf16_kernel(const GemvParams p) {
   const int row_bytes = kgroups * 64 + 64;               // +64 B: consecutive token rows land in different bank halves
   const int n_out = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
 
+  const int item_slot = warp / KSPLIT, ks = warp % KSPLIT;
+  const int per = (kgroups + KSPLIT - 1) / KSPLIT;
+  const int kg_beg = ks * per, kg_end = min(kgroups, kg_beg + per);
+  const int n_items = (n_out + 15) / 16;
+  const int iters = (n_items + gridDim.x * kItemsPerIter - 1) / (gridDim.x * kItemsPerIter);
+
+  auto row_ptrs = [&](int it, const __nv_bfloat16* (&wr)[kTiles][2], int& n0, bool& item_valid) {
+    const int item = (it * gridDim.x + blockIdx.x) * kItemsPerIter + item_slot;
+    item_valid = item < n_items;
+    n0 = (item_valid ? item : 0) * 16;
+#pragma unroll
+    for (int tl = 0; tl < kTiles; ++tl) {
+      const int base = tl * n_out;  // the rows this lane streams (clamped at the matrix edge; never stored if clamped)
+      wr[tl][0] = p.W + static_cast<int64_t>(base + min(n0 + g, n_out - 1)) * p.ldw + t * 8;
+      wr[tl][1] = p.W + static_cast<int64_t>(base + min(n0 + g + 8, n_out - 1)) * p.ldw + t * 8;
+    }
+  };
+  auto load_batch = [&](const __nv_bfloat16* (&wr)[kTiles][2], int kg0, uint4 (&w)[kTiles][2][kUnroll]) {
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int kg = kg0 + u;
+      const bool ok = kg < kg_end && (kg * 4 + t) < kchunks;
+#pragma unroll
+      for (int tl = 0; tl < kTiles; ++tl) {
+        w[tl][0][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][0] + kg * 32)) : make_uint4(0, 0, 0, 0);
+        w[tl][1][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][1] + kg * 32)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+
+  // PDL: let the next kernel of the stream start launching, and put this warp's FIRST batch of weight loads in flight
+  // before anything else: weights do not depend on the predecessor, so their DRAM latency overlaps the predecessor's
+  // tail, the wait, and the staging of the activations below
+  pdl_launch_dependents();
+  const __nv_bfloat16* wr0[kTiles][2];
+  int n0_first;
+  bool valid_first;
+  row_ptrs(0, wr0, n0_first, valid_first);
+  uint4 w[kTiles][2][kUnroll];
+  load_batch(wr0, kg_beg, w);
+  pdl_wait();
+
   // stage the activations: rows 0..M-1, then one zero row shared by the unused MMA columns
   for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
     const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
@@ -84,39 +126,17 @@ gemv_bf16_kernel(const GemvParams p) {
   __syncthreads();
   const uint8_t* xrow = gemv_smem + min(g, p.M) * row_bytes + t * 16;
 
-  const int item_slot = warp / KSPLIT, ks = warp % KSPLIT;
-  const int per = (kgroups + KSPLIT - 1) / KSPLIT;
-  const int kg_beg = ks * per, kg_end = min(kgroups, kg_beg + per);
-  const int n_items = (n_out + 15) / 16;
-  const int iters = (n_items + gridDim.x * kItemsPerIter - 1) / (gridDim.x * kItemsPerIter);
   for (int it = 0; it < iters; ++it) {
-    const int item = (it * gridDim.x + blockIdx.x) * kItemsPerIter + item_slot;
-    const bool item_valid = item < n_items;
-    const int n0 = (item_valid ? item : 0) * 16;
-    // the two rows this lane streams (clamped at the matrix edge; the results of clamped rows are never stored)
     const __nv_bfloat16* wr[kTiles][2];
-#pragma unroll
-    for (int tl = 0; tl < kTiles; ++tl) {
-      const int base = tl * n_out;
-      wr[tl][0] = p.W + static_cast<int64_t>(base + min(n0 + g, n_out - 1)) * p.ldw + t * 8;
-      wr[tl][1] = p.W + static_cast<int64_t>(base + min(n0 + g + 8, n_out - 1)) * p.ldw + t * 8;
-    }
+    int n0;
+    bool item_valid;
+    row_ptrs(it, wr, n0, item_valid);
     float acc[kTiles][4];
 #pragma unroll
     for (int tl = 0; tl < kTiles; ++tl) acc[tl][0] = acc[tl][1] = acc[tl][2] = acc[tl][3] = 0.f;
 
     for (int kg0 = kg_beg; kg0 < kg_end; kg0 += kUnroll) {
-      uint4 w[kTiles][2][kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const int kg = kg0 + u;
-        const bool ok = kg < kg_end && (kg * 4 + t) < kchunks;
-#pragma unroll
-        for (int tl = 0; tl < kTiles; ++tl) {
-          w[tl][0][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][0] + kg * 32)) : make_uint4(0, 0, 0, 0);
-          w[tl][1][u] = ok ? ldg_stream(reinterpret_cast<const uint4*>(wr[tl][1] + kg * 32)) : make_uint4(0, 0, 0, 0);
-        }
-      }
+      if (!(it == 0 && kg0 == kg_beg)) load_batch(wr, kg0, w);  // the very first batch is already in flight
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const int kg = kg0 + u;
@@ -191,7 +211,7 @@ static int launch_gemv_ks(const GemvParams& p, int epi, int grid, size_t smem, c
                                          160 * 1024));                                                         \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    gemv_bf16_kernel<E_, KSPLIT><<<grid, kGemvThreads, smem, stream>>>(p);                                     \
+    MB_CHECK_CUDA(launch_pdl(gemv_bf16_kernel<E_, KSPLIT>, dim3(grid), dim3(kGemvThreads), smem, stream, p));  \
     break;                                                                                                     \
   }
   switch (epi) {

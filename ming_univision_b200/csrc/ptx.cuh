@@ -235,6 +235,17 @@ __device__ __forceinline__ float silu(float x) { return x * fast_rcp(1.0f + fast
 }  // namespace mb
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor drains; it must not touch memory the predecessor produces (or still reads) before
+// pdl_wait().  pdl_launch_dependents() lets the NEXT kernel in the stream start launching early.
+// ----------------------------------------------------------------------------------------------
+namespace mb {
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+}  // namespace mb
+
+// ----------------------------------------------------------------------------------------------
 // clusters / CTA pairs (cta_group::2)
 // ----------------------------------------------------------------------------------------------
 namespace mb {

@@ -30,6 +30,8 @@ adaln_modulate_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
                       const __nv_bfloat16* __restrict__ scale, int64_t ldsc, __nv_bfloat16* __restrict__ y, int64_t ldy,
                       int dim, float eps) {
   __shared__ float scratch[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
   const __nv_bfloat16* xr = x + m * ldx;
   float s = 0.f;
@@ -72,6 +74,8 @@ __global__ void silu_add_rows_kernel(const __nv_bfloat16* __restrict__ temb, con
 __global__ void rf_euler_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ x_bf16,
                                 const __nv_bfloat16* __restrict__ v, int B, int C, float dt, float text_cfg,
                                 float image_cfg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (B == 3) {
@@ -113,11 +117,11 @@ extern "C" int mb_adaln_modulate(const void* x, int64_t ldx, const void* gamma, 
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_adaln_modulate: no sm_100 device");
   MB_CHECK_ARG(rows >= 0 && dim >= 1 && shift && scale, MB_ERR_SHAPE, "mb_adaln_modulate: bad arguments");
   if (rows == 0) return MB_OK;
-  adaln_modulate_kernel<<<rows, 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma),
-      static_cast<const __nv_bfloat16*>(beta), static_cast<const __nv_bfloat16*>(shift), ld_shift,
-      static_cast<const __nv_bfloat16*>(scale), ld_scale, static_cast<__nv_bfloat16*>(y), ldy, dim, eps);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(adaln_modulate_kernel, dim3(rows), dim3(256), 0, stream,
+                           static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(gamma),
+                           static_cast<const __nv_bfloat16*>(beta), static_cast<const __nv_bfloat16*>(shift), ld_shift,
+                           static_cast<const __nv_bfloat16*>(scale), ld_scale, static_cast<__nv_bfloat16*>(y), ldy,
+                           dim, eps));
   return MB_OK;
 }
 
@@ -140,9 +144,8 @@ extern "C" int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_rf_euler_step: no sm_100 device");
   MB_CHECK_ARG(B >= 1 && B <= 8 && C >= 1, MB_ERR_SHAPE, "mb_rf_euler_step: bad shape B=%d C=%d", B, C);
-  rf_euler_kernel<<<(C + 63) / 64, 64, 0, stream>>>(static_cast<float*>(x_f32), static_cast<__nv_bfloat16*>(x_bf16),
-                                                    static_cast<const __nv_bfloat16*>(v), B, C, dt, text_cfg,
-                                                    image_cfg);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(rf_euler_kernel, dim3((C + 63) / 64), dim3(64), 0, stream, static_cast<float*>(x_f32),
+                           static_cast<__nv_bfloat16*>(x_bf16), static_cast<const __nv_bfloat16*>(v), B, C, dt,
+                           text_cfg, image_cfg));
   return MB_OK;
 }
