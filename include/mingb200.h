@@ -215,6 +215,9 @@ int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, void* q_out,
 int mb_attn_decode_gqa(const void* q, const void* kcache, const void* vcache, const int32_t* key_mask,
                        int64_t mask_stride, void* out, int B, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev,
                        int t_host, float scale, void* stream);
+/* Greedy next-token choice over fp32 logits [rows, V] (HF generate with do_sample = false, mingunivision/config.json:30;
+ * first index on ties, as torch.argmax). */
+int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, void* stream);
 /* BailingMoeGate.forward (:505-520) after the logits GEMM: fp32 softmax over E bf16 logits, top-k, renormalise.
  * With logits_img + image_mask (uint8 [T]) tokens flagged as image tokens use the image gate's logits (:574-580). */
 int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* image_mask, int32_t* idx,

@@ -32,6 +32,7 @@ SIGNATURES = {
     "mb_rmsnorm": [_vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp],
     "mb_rope_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
     "mb_attn_decode_gqa": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
+    "mb_argmax_f32": [_vp, _vp, _i, _i, _vp],
     "mb_router_topk": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -110,6 +110,8 @@ attn_fwd_kernel(const AttnParams p) {
     n_blocks = min(n_blocks, last_key / kBN + 1);
     if (last_key < 0) n_blocks = 0;
   }
+  pdl_launch_dependents();
+  pdl_wait();
 
   load_tile_async<HD, kBM>(sQ, gq, p.q_ts, q0, p.Sq, tid);
   if (n_blocks > 0) {
@@ -308,8 +310,7 @@ static int launch_attn_mt(const AttnParams& p, int B, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.Sq + 64 * MTW - 1) / (64 * MTW), p.Hq, B);
-  attn_fwd_kernel<HD, MTW><<<grid, 128, smem, stream>>>(p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(attn_fwd_kernel<HD, MTW>, grid, dim3(128), smem, stream, p));
   return MB_OK;
 }
 

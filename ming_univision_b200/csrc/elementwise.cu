@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
                  const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int dim,
                  float eps, int act, int rows_per_group, int64_t group_stride_x) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -289,9 +291,9 @@ extern "C" int mb_layernorm(const void* x, int64_t ldx, const void* gamma, const
   const __nv_bfloat16* gg = static_cast<const __nv_bfloat16*>(gamma);
   const __nv_bfloat16* bb = static_cast<const __nv_bfloat16*>(beta);
   __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
-#define MB_LN(NV_)                                                                                        \
-  layernorm_kernel<NV_><<<grid, block, 0, stream>>>(xx, ldx, gg, bb, yy, ldy, rows, dim, eps, act, rows_per_group, \
-                                                    group_stride_x)
+#define MB_LN(NV_)                                                                                           \
+  MB_CHECK_CUDA(launch_pdl(layernorm_kernel<NV_>, grid, block, 0, stream, xx, ldx, gg, bb, yy, ldy, rows, dim, eps,  \
+                           act, rows_per_group, group_stride_x))
   if (nv <= 1) MB_LN(1);
   else if (nv <= 2) MB_LN(2);
   else if (nv <= 3) MB_LN(3);

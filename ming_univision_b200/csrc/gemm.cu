@@ -245,9 +245,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail; from
+  // here on the roles touch global memory, each after its own pdl_wait()
+  pdl_launch_dependents();
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
@@ -315,6 +319,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_phase = 0;
+    pdl_wait();  // the epilogue reads bias / residual / statistics and overwrites buffers earlier kernels may still read
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
@@ -481,13 +486,15 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, EPI, CG>, ta, tb, to, tr, p));
   return MB_OK;
 }

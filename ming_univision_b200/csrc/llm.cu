@@ -421,9 +421,46 @@ __global__ void moe_finalize_kernel(const float* __restrict__ y_sum, const __nv_
   }
 }
 
+// greedy sampling: first index of the row maximum (torch.argmax tie rule)   one CTA per row
+__global__ void __launch_bounds__(256)
+argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int V) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const float* xr = x + static_cast<int64_t>(blockIdx.x) * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += 256) {
+    const float v = xr[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    out[blockIdx.x] = bi;
+  }
+}
+
 }  // namespace mb
 
 using namespace mb;
+
+extern "C" int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_argmax_f32: no sm_100 device");
+  MB_CHECK_ARG(rows >= 0 && V >= 1, MB_ERR_SHAPE, "mb_argmax_f32: bad shape");
+  if (rows == 0) return MB_OK;
+  argmax_f32_kernel<<<rows, 256, 0, stream>>>(x, out, V);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
 
 extern "C" int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, int rows, int dim, float eps,
                           void* stream_) {

@@ -126,3 +126,41 @@ class MingUniVisionForConditionalGeneration(nn.Module):
             noises=noises)
         self.past_key_values, self.past_attention_mask = cache, fmask[0:1]
         return img[0:1], fmask
+
+    @torch.no_grad()
+    def generate_text(self, input_ids, pixel_values=None, max_new_tokens: int = 32, eos_token_id=None):
+        """Image -> text understanding / plain text continuation (BASELINE configs[2] path): prefill `input_ids` with
+        the image features scattered at the `<imagePatch>` positions (routed by `image_gate`,
+        modeling_bailingmm.py:245-258), then greedy decoding — what `MingUniVisionForConditionalGeneration.generate`
+        does through HF GenerationMixin with do_sample = false (config.json:30).  Stops at `eos_token_id` (default:
+        config.pad_token_id = <|endoftext|>) or at the `<image>` start token (image generation is a separate call
+        here).  Returns the list of new token ids."""
+        llm, cfg = self.model, self.model.config
+        dev = input_ids.device
+        eos = cfg.pad_token_id if eos_token_id is None else eos_token_id
+        S = input_ids.shape[1]
+        emb = llm.model.embed(input_ids)
+        image_mask = None
+        if pixel_values is not None:
+            emb, image_mask = self.prompt_wrap_vision(input_ids, emb, self.extract_image_feature(pixel_values))
+        need = S + max_new_tokens + 8
+        cache = getattr(self, "_ws_cache", None)
+        if cache is None or cache.max_len < need or cache.k[0].device != dev:
+            cache = self._ws_cache = llm.new_cache(max_len=max(need, 512))
+            llm._gen_ws = {}
+        cache.seq_len, cache.batch = 0, 1
+        pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0)
+        hidden = llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
+        out_ids = []
+        last = hidden[:, -1]
+        for _ in range(max_new_tokens):
+            tok = ops.argmax_rows(llm.compute_logit(last).reshape(1, -1))
+            t = int(tok.item())  # per-token EOS check on the host, as HF generate does
+            out_ids.append(t)
+            if t == eos or t == cfg.image_start_token:
+                break
+            e = llm.model.embed(tok.view(1, 1).long())
+            p1 = torch.full((1, 1), cache.seq_len, dtype=torch.int32, device=dev)
+            last = llm.model.forward_tokens(e, p1, cache, key_mask=None)[:, -1]
+        self.past_key_values = cache
+        return out_ids

