@@ -245,12 +245,17 @@ def run_ours(args, world, rank, local):
     if sampler:
         sampler.start()
     launches0 = _lib.launch_count()
+    ncu_range = os.environ.get("MB_NCU_RANGE") == "1"  # tools/profile.sh: ncu --profile-from-start off
+    if ncu_range:
+        torch.cuda.profiler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         step_resident(i)
     e1.record()
     torch.cuda.synchronize()
+    if ncu_range:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     _barrier(world)
     ms_res = _max_over_ranks(e0.elapsed_time(e1), world, dev)

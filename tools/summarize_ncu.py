@@ -26,8 +26,8 @@ for row in csv.DictReader(lines):
     tot += v
 n_launch = sum(a[0] for a in agg.values())
 out = [f"# ncu launch list — {tag}", "",
-       f"`ncu --metrics gpu__time_duration.sum --clock-control none -s 2604 -c 900 python bench.py --steps 2 --warmup 3` "
-       f"(tools/profile.sh): {n_launch} consecutive launches of the timed region (~2.07 steps of 434 launches; "
+       f"`MB_NCU_RANGE=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python bench.py "
+       f"--steps 2 --warmup 3` (tools/profile.sh): the {n_launch} launches of the timed region (2 steps; "
        "per-launch times are serialised / cold-cache, so compare SHARES, not absolutes).", "",
        f"Total device time of the {n_launch} launches: {tot / 1e3:.2f} ms.", "",
        "| kernel | launches | total µs | share | avg µs |", "|---|---:|---:|---:|---:|"]
