@@ -232,8 +232,26 @@ int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets
                    void* hid, int T, int k, int E, int D, int I, void* stream);
 int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
                 void* out_pairs, int T, int k, int E, int D, int I, void* stream);
+/* pair_row == NULL: out_pairs is in (token, slot) order; else pair p = t*k+j lives in row pair_row[p] of out_pairs
+ * (grouped layout of mb_moe_plan; negative = expert not local, contributes zero). */
 int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual, void* y,
-                   float* y_partial, int T, int k, int D, void* stream);
+                   float* y_partial, const int32_t* pair_row, int T, int k, int D, void* stream);
+/* moe_infer (:608-639) for the PREFILL regime (hundreds of tokens per expert), on tcgen05 tensor cores:
+ * mb_moe_plan lays the (token, slot) pairs out bucket-sorted, bucket = (expert - e_begin) / div, every bucket's
+ * segment padded to `granule` rows (pair_row[T*k], row_token[max_rows], tile_expert[max_rows/128] or NULL,
+ * meta = {128-row tiles, rows}, counts[E] or NULL; max_rows >= roundup(T*k + (granule-1) E)).  granule = 128, div = 1
+ * is the tile plan of the grouped GEMMs; granule = 1, div = experts per rank orders an expert-parallel send buffer by
+ * destination rank.  mb_moe_gather_rows copies rows x[row_token[r]] into that layout (row count from meta[1] on the
+ * device, or max_rows when meta is NULL; negative indices give zero rows), and mb_moe_grouped_gemm runs
+ * one persistent TMA/tcgen05 GEMM over all experts: swiglu = 1 -> out[r, 0:I] = silu(A W_gate^T) * (A W_up^T) with
+ * W = [E][2I][K] (gate rows then up rows, no repack), swiglu = 0 -> out = A W^T with W = [E][N][K].  The number of
+ * tiles is read from meta on the device: no host synchronisation anywhere (the reference syncs per layer, :616). */
+int mb_moe_plan(const int32_t* idx, int32_t* pair_row, int32_t* row_token, int32_t* tile_expert, int32_t* meta,
+                int32_t* counts, int T, int k, int E, int e_begin, int div, int granule, int max_rows, void* stream);
+int mb_moe_gather_rows(const void* x, const int32_t* row_token, const int32_t* meta, void* out, int max_rows, int D,
+                       void* stream);
+int mb_moe_grouped_gemm(const void* A, const void* W, void* out, const int32_t* tile_expert,
+                        const int32_t* num_m_tiles, int max_rows, int N, int K, int E, int swiglu, void* stream);
 /* Expert parallelism (no reference implementation — the reference keeps all experts on one device):
  * rank r owns experts [e_begin, e_begin + E) — mb_moe_sort lists only the pairs routed to them, mb_moe_gate_up /
  * mb_moe_down run on the local slabs, mb_moe_combine with y_partial != NULL writes this rank's fp32 share of the

@@ -37,7 +37,10 @@ SIGNATURES = {
     "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "mb_moe_plan": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "mb_moe_grouped_gemm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mb_moe_finalize": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
     "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],

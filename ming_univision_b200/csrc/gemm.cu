@@ -51,6 +51,15 @@ struct GemmParams {
   float ln_inv_dim, ln_eps;
   float* ln_stats_out;        // [M][ceil(N/64)][2] RESIDUAL epilogue: (sum, sumsq) of every 64-column box it writes
   int ln_slots_out;           //   (one slot per box, each written exactly once: deterministic, no atomics)
+  // Grouped (per-expert) mode, mb_moe_grouped_gemm: A rows are expert-sorted and every expert's segment is padded to
+  // a multiple of 128 rows, so each 128-row M tile belongs to ONE expert; W is [E][N][K] and the tile's B rows start at
+  // expert * N.  The number of M tiles is data dependent and is read from device memory (no host sync).
+  const int32_t* grp_tile_expert;  // [max M tiles] expert of every M tile, or NULL (dense GEMM)
+  const int32_t* grp_num_m_tiles;  // device scalar
+  int grp_w_rows;             // rows of W per expert (N, or 2I for the [gate; up] slab)
+  int grp_n_out;              // output width (I or N)
+  int grp_split;              // > 0: the B tile is two (BN/2)-row boxes, rows n_tile*BN/2 and grp_split + n_tile*BN/2 of
+                              //      the expert's [gate; up] slab, so the SwiGLU epilogue needs no interleaved repack
 };
 
 template <int BN, int CG>
@@ -208,10 +217,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_tiles = (p.M + kTileM - 1) / kTileM;
+  const bool grouped = p.grp_tile_expert != nullptr;
   const int num_n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_k_blocks = (p.K + kBK - 1) / kBK;
+  // dense: from the shape; grouped: produced on the device by the routing plan -> read it after pdl_wait()
+  auto tile_count = [&]() -> int {
+    const int m_tiles = grouped ? __ldg(p.grp_num_m_tiles) : (p.M + kTileM - 1) / kTileM;
+    return m_tiles * num_n_tiles;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -252,13 +265,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       pdl_wait();
+      const int num_tiles = tile_count();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         const int m_tile = tile / num_n_tiles;
         const int n_tile = tile % num_n_tiles;
         const int a_row = m_tile * kTileM + static_cast<int>(cta_rank) * kBM;
-        const int b_row = n_tile * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        int b_row = n_tile * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+        if (grouped) {
+          const int e = __ldg(p.grp_tile_expert + m_tile);
+          b_row = e * p.grp_w_rows + (p.grp_split > 0 ? n_tile * (BN / 2) : n_tile * BN);
+        }
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (CG == 2) {
@@ -271,6 +289,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBK, a_row);
             tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBK, b_row);
+            if (p.grp_split > 0)  // second half of the B tile: the matching `up` rows (tmap_b box = BN/2 rows)
+              tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes + Cfg::kBBytes / 2, kb * kBK,
+                          b_row + p.grp_split);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -284,6 +305,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (grouped) pdl_wait();
+      const int num_tiles = tile_count();
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -315,11 +338,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int half = ew >> 2;           // which half of the tile's columns
     constexpr int kOutTileN = (EPI == MB_EPI_SWIGLU) ? BN / 2 : BN;
     constexpr int kColsPerWarp = kOutTileN / 2;
-    const int n_out_total = (EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N;
+    const int n_out_total = grouped ? p.grp_n_out : ((EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N);
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_phase = 0;
     pdl_wait();  // the epilogue reads bias / residual / statistics and overwrites buffers earlier kernels may still read
+    const int num_tiles = tile_count();
     for (int tile = worker; tile < num_tiles; tile += num_workers) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
@@ -603,6 +627,11 @@ extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_
   p.ln_inv_dim = 1.0f / static_cast<float>(K);
   p.ln_eps = ln_eps;
   p.ln_stats_out = ln_stats_out;
+  p.grp_tile_expert = nullptr;
+  p.grp_num_m_tiles = nullptr;
+  p.grp_split = 0;
+  p.grp_w_rows = 0;
+  p.grp_n_out = 0;
   if (ln_stats_in != nullptr)
     MB_CHECK_ARG(ln_csum != nullptr && ln_bias_f32 != nullptr && epi != MB_EPI_RESIDUAL && ln_slots_in >= 1 &&
                      (reinterpret_cast<uintptr_t>(ln_csum) & 15) == 0 && (reinterpret_cast<uintptr_t>(ln_bias_f32) & 15) == 0,
@@ -639,6 +668,55 @@ extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_
 #undef MB_DISPATCH_EPI
   set_error("mb_gemm_bf16: unreachable dispatch");
   return MB_ERR_SHAPE;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Grouped (per-expert) GEMM of the routed MoE experts, prefill regime (modeling_bailing_moe.py:609-639 replaces the
+// Python loop over experts + one cuBLAS call per expert and projection):
+//   swiglu = 1:  out[r, i] = bf16( bf16(silu(bf16(A[r] . Wg[e(r)][i]))) * bf16(A[r] . Wu[e(r)][i]) ),  W = [E][2I][K]
+//   swiglu = 0:  out[r, n] = bf16( A[r] . W[e(r)][n] ),                                               W = [E][N][K]
+// Rows are expert-sorted with every expert segment padded to 128 rows (mb_moe_plan), e(r) = tile_expert[r / 128].
+// Same tcgen05 / TMA kernel as the dense GEMM (128 x 256 tile per CTA, persistent over the device-side tile count).
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int mb_moe_grouped_gemm(const void* A, const void* W, void* out, const int32_t* tile_expert,
+                                   const int32_t* num_m_tiles, int max_rows, int N, int K, int E, int swiglu,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_grouped_gemm: no sm_100 device");
+  MB_CHECK_ARG(max_rows >= 0 && max_rows % 128 == 0 && N >= 8 && K >= 8 && E >= 1, MB_ERR_SHAPE,
+               "mb_moe_grouped_gemm: bad shape rows=%d N=%d K=%d E=%d (rows must be a multiple of 128)", max_rows, N, K, E);
+  if (max_rows == 0) return MB_OK;
+  const int n_out = swiglu ? N / 2 : N;
+  MB_CHECK_ARG(K % 8 == 0 && n_out % 8 == 0 && (!swiglu || N % 16 == 0), MB_ERR_ALIGN,
+               "mb_moe_grouped_gemm: K and the output width must be multiples of 8 (K=%d N=%d)", K, N);
+  MB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0 && tile_expert != nullptr && num_m_tiles != nullptr,
+               MB_ERR_ALIGN, "mb_moe_grouped_gemm: A/W/out must be 16-byte aligned, plan pointers non-null");
+  constexpr int BN = 256;
+  CUtensorMap ta, tb, to;
+  if (!make_tmap_2d_bf16(&ta, A, K, max_rows, K, kBK, kBM)) return MB_ERR_CUDA;
+  if (!make_tmap_2d_bf16(&tb, W, K, static_cast<uint64_t>(E) * N, K, kBK, swiglu ? BN / 2 : BN)) return MB_ERR_CUDA;
+  if (!make_tmap_2d_bf16(&to, out, n_out, max_rows, n_out, 64, 32)) return MB_ERR_CUDA;
+  GemmParams p = {};
+  p.M = max_rows;
+  // swiglu: one "N tile" = 128 gate + 128 up rows -> ceil(I / 128) tiles; the kernel derives that from p.N / BN
+  p.N = swiglu ? 2 * (((n_out + 127) / 128) * 128) : N;
+  p.K = K;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.ldo = n_out;
+  p.tma_epi = 1;
+  p.ln_inv_dim = 1.f;
+  p.ln_slots_out = (n_out + 63) / 64;
+  p.grp_tile_expert = tile_expert;
+  p.grp_num_m_tiles = num_m_tiles;
+  p.grp_split = swiglu ? n_out : 0;
+  p.grp_w_rows = N;
+  p.grp_n_out = n_out;
+  const int sms = mb::num_sms();
+  const long tiles = static_cast<long>(max_rows / 128) * ((p.N + BN - 1) / BN);
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  if (swiglu) return launch_gemm<256, MB_EPI_SWIGLU, 1>(ta, tb, to, ta, p, grid, stream);
+  return launch_gemm<256, MB_EPI_BIAS, 1>(ta, tb, to, ta, p, grid, stream);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -386,18 +386,116 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Routing plan: bucket-sorted row layout of the T*k (token, slot) pairs.  Bucket of pair p = (idx[p] - e_begin) / div
+// (pairs outside [0, E) buckets are "not local"), every bucket's segment padded to `granule` rows.  Two uses:
+//   * grouped (prefill) expert GEMMs: div = 1, granule = 128 -> each 128-row GEMM tile belongs to ONE local expert
+//   * expert-parallel dispatch:       div = experts per rank, granule = 1 -> send buffer ordered by destination rank
+//   pair_row[p]     row of pair p = t*k + j, or -1 if not local
+//   row_token[r]    source token (p / k) of row r, or -1 for padding rows
+//   tile_expert[m]  bucket of 128-row tile m (granule = 128 only; else NULL)
+//   meta[0] = number of 128-row tiles, meta[1] = number of rows incl. padding;  counts[b] = pairs in bucket b (or NULL)
+// Single CTA (T*k <= a few 10^4 pairs).  Row order inside a bucket is the arrival order of a shared-memory atomic: it
+// may differ from run to run, but every output row of the grouped GEMMs depends on its own input row only and the
+// combine addresses rows through pair_row, so the RESULTS are bitwise reproducible.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPlanThreads = 1024;
+__global__ void __launch_bounds__(kPlanThreads)
+moe_plan_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ pair_row, int32_t* __restrict__ row_token,
+                int32_t* __restrict__ tile_expert, int32_t* __restrict__ meta, int32_t* __restrict__ counts_out,
+                int npairs, int topk, int E, int e_begin, int div, int granule, int max_rows) {
+  extern __shared__ int32_t psm[];  // counts[E], pad_off[E + 1]
+  int32_t* counts = psm;
+  int32_t* pad_off = psm + E;
+  const int tid = threadIdx.x;
+  const int last = e_begin + E * div;  // first global expert id past the local buckets
+  for (int i = tid; i < E; i += kPlanThreads) counts[i] = 0;
+  for (int r = tid; r < max_rows; r += kPlanThreads) row_token[r] = -1;
+  __syncthreads();
+  // pass 1: rank of every local pair inside its bucket (smem atomic), parked in pair_row until the offsets exist
+  for (int p = tid; p < npairs; p += kPlanThreads) {
+    const int g = idx[p];
+    if (g >= e_begin && g < last) pair_row[p] = atomicAdd(&counts[(g - e_begin) / div], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {  // one warp: padded offsets by a shuffle scan over the buckets, 32 at a time
+    int rows_carry = 0;
+    for (int e0 = 0; e0 < E; e0 += 32) {
+      const int e = e0 + tid;
+      const int c = (e < E) ? counts[e] : 0;
+      const int padded = ((c + granule - 1) / granule) * granule;
+      int incl = padded;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      const int first = rows_carry + incl - padded;
+      if (e < E) {
+        pad_off[e] = first;
+        if (counts_out != nullptr) counts_out[e] = c;
+        if (tile_expert != nullptr)
+          for (int t = 0; t < (padded >> 7); ++t) tile_expert[(first >> 7) + t] = e;
+      }
+      rows_carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (tid == 0) {
+      pad_off[E] = rows_carry;
+      meta[0] = (rows_carry + 127) >> 7;
+      meta[1] = rows_carry;
+    }
+  }
+  __syncthreads();
+  for (int p = tid; p < npairs; p += kPlanThreads) {  // same thread wrote pair_row[p] in pass 1
+    const int g = idx[p];
+    int r = -1;
+    if (g >= e_begin && g < last) {
+      r = pad_off[(g - e_begin) / div] + pair_row[p];
+      row_token[r] = p / topk;
+    }
+    pair_row[p] = r;
+  }
+}
+
+// Ag[r] = x[row_token[r]] (zero rows for padding) for r < meta[1]; 16-byte vectors, one warp-row per loop step
+__global__ void __launch_bounds__(256)
+moe_gather_rows_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ row_token,
+                       const int32_t* __restrict__ meta, __nv_bfloat16* __restrict__ out, int n_rows_host, int D) {
+  const int rows = (meta != nullptr) ? meta[1] : n_rows_host;
+  const int vec_per_row = D >> 3;
+  const int64_t total = static_cast<int64_t>(rows) * vec_per_row;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / vec_per_row);
+    const int c = static_cast<int>(i % vec_per_row);
+    const int t = __ldg(row_token + r);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (t >= 0) v = __ldg(reinterpret_cast<const uint4*>(x + static_cast<int64_t>(t) * D) + c);
+    reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * D)[c] = v;
+  }
+}
+
 // y[t] = bf16( bf16( bf16(sum_j w[t,j] * out_pairs[t*k+j]) + shared[t] ) + residual[t] )
 // (moe_infer's fp32 weighted sum :632-638, `y + shared_experts(identity)` :604-605, layer residual :1226)
 __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ out_pairs, const float* __restrict__ w,
                                    const __nv_bfloat16* __restrict__ shared, const __nv_bfloat16* __restrict__ residual,
-                                   __nv_bfloat16* __restrict__ y, float* __restrict__ y_partial, int T, int k, int D) {
+                                   __nv_bfloat16* __restrict__ y, float* __restrict__ y_partial,
+                                   const int32_t* __restrict__ pair_row, int T, int k, int D) {
   const int64_t total = static_cast<int64_t>(T) * D;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t t = i / D;
     const int d = static_cast<int>(i % D);
     float acc = 0.f;
-    for (int j = 0; j < k; ++j) acc += w[t * k + j] * __bfloat162float(out_pairs[(t * k + j) * D + d]);
+    if (pair_row != nullptr) {  // grouped layout: pair p lives in row pair_row[p] (< 0: expert owned by another rank)
+      for (int j = 0; j < k; ++j) {
+        const int r = pair_row[t * k + j];
+        if (r >= 0) acc += w[t * k + j] * __bfloat162float(out_pairs[static_cast<int64_t>(r) * D + d]);
+      }
+    } else {
+      for (int j = 0; j < k; ++j) acc += w[t * k + j] * __bfloat162float(out_pairs[(t * k + j) * D + d]);
+    }
     if (y_partial != nullptr) {  // expert-parallel: this rank's share of the fp32 sum; finalised after the all-reduce
       y_partial[i] = acc;
       continue;
@@ -576,6 +674,42 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
                           static_cast<cudaStream_t>(stream_));
 }
 
+
+extern "C" int mb_moe_plan(const int32_t* idx, int32_t* pair_row, int32_t* row_token, int32_t* tile_expert,
+                           int32_t* meta, int32_t* counts, int T, int k, int E, int e_begin, int div, int granule,
+                           int max_rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_plan: no sm_100 device");
+  MB_CHECK_ARG(E >= 1 && E <= 4096 && e_begin >= 0 && k >= 1 && T >= 0 && div >= 1, MB_ERR_SHAPE,
+               "mb_moe_plan: bad bucket range");
+  MB_CHECK_ARG(granule == 1 || granule == 128, MB_ERR_SHAPE, "mb_moe_plan: granule must be 1 (dispatch) or 128 (GEMM tiles)");
+  MB_CHECK_ARG(granule == 128 || tile_expert == nullptr, MB_ERR_SHAPE, "mb_moe_plan: tile_expert needs granule 128");
+  // worst case: every bucket wastes granule - 1 padding rows
+  int64_t need = static_cast<int64_t>(T) * k + static_cast<int64_t>(E) * (granule - 1);
+  need = ((need + granule - 1) / granule) * granule;
+  MB_CHECK_ARG(max_rows % granule == 0 && max_rows >= need, MB_ERR_SHAPE,
+               "mb_moe_plan: max_rows=%d must be a multiple of %d and >= %ld", max_rows, granule, (long)need);
+  const size_t smem = (2 * static_cast<size_t>(E) + 1) * sizeof(int32_t);
+  moe_plan_kernel<<<1, kPlanThreads, smem, stream>>>(idx, pair_row, row_token, tile_expert, meta, counts, T * k, k, E,
+                                                     e_begin, div, granule, max_rows);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_moe_gather_rows(const void* x, const int32_t* row_token, const int32_t* meta, void* out, int max_rows,
+                                  int D, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_gather_rows: no sm_100 device");
+  MB_CHECK_ARG(D % 8 == 0 && max_rows >= 0, MB_ERR_SHAPE, "mb_moe_gather_rows: D must be a multiple of 8");
+  if (max_rows == 0) return MB_OK;
+  int64_t blocks = (static_cast<int64_t>(max_rows) * (D / 8) + 255) / 256;
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  moe_gather_rows_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), row_token, meta, static_cast<__nv_bfloat16*>(out), max_rows, D);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
 extern "C" int mb_moe_finalize(const float* y_sum, const void* shared, const void* residual, void* y, int T, int D,
                                void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -592,7 +726,7 @@ extern "C" int mb_moe_finalize(const float* y_sum, const void* shared, const voi
 }
 
 extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual,
-                              void* y, float* y_partial, int T, int k, int D, void* stream_) {
+                              void* y, float* y_partial, const int32_t* pair_row, int T, int k, int D, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_combine: no sm_100 device");
   const int64_t total = static_cast<int64_t>(T) * D;
@@ -602,7 +736,7 @@ extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const
   moe_combine_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out_pairs), weights,
                                                static_cast<const __nv_bfloat16*>(shared),
                                                static_cast<const __nv_bfloat16*>(residual),
-                                               static_cast<__nv_bfloat16*>(y), y_partial, T, k, D);
+                                               static_cast<__nv_bfloat16*>(y), y_partial, pair_row, T, k, D);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

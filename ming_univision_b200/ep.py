@@ -1,0 +1,69 @@
+"""Expert-parallel exchange for the routed MoE experts: one process per GPU, NCCL over NVLink.
+
+The reference keeps all 64 experts on one device (modeling_bailing_moe.py:543-549); there is nothing to mirror.  Here the
+experts are sharded (rank r owns experts [r E/G, (r+1) E/G)) and, for prefill-sized inputs, so are the tokens of the MoE
+block: every rank routes its slice of the tokens, the (token, slot) rows travel to the rank that owns their expert in ONE
+all-to-all, come back in a second all-to-all after the grouped expert GEMMs, are combined in fp32 at the owner (the
+reference's summation order, :632-638), and the slices are all-gathered for the replicated attention of the next layer.
+
+`torch.distributed` is the plumbing (all_to_all_single / all_gather_into_tensor); the row layouts on both sides are
+produced by the CUDA routing-plan kernel (mb_moe_plan with granule 1: rows ordered by destination rank).  The class is
+device- and dtype-agnostic so the world-size-2 gloo test can drive it on CPU tensors.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class ExpertParallelAllToAll:
+    """All-to-all dispatch / return of variable-length row blocks between the ranks of `group`."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.size = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def exchange_counts(self, send_counts: torch.Tensor) -> tuple[list[int], list[int]]:
+        """send_counts int32 [G] (rows for every destination) -> (send_splits, recv_splits) as host lists.
+        One tiny all-to-all plus ONE host read per call (the reference reads the per-expert counts on the host in
+        every layer too, modeling_bailing_moe.py:616)."""
+        if send_counts.numel() != self.size:
+            raise ValueError(f"send_counts must have {self.size} entries")
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        both = torch.stack([send_counts, recv_counts]).tolist()
+        return [int(v) for v in both[0]], [int(v) for v in both[1]]
+
+    def dispatch(self, send_rows: torch.Tensor, send_ids: torch.Tensor, send_splits: list[int],
+                 recv_splits: list[int]) -> tuple[torch.Tensor, torch.Tensor]:
+        """send_rows [n, D] ordered by destination rank (send_splits rows each) with their expert ids send_ids [n] ->
+        (recv_rows [m, D], recv_ids [m]) ordered by source rank."""
+        if send_rows.shape[0] != sum(send_splits) or send_ids.shape[0] != send_rows.shape[0]:
+            raise ValueError("send buffer does not match the split sizes")
+        m = sum(recv_splits)
+        recv_rows = send_rows.new_empty((m, send_rows.shape[1]))
+        recv_ids = send_ids.new_empty((m,))
+        dist.all_to_all_single(recv_rows, send_rows.contiguous(), recv_splits, send_splits, group=self.group)
+        dist.all_to_all_single(recv_ids, send_ids.contiguous(), recv_splits, send_splits, group=self.group)
+        return recv_rows, recv_ids
+
+    def combine(self, out_rows: torch.Tensor, send_splits: list[int], recv_splits: list[int]) -> torch.Tensor:
+        """The way back: out_rows [m, D] in arrival order of `dispatch` -> [n, D] in the order the rows were sent."""
+        if out_rows.shape[0] != sum(recv_splits):
+            raise ValueError("returned rows do not match the split sizes")
+        back = out_rows.new_empty((sum(send_splits), out_rows.shape[1]))
+        dist.all_to_all_single(back, out_rows.contiguous(), send_splits, recv_splits, group=self.group)
+        return back
+
+    def all_gather_rows(self, local_rows: torch.Tensor) -> torch.Tensor:
+        """local_rows [Tc, D] (same Tc on every rank) -> [G * Tc, D] in rank order."""
+        out = local_rows.new_empty((self.size * local_rows.shape[0], local_rows.shape[1]))
+        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=self.group)
+        return out
+
+
+def token_slice(T: int, size: int, rank: int) -> tuple[int, int, int]:
+    """Contiguous token slice of `rank`: chunk = ceil(T / size); returns (begin, end, chunk) with end <= T."""
+    chunk = (T + size - 1) // size
+    return min(rank * chunk, T), min((rank + 1) * chunk, T), chunk

@@ -123,11 +123,23 @@ class BailingMoeSparseMoeBlock(nn.Module):
         self._pk = None
         # expert parallelism: this rank keeps experts [ep_rank * E / ep_size, (ep_rank + 1) * E / ep_size)
         self.ep_group, self.ep_rank, self.ep_size = None, 0, 1
+        self.ep_mode, self._a2a = "allreduce", None
 
-    def set_expert_parallel(self, group, rank: int, size: int) -> None:
+    # below this many tokens per rank the all-to-all exchange costs more than it saves (decode: B <= 3 rows)
+    A2A_MIN_TOKENS_PER_RANK = 4
+
+    def set_expert_parallel(self, group, rank: int, size: int, mode: str = "allreduce") -> None:
+        """mode "allreduce": tokens replicated, every rank runs its experts on all tokens and the fp32 partial sums are
+        all-reduced (decode-sized inputs).  mode "alltoall": prefill-sized inputs additionally shard the TOKENS of the
+        MoE block over the ranks with an all-to-all dispatch / combine (ming_univision_b200/ep.py); small inputs still
+        take the all-reduce path."""
         if self.config.num_experts % size != 0:
             raise ValueError("num_experts must be divisible by the expert-parallel world size")
+        if mode not in ("allreduce", "alltoall"):
+            raise ValueError("mode must be 'allreduce' or 'alltoall'")
         self.ep_group, self.ep_rank, self.ep_size = (group if size > 1 else None), rank, size
+        self.ep_mode = mode
+        self._a2a = None
         self._pk = None
 
     def _pack(self):
@@ -162,6 +174,9 @@ class BailingMoeSparseMoeBlock(nn.Module):
         """x2d [T, D] (post-attention-norm) -> (residual + moe(x) [T, D], router logits [T, E], topk idx [T, k])."""
         pk = self._pack()
         cfg = self.config
+        if (self.ep_group is not None and self.ep_mode == "alltoall"
+                and x2d.shape[0] >= self.A2A_MIN_TOKENS_PER_RANK * self.ep_size):
+            return self._run_alltoall(pk, x2d, residual, image_mask), None, None
         logits = _dense(x2d, pk["gate"])
         logits_img, im = None, None
         if self.multi_gate and image_mask is not None:
@@ -177,6 +192,65 @@ class BailingMoeSparseMoeBlock(nn.Module):
                 shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
         y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual, pk["e_begin"], self.ep_group)
         return y, logits, idx
+
+    @torch.no_grad()
+    def _run_alltoall(self, pk, x2d: torch.Tensor, residual: Optional[torch.Tensor], image_mask: Optional[torch.Tensor]):
+        """Token- and expert-sharded MoE block: this rank routes tokens [t0, t1), sends every
+        (token, slot) row to the rank owning its expert (all-to-all), runs the grouped tcgen05 expert GEMMs on what it
+        receives, returns the rows (all-to-all), combines its tokens in fp32 in slot order (:632-638) with the shared
+        expert and the residual, and all-gathers the token slices.  Returns residual + moe(x) for ALL T tokens."""
+        from .ep import ExpertParallelAllToAll, token_slice
+
+        if self._a2a is None:
+            self._a2a = ExpertParallelAllToAll(self.ep_group)
+        a2a, cfg = self._a2a, self.config
+        G, r = self.ep_size, self.ep_rank
+        T, D = x2d.shape
+        k, E = cfg.num_experts_per_tok, cfg.num_experts
+        E_local = E // G
+        t0, t1, Tc = token_slice(T, G, r)
+        n_loc = t1 - t0
+        dev = x2d.device
+        y_loc = torch.zeros((Tc, D), dtype=BF16, device=dev)
+        if n_loc > 0:
+            x_loc = x2d[t0:t1].contiguous()
+            logits = _dense(x_loc, pk["gate"])
+            logits_img, im = None, None
+            if self.multi_gate and image_mask is not None:
+                logits_img = _dense(x_loc, pk["image_gate"])
+                im = image_mask.reshape(-1)[t0:t1].to(torch.uint8).contiguous()
+            idx, w = ops.router_topk(logits, k, k > 1 and cfg.norm_topk_prob, logits_img, im)
+            shared = None
+            if "s12" in pk:
+                if n_loc <= 8:
+                    shared = ops.gemv(ops.gemv(x_loc, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
+                else:
+                    shared = ops.linear(ops.linear(x_loc, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
+            # send buffer ordered by destination rank (bucket = expert // E_local), no padding
+            pair_row, row_token, _, _, n_send, counts = ops.moe_plan(idx, G, 0, div=E_local, granule=1,
+                                                                      want_counts=True)
+            send_rows = ops.gather_rows(x_loc, row_token, n_send)
+            send_ids = torch.empty((n_send,), dtype=torch.int32, device=dev)
+            send_ids[pair_row.long()] = idx.reshape(-1)  # pure indexing: expert id of every row in send order
+        else:
+            counts = torch.zeros((G,), dtype=torch.int32, device=dev)
+            send_rows = torch.empty((0, D), dtype=BF16, device=dev)
+            send_ids = torch.empty((0,), dtype=torch.int32, device=dev)
+        send_splits, recv_splits = a2a.exchange_counts(counts)
+        recv_rows, recv_ids = a2a.dispatch(send_rows, send_ids, send_splits, recv_splits)
+        n_recv = recv_rows.shape[0]
+        if n_recv > 0:
+            # every received row is one pair for one LOCAL expert: tile plan with k = 1
+            pr2, rt2, te2, meta2, mr2 = ops.moe_plan(recv_ids.view(n_recv, 1), E_local, pk["e_begin"])
+            xg = ops.gather_rows(recv_rows, rt2, mr2, meta2)
+            out_recv = ops.gather_rows(ops.moe_grouped_ffn(xg, pk["Wgu"], pk["Wd"], te2, meta2), pr2, n_recv)
+        else:
+            out_recv = recv_rows
+        back = a2a.combine(out_recv, send_splits, recv_splits)
+        if n_loc > 0:
+            res_loc = None if residual is None else residual[t0:t1].contiguous()
+            ops.moe_combine(back, w, shared, res_loc, y_loc[:n_loc], pair_row)
+        return a2a.all_gather_rows(y_loc)[:T]
 
     @torch.no_grad()
     def forward(self, hidden_states, image_mask=None, audio_mask=None):
@@ -276,16 +350,17 @@ class BailingMoeModel(nn.Module):
             self._pk = dict(dev=dev, layers=layers, norm=d(self.norm.weight), emb=d(self.word_embeddings.weight))
         return self._pk
 
-    def set_expert_parallel(self, group=None) -> None:
+    def set_expert_parallel(self, group=None, mode: str = "allreduce") -> None:
         """Shards the routed experts of every layer over the ranks of `group` (default: the world group); attention,
-        gates, shared experts and norms stay replicated.  One process per GPU; NCCL over NVLink."""
+        gates, shared experts and norms stay replicated.  One process per GPU; NCCL over NVLink.
+        mode "alltoall" also shards the tokens of prefill-sized MoE inputs (BailingMoeSparseMoeBlock.set_expert_parallel)."""
         import torch.distributed as dist
 
         size = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         for lyr in self.layers:
             lyr.mlp.set_expert_parallel(group if group is not None else (dist.group.WORLD if size > 1 else None),
-                                        rank, size)
+                                        rank, size, mode)
         self.ep_size = size
 
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:

@@ -5,6 +5,8 @@ sm_100a kernels from libmingb200.so.  No function has an eager-PyTorch fallback.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -451,11 +453,77 @@ def router_topk(logits: torch.Tensor, k: int, renorm: bool, logits_img: torch.Te
     return idx, w
 
 
+# token count above which the routed experts run as ONE grouped tcgen05 GEMM per projection instead of the
+# weight-streaming kernel (which re-reads an expert's 17 MB once per 8 rows); MB_MOE_GROUPED=0/1 forces either path
+MOE_GROUPED_MIN_PAIRS_PER_EXPERT = 16
+
+
+def _moe_use_grouped(T: int, k: int, E: int) -> bool:
+    force = os.environ.get("MB_MOE_GROUPED")
+    if force is not None:
+        return force == "1"
+    return T * k >= MOE_GROUPED_MIN_PAIRS_PER_EXPERT * E
+
+
+def moe_plan(idx: torch.Tensor, E: int, e_begin: int = 0, div: int = 1, granule: int = 128, want_counts: bool = False):
+    """Routing plan (mb_moe_plan): idx int32 [T, k] (global expert ids) bucketed by (idx - e_begin) // div into E
+    buckets, each padded to `granule` rows -> (pair_row [T*k], row_token [max_rows], tile_expert [max_rows/128] or
+    None, meta [2] = {128-row tiles, rows}, max_rows[, counts [E]])."""
+    lib = _lib.load()
+    T, k = idx.shape
+    dev = idx.device
+    max_rows = T * k + (granule - 1) * E
+    max_rows = ((max_rows + granule - 1) // granule) * granule
+    pair_row = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    row_token = torch.empty((max_rows,), dtype=torch.int32, device=dev)
+    tile_expert = torch.zeros((max_rows // 128,), dtype=torch.int32, device=dev) if granule == 128 else None
+    meta = torch.empty((2,), dtype=torch.int32, device=dev)
+    counts = torch.empty((E,), dtype=torch.int32, device=dev) if want_counts else None
+    _lib.check(lib.mb_moe_plan(idx.data_ptr(), pair_row.data_ptr(), row_token.data_ptr(), _ptr(tile_expert),
+                               meta.data_ptr(), _ptr(counts), T, k, E, int(e_begin), int(div), int(granule), max_rows,
+                               _stream()), "mb_moe_plan")
+    if want_counts:
+        return pair_row, row_token, tile_expert, meta, max_rows, counts
+    return pair_row, row_token, tile_expert, meta, max_rows
+
+
+def gather_rows(x: torch.Tensor, row_index: torch.Tensor, n_rows: int, meta: torch.Tensor | None = None) -> torch.Tensor:
+    """out[r] = x[row_index[r]] (zero row where the index is negative) for r < n_rows (or < meta[1], read on the device)."""
+    _check_bf16(x)
+    lib = _lib.load()
+    D = x.shape[-1]
+    out = torch.empty((n_rows, D), dtype=BF16, device=x.device)
+    _lib.check(lib.mb_moe_gather_rows(x.data_ptr(), row_index.data_ptr(), _ptr(meta), out.data_ptr(), n_rows, D,
+                                      _stream()), "mb_moe_gather_rows")
+    return out
+
+
+def moe_grouped_ffn(xg: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor, tile_expert: torch.Tensor,
+                    meta: torch.Tensor) -> torch.Tensor:
+    """Expert FFN over expert-sorted, 128-row-padded rows xg [max_rows, D]: grouped gate/up GEMM with the SwiGLU
+    epilogue, then the grouped down GEMM (both tcgen05 / TMA, one launch each) -> [max_rows, D]."""
+    _check_bf16(xg, Wgu, Wd)
+    lib = _lib.load()
+    max_rows, D = xg.shape
+    E, I2, _ = Wgu.shape
+    I = I2 // 2
+    s = _stream()
+    hid = torch.empty((max_rows, I), dtype=BF16, device=xg.device)
+    out = torch.empty((max_rows, D), dtype=BF16, device=xg.device)
+    _lib.check(lib.mb_moe_grouped_gemm(xg.data_ptr(), Wgu.data_ptr(), hid.data_ptr(), tile_expert.data_ptr(),
+                                       meta.data_ptr(), max_rows, I2, D, E, 1, s), "mb_moe_grouped_gemm")
+    _lib.check(lib.mb_moe_grouped_gemm(hid.data_ptr(), Wd.data_ptr(), out.data_ptr(), tile_expert.data_ptr(),
+                                       meta.data_ptr(), max_rows, D, I, E, 0, s), "mb_moe_grouped_gemm")
+    return out
+
+
 def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor,
                 shared: torch.Tensor | None, residual: torch.Tensor | None, e_begin: int = 0,
                 ep_group=None) -> torch.Tensor:
     """moe_infer + shared-expert add + residual: x [T, D]; Wgu [E_local, 2I, D]; Wd [E_local, D, I]; idx int32 [T, k]
-    (GLOBAL expert ids); w fp32.  With `ep_group` the slabs hold only experts [e_begin, e_begin + E_local): each rank
+    (GLOBAL expert ids); w fp32.  Small token counts stream each hit expert's weights once per 8 rows
+    (mb_moe_gate_up / mb_moe_down); prefill-sized inputs run as grouped tcgen05 GEMMs (mb_moe_plan /
+    mb_moe_grouped_gemm).  With `ep_group` the slabs hold only experts [e_begin, e_begin + E_local): each rank
     computes the fp32 weighted sum of its experts, the partials are all-reduced over NCCL (torch.distributed is the
     plumbing; the tokens of this path are replicated on every rank, so there is no dispatch exchange), and the
     reference's rounding chain is applied after the reduction."""
@@ -466,31 +534,53 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
     I = I2 // 2
     k = idx.shape[1]
     dev = x.device
-    offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
-    sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
-    hid = torch.empty((T * k, I), dtype=BF16, device=dev)
     ep = ep_group is not None
-    out_pairs = (torch.zeros if ep else torch.empty)((T * k, D), dtype=BF16, device=dev)
     y = torch.empty((T, D), dtype=BF16, device=dev)
     s = _stream()
-    _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
-               "mb_moe_sort")
-    _lib.check(lib.mb_moe_gate_up(x.contiguous().data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                                  hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
-    _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                               out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+    x = x.contiguous()
+    if _moe_use_grouped(T, k, E):
+        pair_row, row_token, tile_expert, meta, max_rows = moe_plan(idx, E, e_begin)
+        xg = gather_rows(x, row_token, max_rows, meta)
+        out_pairs = moe_grouped_ffn(xg, Wgu, Wd, tile_expert, meta)
+        pr = pair_row.data_ptr()
+    else:
+        offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+        sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
+        hid = torch.empty((T * k, I), dtype=BF16, device=dev)
+        out_pairs = (torch.zeros if ep else torch.empty)((T * k, D), dtype=BF16, device=dev)
+        _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
+                   "mb_moe_sort")
+        _lib.check(lib.mb_moe_gate_up(x.data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                                      hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
+        _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                                   out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+        pr = None
     if not ep:
         _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(),
-                                      None, T, k, D, s), "mb_moe_combine")
+                                      None, pr, T, k, D, s), "mb_moe_combine")
         return y
     import torch.distributed as dist
 
     part = torch.empty((T, D), dtype=torch.float32, device=dev)
-    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), part.data_ptr(), T, k,
-                                  D, s), "mb_moe_combine")
+    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), None, None, y.data_ptr(), part.data_ptr(), pr, T,
+                                  k, D, s), "mb_moe_combine")
     dist.all_reduce(part, op=dist.ReduceOp.SUM, group=ep_group)
     _lib.check(lib.mb_moe_finalize(part.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, D, s),
                "mb_moe_finalize")
+    return y
+
+
+def moe_combine(out_pairs: torch.Tensor, w: torch.Tensor, shared: torch.Tensor | None, residual: torch.Tensor | None,
+                y: torch.Tensor, pair_row: torch.Tensor | None = None) -> torch.Tensor:
+    """y[t] = bf16(bf16(bf16(sum_j w[t, j] * out_pairs[row(t, j)]) + shared[t]) + residual[t]) written into `y` [T, D];
+    row(t, j) = pair_row[t*k + j] (or t*k + j without a plan)."""
+    _check_bf16(out_pairs, shared, residual, y)
+    if not y.is_contiguous():
+        raise ValueError("moe_combine writes a contiguous [T, D] view")
+    lib = _lib.load()
+    T, k = w.shape
+    _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), None,
+                                  _ptr(pair_row), T, k, y.shape[1], _stream()), "mb_moe_combine")
     return y
 
 

@@ -1,6 +1,8 @@
 """Expert parallelism over 2 GPUs (one process per GPU, NCCL): the MoE block with its routed experts sharded over the
 ranks must reproduce the single-GPU block (same router decisions; fp32 partial sums reduced in a different order, so
-equality is to bf16 rounding), and every rank must end with the same output.  Needs >= 2 GPUs (`gpurun --gpus 2`)."""
+equality is to bf16 rounding), and every rank must end with the same output — both for the replicated-token all-reduce
+mode (decode) and for the token-sharded all-to-all dispatch / combine mode (prefill).  Needs >= 2 GPUs
+(`gpurun --gpus 2`)."""
 import os
 import socket
 import subprocess
@@ -48,6 +50,24 @@ WORKER = textwrap.dedent("""
         dist.all_gather(gathered, y2)
         assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree"
         print("rank", rank, "T", T, "rel err vs single GPU", err, flush=True)
+    # token- AND expert-sharded block: all-to-all dispatch / combine + all-gather (prefill-sized inputs; T = 7 stays
+    # on the all-reduce path, T = 41 gives uneven token slices 21 + 20)
+    a2a = build()
+    a2a.set_expert_parallel(dist.group.WORLD, rank, world, mode="alltoall")
+    os.environ["MB_MOE_GROUPED"] = "1"
+    for T in (7, 41, 300):
+        x = torch.randn((1, T, cfg["hidden_size"]), generator=g).to(dev).to(torch.bfloat16)
+        res = torch.randn((T, cfg["hidden_size"]), generator=g).to(dev).to(torch.bfloat16)
+        im = (torch.arange(T) %% 3 == 0).to(dev)
+        y1, _, _ = single._run(x.view(T, -1), res, im)
+        y2, _, _ = a2a._run(x.view(T, -1), res, im)
+        assert y2.shape == y1.shape
+        err = ((y1.float() - y2.float()).norm() / y1.float().norm()).item()
+        assert err < 5e-3, err
+        gathered = [torch.empty_like(y2) for _ in range(world)]
+        dist.all_gather(gathered, y2.contiguous())
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree"
+        print("rank", rank, "T", T, "all-to-all rel err vs single GPU", err, flush=True)
     dist.destroy_process_group()
     print("rank", rank, "ok")
 """) % ROOT

@@ -100,10 +100,13 @@ def test_router_topk(cuda_device):
     assert (idx >= 0).all() and (idx < E).all()
 
 
-@pytest.mark.parametrize("T", [1, 3, 40])
-def test_moe_block_operator(cuda_device, T):
-    """BailingMoeSparseMoeBlock.forward (the MoE operator boundary) against the oracle's per-token expert loop."""
+@pytest.mark.parametrize("T,grouped", [(1, "0"), (3, "0"), (40, "0"), (40, "1"), (333, "1"), (5, "1")])
+def test_moe_block_operator(cuda_device, T, grouped, monkeypatch):
+    """BailingMoeSparseMoeBlock.forward (the MoE operator boundary) against the oracle's per-token expert loop, on the
+    weight-streaming kernels (grouped = 0) and on the grouped tcgen05 GEMMs of the prefill regime (grouped = 1)."""
     from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig, BailingMoeSparseMoeBlock
+
+    monkeypatch.setenv("MB_MOE_GROUPED", grouped)
 
     cfg = dict(synthetic.LLM_TINY_CONFIG, num_experts=16, num_experts_per_tok=6, moe_intermediate_size=96,
                num_shared_experts=2)
@@ -124,6 +127,56 @@ def test_moe_block_operator(cuda_device, T):
     same = (idx.cpu().view(-1, 6) == ridx).all(dim=1)
     assert same.float().mean() >= 0.9, f"only {int(same.sum())}/{T} tokens routed like the reference"
     assert rel_l2(y.view(-1, y.shape[-1]).cpu()[same], ref.view(-1, ref.shape[-1])[same]) < 1e-2
+
+
+def _moe_ref(x, idx, w, Wgu, Wd):
+    """fp32 torch statement of moe_infer (:608-639) with the reference's bf16 rounding points."""
+    T, D = x.shape
+    I = Wgu.shape[1] // 2
+    out = torch.zeros((T, D), dtype=torch.float32, device=x.device)
+    xf = x.float()
+    for e in range(Wgu.shape[0]):
+        tok, slot = (idx == e).nonzero(as_tuple=True)
+        if tok.numel() == 0:
+            continue
+        h = xf[tok] @ Wgu[e].float().t()
+        g, u = h[:, :I].to(BF16).float(), h[:, I:].to(BF16).float()
+        hid = (F.silu(g).to(BF16).float() * u).to(BF16).float()
+        o = (hid @ Wd[e].float().t()).to(BF16).float()
+        out.index_add_(0, tok, o * w[tok, slot].unsqueeze(1))
+    return out.to(BF16)
+
+
+@pytest.mark.parametrize("T,D,I,E,k", [(300, 2048, 1408, 64, 6), (1536, 2048, 1408, 64, 6), (77, 256, 200, 8, 2),
+                                       (129, 128, 64, 3, 1)])
+def test_moe_grouped_gemm(cuda_device, T, D, I, E, k, monkeypatch):
+    """Grouped tcgen05 expert GEMMs (mb_moe_plan / mb_moe_gather_rows / mb_moe_grouped_gemm) against an fp32 torch
+    statement of moe_infer and against the weight-streaming kernels on the same routing."""
+    from ming_univision_b200 import ops
+
+    x = _rand((T, D), cuda_device, 1.0, 11)
+    Wgu = _rand((E, 2 * I, D), cuda_device, D ** -0.5, 12)
+    Wd = _rand((E, D, I), cuda_device, I ** -0.5, 13)
+    g = torch.Generator(device="cpu").manual_seed(14)
+    idx = torch.stack([torch.randperm(E, generator=g)[:k] for _ in range(T)]).to(torch.int32).to(cuda_device)
+    if E >= 8:
+        idx[idx == 5] = 4  # leave one expert without tokens (and expert 4 oversubscribed, duplicates allowed)
+    w = torch.rand((T, k), generator=g).to(cuda_device)
+    monkeypatch.setenv("MB_MOE_GROUPED", "1")
+    y_g = ops.moe_experts(x, idx, w, Wgu, Wd, None, None)
+    monkeypatch.setenv("MB_MOE_GROUPED", "0")
+    y_s = ops.moe_experts(x, idx, w, Wgu, Wd, None, None)
+    ref = _moe_ref(x, idx.long(), w, Wgu, Wd)
+    assert torch.isfinite(y_g.float()).all()
+    assert rel_l2(y_g.cpu(), ref.cpu()) < 6e-3
+    assert rel_l2(y_g.cpu(), y_s.cpu()) < 6e-3
+    # the plan itself: every pair has a distinct row inside its expert's padded segment
+    pair_row, row_token, tile_expert, meta, max_rows = ops.moe_plan(idx, E)
+    pr, rt, te, mt = pair_row.cpu(), row_token.cpu(), tile_expert.cpu(), meta.cpu()
+    assert len(set(pr.tolist())) == T * k and int(pr.min()) >= 0 and int(pr.max()) < int(mt[1]) <= max_rows
+    assert torch.equal(rt[pr.long()], torch.arange(T * k, dtype=torch.int32) // k)
+    assert torch.equal(te[(pr // 128).long()], idx.cpu().reshape(-1))
+    assert int((rt >= 0).sum()) == T * k and int(mt[0]) * 128 == int(mt[1])
 
 
 @pytest.fixture(scope="module")

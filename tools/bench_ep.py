@@ -60,7 +60,28 @@ if world > 1:
     y_ep, _, _ = blk._run(x, res, None)
     out["rel_err_vs_unsharded"] = float(((y_ep.float() - y_single.float()).norm() / y_single.float().norm()).item())
     out["ms_layer_ep"] = round(timeit(lambda: blk._run(x, res, None)), 4)
+# ---- prefill-sized input (BASELINE configs[2] shape: 1552 tokens): unsharded grouped tcgen05 GEMMs vs expert-parallel
+# all-reduce (tokens replicated) vs token-sharded all-to-all dispatch / combine + all-gather
+T = int(os.environ.get("EP_PREFILL_TOKENS", "1552"))
+xp = torch.randn((T, 2048), device=dev).to(torch.bfloat16)
+rp = torch.randn((T, 2048), device=dev).to(torch.bfloat16)
+if world > 1:
+    dist.broadcast(xp, 0)
+    dist.broadcast(rp, 0)
+    blk.set_expert_parallel(None, 0, 1)
+yp_single, _, _ = blk._run(xp, rp, None)
+out["prefill_tokens"] = T
+out["ms_prefill_layer_unsharded"] = round(timeit(lambda: blk._run(xp, rp, None), iters=20), 4)
+if world > 1:
+    for mode in ("allreduce", "alltoall"):
+        blk.set_expert_parallel(dist.group.WORLD, rank, world, mode=mode)
+        yp, _, _ = blk._run(xp, rp, None)
+        out[f"prefill_rel_err_{mode}"] = float(((yp.float() - yp_single.float()).norm() / yp_single.float().norm()).item())
+        out[f"ms_prefill_layer_ep_{mode}"] = round(timeit(lambda: blk._run(xp, rp, None), iters=20), 4)
 if rank == 0:
     print(json.dumps(out), flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/bench_ep_{world}.json", "w") as f:
+        json.dump(out, f, indent=1)
 if world > 1:
     dist.destroy_process_group()
