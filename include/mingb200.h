@@ -145,6 +145,12 @@ int mb_attn_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const v
                 int64_t o_ts, int64_t o_hs, int B, int Sq, int Sk, int Hq, int Hkv, int hd, float scale, int causal,
                 void* stream);
 
+/* Attention backend of mb_attn_hd64 / mb_attn_fwd: 0 = auto (tcgen05 / TMEM kernel whenever eligible), 1 = same,
+ * 2 = force the warp-level mma.sync kernel (A/B measurements and tests).  Env MB_ATTN_BACKEND sets the default. */
+int mb_attn_set_backend(int backend);
+/* Development aid: device buffer (>= 64 x 16 int64) receiving clock64() phase stamps of CTA 0 of the tcgen05 attention
+ * kernel; NULL switches it off. */
+int mb_attn_set_debug(void* dev_buf);
 /* Decode-step attention against a static KV cache (semantic decoder, q_len = 1; layers/attention.py:213-239 with
  * past_key_value).  qkv[B, 3, H, 64] holds the new token; its K/V are appended at position `t` of
  * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t.

@@ -25,6 +25,8 @@ SIGNATURES = {
                         _f, _vp, _vp],
     "mb_row_stats": [_vp, _i64, _vp, _i, _i, _vp],
     "mb_gemm_force_tile": [_i, _i],
+    "mb_attn_set_backend": [_i],
+    "mb_attn_set_debug": [_vp],
     "mb_gemv_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
     "mb_adaln_modulate": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],

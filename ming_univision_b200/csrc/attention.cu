@@ -368,6 +368,12 @@ attn_hd64_decode_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   *reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * H + h) * 64 + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
 }
 
+// attention_tc.cu: tcgen05 / TMEM kernel.  Returns 1 if it launched, 0 if the problem is not eligible, < 0 on error.
+int launch_attn_tc(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_hs, const void* k, int64_t k_bs, int64_t k_ts,
+                   int64_t k_hs, const void* v, int64_t v_bs, int64_t v_ts, int64_t v_hs, void* out, int64_t o_bs,
+                   int64_t o_ts, int64_t o_hs, int B, int Sq, int Sk, int Hq, int Hkv, int hd, float scale, int causal,
+                   cudaStream_t stream);
+
 }  // namespace mb
 
 using namespace mb;
@@ -391,6 +397,11 @@ extern "C" int mb_attn_hd64(const void* qkv, void* out, int B, int S, int H, flo
   p.Sq = S; p.Sk = S; p.Hq = H; p.Hkv = H;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  {
+    const int rc = launch_attn_tc(p.q, p.q_bs, p.q_ts, p.q_hs, p.k, p.k_bs, p.k_ts, p.k_hs, p.v, p.v_bs, p.v_ts, p.v_hs,
+                                  p.o, p.o_bs, p.o_ts, p.o_hs, B, S, S, H, H, 64, scale, causal, stream);
+    if (rc != 0) return rc < 0 ? rc : MB_OK;
+  }
   return launch_attn<64>(p, B, stream);
 }
 
@@ -433,5 +444,10 @@ extern "C" int mb_attn_fwd(const void* q, int64_t q_bs, int64_t q_ts, int64_t q_
   p.Sq = Sq; p.Sk = Sk; p.Hq = Hq; p.Hkv = Hkv;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
+  if (Sk >= 1) {
+    const int rc = launch_attn_tc(q, q_bs, q_ts, q_hs, k, k_bs, k_ts, k_hs, v, v_bs, v_ts, v_hs, out, o_bs, o_ts, o_hs, B,
+                                  Sq, Sk, Hq, Hkv, hd, scale, causal, stream);
+    if (rc != 0) return rc < 0 ? rc : MB_OK;
+  }
   return hd == 64 ? launch_attn<64>(p, B, stream) : launch_attn<128>(p, B, stream);
 }

@@ -57,6 +57,30 @@ bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint6
   return true;
 }
 
+bool make_tmap_4d_bf16(CUtensorMap* map, const void* base, const uint64_t dims_[4], const uint64_t strides_elems[3],
+                       const uint32_t box_[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return false;
+  }
+  cuuint64_t dims[4] = {dims_[0], dims_[1], dims_[2], dims_[3]};
+  cuuint64_t strides[3] = {strides_elems[0] * 2, strides_elems[1] * 2, strides_elems[2] * 2};
+  cuuint32_t box[4] = {box_[0], box_[1], box_[2], box_[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): base=%p dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu)",
+              (int)r, base, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+              (unsigned long long)strides[2]);
+    return false;
+  }
+  return true;
+}
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {

@@ -34,6 +34,11 @@ void set_error(const char* fmt, ...);
 bool make_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
                        uint32_t box_inner, uint32_t box_outer);
 
+// 4-D bf16 view {d0 (contiguous), d1, d2, d3} with element strides {1, s1, s2, s3} and box {b0, b1, b2, b3}; 128-byte
+// swizzle (b0 * 2 bytes <= 128), zero fill out of bounds.  Used for [batch][token][head][head_dim] attention operands.
+bool make_tmap_4d_bf16(CUtensorMap* map, const void* base, const uint64_t dims[4], const uint64_t strides_elems[3],
+                       const uint32_t box[4]);
+
 int num_sms();
 
 // Launch with the programmatic-stream-serialization attribute (PDL).  Only for kernels that call pdl_wait() before

@@ -96,6 +96,14 @@ __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, voi
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0,
+                                            int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(desc)),
@@ -182,6 +190,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                // SWIZZLE_128B
   return d;
 }
+// Same for an MN-major operand tile [K rows][64 MN elements] (e.g. V[keys][head_dim] as the B operand of P.V): the 64
+// MN elements of one K row are contiguous (128 B, TMA 128-byte swizzle), 8-row K groups are 1024 B apart (SBO), and
+// further 64-element MN groups are `lbo_bytes` apart (LBO).  Used with umma_idesc_bf16(...) | kUmmaBMajorMN.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+constexpr uint32_t kUmmaBMajorMN = 1u << 16;  // instruction-descriptor bit: B operand is MN-major ("transposed")
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N (K = 16 per instruction).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
   return (1u << 4)            // D format fp32

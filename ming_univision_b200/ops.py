@@ -201,6 +201,13 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | 
     return y.view(x.shape)
 
 
+def set_attn_backend(backend: int) -> None:
+    """0 auto / 1 tcgen05 kernel whenever eligible, 2 force the mma.sync kernel (tests, A/B measurements)."""
+    rc = _lib.load().mb_attn_set_backend(int(backend))
+    if rc != 0:
+        raise RuntimeError("mb_attn_set_backend failed")
+
+
 def attention_hd64(qkv: torch.Tensor, B: int, S: int, H: int, causal: bool) -> torch.Tensor:
     """qkv: [B, S, 3*H*64] packed as (3, H, 64) -> [B, S, H*64]."""
     _check_bf16(qkv)

@@ -167,11 +167,17 @@ def test_layernorm(cuda_device, rows, dim, act):
 @pytest.mark.parametrize("B,S,H", [(1, 65, 12), (2, 257, 16), (3, 64, 16), (2, 256, 16), (1, 1025, 12), (2, 1, 4),
                                    (1, 130, 2)])
 @pytest.mark.parametrize("causal", [False, True])
-def test_attention_hd64(cuda_device, B, S, H, causal):
+@pytest.mark.parametrize("backend", [1, 2])
+def test_attention_hd64(cuda_device, B, S, H, causal, backend):
+    """backend 1: tcgen05 / TMEM kernel (attention_tc.cu), 2: warp-level mma.sync kernel (attention.cu)."""
     from ming_univision_b200 import ops
 
     qkv = _rand((B, S, 3 * H * 64), cuda_device, 1.0, 30)
-    out = ops.attention_hd64(qkv, B, S, H, causal)
+    ops.set_attn_backend(backend)
+    try:
+        out = ops.attention_hd64(qkv, B, S, H, causal)
+    finally:
+        ops.set_attn_backend(0)
     q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
     att = (q @ k.transpose(-1, -2)) * 64 ** -0.5
     if causal:
@@ -180,6 +186,32 @@ def test_attention_hd64(cuda_device, B, S, H, causal):
     err = (out.float() - ref).abs()
     # P is rounded to bf16 before the PV product (as flash-attn does): 2^-8 relative on O(1) values
     assert err.max().item() < 2e-2, f"max err {err.max().item()}"
+    assert _rel_err(out, ref) < 8e-3
+
+
+@pytest.mark.parametrize("B,S,H,Hkv,hd", [(1, 300, 16, 4, 128), (2, 129, 8, 8, 128), (1, 1552, 16, 4, 128),
+                                          (2, 77, 4, 2, 64), (1, 40, 4, 1, 128)])
+@pytest.mark.parametrize("backend", [1, 2])
+def test_attention_prefill_gqa(cuda_device, B, S, H, Hkv, hd, backend):
+    """Causal GQA prefill attention reading K / V in place from the [B, Hkv, Tmax, hd] cache (mb_attn_fwd)."""
+    from ming_univision_b200 import ops
+
+    Tmax = S + 19
+    q = _rand((B * S, H * hd), cuda_device, 1.0, 40)
+    kc = _rand((B, Hkv, Tmax, hd), cuda_device, 1.0, 41)
+    vc = _rand((B, Hkv, Tmax, hd), cuda_device, 1.0, 42)
+    ops.set_attn_backend(backend)
+    try:
+        out = ops.attn_prefill_gqa(q, kc, vc, B, S, H)
+    finally:
+        ops.set_attn_backend(0)
+    qf = q.float().view(B, S, H, hd).permute(0, 2, 1, 3)
+    kf = kc[:, :, :S].float().repeat_interleave(H // Hkv, dim=1)
+    vf = vc[:, :, :S].float().repeat_interleave(H // Hkv, dim=1)
+    att = (qf @ kf.transpose(-1, -2)) * hd ** -0.5
+    att = att.masked_fill(torch.triu(torch.ones(S, S, device=cuda_device, dtype=torch.bool), 1), float("-inf"))
+    ref = (att.softmax(-1) @ vf).permute(0, 2, 1, 3).reshape(B * S, H * hd)
+    assert (out.float() - ref).abs().max().item() < 2e-2
     assert _rel_err(out, ref) < 8e-3
 
 
