@@ -61,12 +61,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: two lanes of fp32 math per issue slot).
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// Bounded wait with a back-off sleep between polls: for roles whose wake-up latency is not critical (a spinning warp
+// competes for issue slots with the warps doing the work).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns);
 // Bounded wait: a protocol bug must surface as a trapped kernel (CUDA error), never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
       printf("mbar_wait timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) {
+      printf("mbar_wait_sleep timeout block %d thread %d bar %p parity %u\n", (int)blockIdx.x, (int)threadIdx.x, bar,
              parity);
       __trap();
     }

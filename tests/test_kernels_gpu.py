@@ -189,6 +189,37 @@ def test_attention_hd64(cuda_device, B, S, H, causal, backend):
     assert _rel_err(out, ref) < 8e-3
 
 
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_hd64_growing_scores(cuda_device, causal):
+    """Scores that keep growing along the key axis: every later key block exceeds the running maximum by far more than
+    the tcgen05 kernel's lazy-rescaling bound, so its redo path (true block maximum + rescale of O) is exercised."""
+    from ming_univision_b200 import ops
+
+    B, S, H = 2, 500, 3
+    qkv = _rand((B, S, 3, H, 64), cuda_device, 1.0, 33).float()
+    ramp = torch.linspace(0.2, 9.0, S, device=cuda_device).view(1, S, 1, 1)
+    qkv[:, :, 1] = qkv[:, :, 1].abs() * ramp          # keys: positive, growing norm
+    qkv[:, :, 0] = qkv[:, :, 0].abs() * 2.0           # queries: positive -> scores grow with the key index
+    qkv = qkv.to(BF16).view(B, S, 3 * H * 64)
+    outs = {}
+    for backend in (1, 2):
+        ops.set_attn_backend(backend)
+        try:
+            outs[backend] = ops.attention_hd64(qkv, B, S, H, causal)
+        finally:
+            ops.set_attn_backend(0)
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-1, -2)) * 64 ** -0.5
+    assert (att[..., -1] - att[..., 0]).min().item() > 50  # beyond the bound of 8 / (scale log2 e) = 44
+    if causal:
+        att = att.masked_fill(torch.triu(torch.ones(S, S, device=cuda_device, dtype=torch.bool), 1), float("-inf"))
+    ref = (att.softmax(-1) @ v).transpose(1, 2).reshape(B, S, H * 64)
+    for backend in (1, 2):
+        assert torch.isfinite(outs[backend].float()).all()
+        assert (outs[backend].float() - ref).abs().max().item() < 3e-2, backend
+        assert _rel_err(outs[backend], ref) < 8e-3, backend
+
+
 @pytest.mark.parametrize("B,S,H,Hkv,hd", [(1, 300, 16, 4, 128), (2, 129, 8, 8, 128), (1, 1552, 16, 4, 128),
                                           (2, 77, 4, 2, 64), (1, 40, 4, 1, 128)])
 @pytest.mark.parametrize("backend", [1, 2])
