@@ -217,13 +217,17 @@ int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, void* q_out,
                       void* stream);
 /* GQA attention for q_len == 1 (head_dim 128) over cache slots 0 .. T-1, skipping keys whose key_mask[b, j] == 0
  * (the 2-D padding mask of the CFG rows; _upad_input / flash_attn_varlen_func :1009-1045, eager :795-812).
- * key_mask may be NULL; mask_stride = elements between rows of key_mask. */
+ * key_mask may be NULL; mask_stride = elements between rows of key_mask.  n_splits > 1 spreads the keys of every head
+ * over n_splits CTAs (flash-decoding: per-chunk partial max / sum / output in `workspace`, B * H * n_splits * 130
+ * floats, merged by a second kernel) so that long contexts use the whole GPU; n_splits = 1 needs no workspace. */
 int mb_attn_decode_gqa(const void* q, const void* kcache, const void* vcache, const int32_t* key_mask,
                        int64_t mask_stride, void* out, int B, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev,
-                       int t_host, float scale, void* stream);
+                       int t_host, float scale, float* workspace, int n_splits, void* stream);
 /* Greedy next-token choice over fp32 logits [rows, V] (HF generate with do_sample = false, mingunivision/config.json:30;
- * first index on ties, as torch.argmax). */
-int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, void* stream);
+ * first index on ties, as torch.argmax).  n_chunks > 1: two stages (per-chunk winners in ws_val / ws_idx
+ * [rows * n_chunks], then the row winner) so that a 126 k-entry vocabulary is scanned by many SMs. */
+int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, float* ws_val, int32_t* ws_idx, int n_chunks,
+                  void* stream);
 /* BailingMoeGate.forward (:505-520) after the logits GEMM: fp32 softmax over E bf16 logits, top-k, renormalise.
  * With logits_img + image_mask (uint8 [T]) tokens flagged as image tokens use the image gate's logits (:574-580). */
 int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* image_mask, int32_t* idx,

@@ -180,15 +180,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         tc_fence_after();
         const int nk16 = (min(BN, cu.kv_end - cu.j * BN) + 15) & ~15;
         const uint32_t idesc = umma_idesc_bf16(128, nk16);
+        // descriptors as (low word, shared high word): K steps / boxes are 32-bit adds on the low word (see ptx.cuh)
         const uint64_t da0 = umma_desc_sw128_kmajor(smem_u32(q_s + qs * Cfg::kQBytes));
         const uint64_t db0 = umma_desc_sw128_kmajor(smem_u32(ring_s + slot * Cfg::kKVBytes));
+        const uint32_t hi = static_cast<uint32_t>(da0 >> 32);
+        const uint32_t a_lo = static_cast<uint32_t>(da0), b_lo = static_cast<uint32_t>(db0);
         const uint32_t d_s = tmem_base + (g & 1) * BN;
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks) {
           // 64-column boxes: Q boxes are 16 KB apart, K boxes BN * 128 B apart; 32 B per K step inside a box
-          const uint64_t offa = static_cast<uint64_t>((ks >> 2) * (16384 >> 4) + 2 * (ks & 3));
-          const uint64_t offb = static_cast<uint64_t>((ks >> 2) * ((BN * 128) >> 4) + 2 * (ks & 3));
-          umma_bf16(d_s, da0 + offa, db0 + offb, idesc, ks != 0);
+          const uint32_t offa = (ks >> 2) * (16384 >> 4) + 2 * (ks & 3);
+          const uint32_t offb = (ks >> 2) * ((BN * 128) >> 4) + 2 * (ks & 3);
+          umma_bf16_lo(d_s, a_lo + offa, b_lo + offb, hi, idesc, ks != 0);
         }
         umma_commit(&kv_empty[slot]);
         if (cu.j == cu.nblk - 1) umma_commit(&q_empty[qs]);
@@ -205,6 +208,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | kUmmaBMajorMN;
         const uint64_t da0 = umma_desc_sw128_kmajor(smem_u32(p_s));
         const uint64_t db0 = umma_desc_sw128_mnmajor(smem_u32(ring_s + slot * Cfg::kKVBytes), BN * 128);
+        const uint32_t hi = static_cast<uint32_t>(da0 >> 32);  // identical for both layouts (SBO, version, swizzle)
+        const uint32_t a_lo = static_cast<uint32_t>(da0), b_lo = static_cast<uint32_t>(db0);
 #pragma unroll
         for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
 #pragma unroll
@@ -212,9 +217,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
             if (ks < nks) {
               // A: 64-key boxes of P are 16 KB apart, 32 B per K step inside a box; B: 16 keys = two 8-row groups of
               // the [keys][64] tile = 2048 B per K step, 64-column boxes BN * 128 B apart
-              const uint64_t offa = static_cast<uint64_t>((ks >> 2) * (16384 >> 4) + 2 * (ks & 3));
-              const uint64_t offb = static_cast<uint64_t>(bx * ((BN * 128) >> 4) + ks * (2048 >> 4));
-              umma_bf16(tmem_o + bx * 64, da0 + offa, db0 + offb, idesc, ks != 0);
+              const uint32_t offa = (ks >> 2) * (16384 >> 4) + 2 * (ks & 3);
+              const uint32_t offb = bx * ((BN * 128) >> 4) + ks * (2048 >> 4);
+              umma_bf16_lo(tmem_o + bx * 64, a_lo + offa, b_lo + offb, hi, idesc, ks != 0);
             }
           }
         }

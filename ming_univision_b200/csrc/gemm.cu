@@ -307,6 +307,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t acc_phase = 0;
       if (grouped) pdl_wait();
       const int num_tiles = tile_count();
+      // stage 0 descriptors, split into (low word, shared high word): stages and K steps are 32-bit adds on the low word
+      const uint64_t da_base = umma_desc_sw128_kmajor(smem_u32(smem_a));
+      const uint64_t db_base = umma_desc_sw128_kmajor(smem_u32(smem_b));
+      const uint32_t desc_hi = static_cast<uint32_t>(da_base >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(da_base), b_lo0 = static_cast<uint32_t>(db_base);
       for (int tile = worker; tile < num_tiles; tile += num_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -314,13 +319,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t da = umma_desc_sw128_kmajor(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = umma_desc_sw128_kmajor(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint32_t a_lo = a_lo0 + stage * (Cfg::kABytes >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (CG == 2) umma_bf16_cg2(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CG == 2) umma_bf16_cg2_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : static_cast<uint32_t>(kb));
+            else umma_bf16_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, (k != 0) ? 1u : static_cast<uint32_t>(kb));
           }
           // frees this smem slot (in both CTAs of a pair) once the MMAs above have read it
           if constexpr (CG == 2) umma_commit_cg2_mc(&empty_bar[stage], 0x3); else umma_commit(&empty_bar[stage]);

@@ -120,24 +120,29 @@ rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
 // GQA decode attention (q_len = 1), head_dim 128: one warp per (batch row, q head); lane owns 4 dims.
 // Keys 0..T-1 of the static cache, skipping keys whose mask entry is 0 (the reference's unpad/varlen path).
 // ------------------------------------------------------------------------------------------------------------
+// Long contexts split the keys over gridDim.y CTAs per head (chunks of `chunk` keys, flash-decoding style): each CTA
+// then writes its un-normalised partial (max, sum, output[128]) to `partial`, and attn_decode_merge_kernel combines them.
 __global__ void __launch_bounds__(128)
 attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kcache,
                           const __nv_bfloat16* __restrict__ vcache, const int32_t* __restrict__ key_mask,
                           int64_t mask_stride, __nv_bfloat16* __restrict__ out, int B, int H, int Hkv, int Tmax,
-                          const int32_t* __restrict__ t_dev, int t_host, float scale) {
+                          const int32_t* __restrict__ t_dev, int t_host, float scale, float* __restrict__ partial,
+                          int chunk) {
   // one CTA (4 warps) per (batch row, q head): the warps take interleaved groups of 4 keys, then merge their partial
   // (max, sum, output) triples through shared memory — 4x shorter dependent chain than one warp per head
   __shared__ float s_m[4], s_l[4], s_o[4][128];
   const int bh = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = bh / H, h = bh % H, hk = h / (H / Hkv);
-  const int T = (t_dev ? *t_dev : 0) + t_host;
+  const int T_all = (t_dev ? *t_dev : 0) + t_host;
+  const int j_begin = partial ? static_cast<int>(blockIdx.y) * chunk : 0;
+  const int T = partial ? min(T_all, j_begin + chunk) : T_all;
   const uint2 qq = *reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4);
   const float2 q0 = unpack_bf16x2(qq.x), q1 = unpack_bf16x2(qq.y);
   const __nv_bfloat16* kc = kcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;
   const __nv_bfloat16* vc = vcache + (static_cast<int64_t>(b) * Hkv + hk) * Tmax * 128 + lane * 4;
   const int32_t* mk = key_mask ? key_mask + static_cast<int64_t>(b) * mask_stride : nullptr;
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-  for (int j0 = warp * 4; j0 < T; j0 += 16) {
+  for (int j0 = j_begin + warp * 4; j0 < T; j0 += 16) {
     uint2 kk[4], vv[4];
     bool ok[4];
 #pragma unroll
@@ -178,12 +183,92 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
       r0 += s_o[w][lane * 4 + 0] * c; r1 += s_o[w][lane * 4 + 1] * c;
       r2 += s_o[w][lane * 4 + 2] * c; r3 += s_o[w][lane * 4 + 3] * c;
     }
+    if (partial != nullptr) {  // [bh][split][2 + 128] floats: max, sum, un-normalised output
+      float* dst = partial + (static_cast<int64_t>(bh) * gridDim.y + blockIdx.y) * 130;
+      if (lane == 0) { dst[0] = mm; dst[1] = lt; }
+      *reinterpret_cast<float2*>(dst + 2 + lane * 4) = make_float2(r0, r1);
+      *reinterpret_cast<float2*>(dst + 4 + lane * 4) = make_float2(r2, r3);
+      return;
+    }
     const float inv = lt > 0.f ? 1.f / lt : 0.f;
     uint2 r;
     r.x = pack_bf16x2(r0 * inv, r1 * inv);
     r.y = pack_bf16x2(r2 * inv, r3 * inv);
     *reinterpret_cast<uint2*>(out + (static_cast<int64_t>(b) * H + h) * 128 + lane * 4) = r;
   }
+}
+
+// one warp per (batch row, q head): combines the per-chunk partials of attn_decode_gqa128_kernel
+__global__ void __launch_bounds__(128)
+attn_decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int n_heads, int n_splits) {
+  const int bh = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (bh >= n_heads) return;
+  const float* src = partial + static_cast<int64_t>(bh) * n_splits * 130;
+  float mm = -INFINITY;
+  for (int sp = 0; sp < n_splits; ++sp) mm = fmaxf(mm, src[sp * 130]);
+  float lt = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+  for (int sp = 0; sp < n_splits; ++sp) {
+    const float ms = src[sp * 130];
+    if (ms == -INFINITY) continue;  // chunk past the end of the context, or fully masked
+    const float c = __expf(ms - mm);
+    lt += src[sp * 130 + 1] * c;
+    const float2 a = *reinterpret_cast<const float2*>(src + sp * 130 + 2 + lane * 4);
+    const float2 b2 = *reinterpret_cast<const float2*>(src + sp * 130 + 4 + lane * 4);
+    r0 += a.x * c; r1 += a.y * c; r2 += b2.x * c; r3 += b2.y * c;
+  }
+  const float inv = lt > 0.f ? 1.f / lt : 0.f;
+  uint2 r;
+  r.x = pack_bf16x2(r0 * inv, r1 * inv);
+  r.y = pack_bf16x2(r2 * inv, r3 * inv);
+  *reinterpret_cast<uint2*>(out + static_cast<int64_t>(bh) * 128 + lane * 4) = r;
+}
+
+// two-stage greedy sampling for large vocabularies: per-chunk (max, first index), then the row winner
+__global__ void __launch_bounds__(256)
+argmax_partial_kernel(const float* __restrict__ x, float* __restrict__ pval, int32_t* __restrict__ pidx, int V,
+                      int chunk) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int row = blockIdx.y, c0 = blockIdx.x * chunk, c1 = min(V, c0 + chunk);
+  const float* xr = x + static_cast<int64_t>(row) * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = c0 + threadIdx.x; i < c1; i += 256) {
+    const float v = xr[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    pval[row * gridDim.x + blockIdx.x] = best;
+    pidx[row * gridDim.x + blockIdx.x] = bi;
+  }
+}
+__global__ void argmax_final_kernel(const float* __restrict__ pval, const int32_t* __restrict__ pidx,
+                                    int32_t* __restrict__ out, int n_chunks) {
+  const int row = blockIdx.x, lane = threadIdx.x;  // one warp per row
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < n_chunks; c += 32) {
+    const float v = pval[row * n_chunks + c];
+    const int i = pidx[row * n_chunks + c];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) out[row] = bi;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -550,12 +635,21 @@ argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int V)
 
 using namespace mb;
 
-extern "C" int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, void* stream_) {
+extern "C" int mb_argmax_f32(const float* x, int32_t* out, int rows, int V, float* ws_val, int32_t* ws_idx, int n_chunks,
+                             void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_argmax_f32: no sm_100 device");
-  MB_CHECK_ARG(rows >= 0 && V >= 1, MB_ERR_SHAPE, "mb_argmax_f32: bad shape");
+  MB_CHECK_ARG(rows >= 0 && V >= 1 && n_chunks >= 1, MB_ERR_SHAPE, "mb_argmax_f32: bad shape");
   if (rows == 0) return MB_OK;
-  argmax_f32_kernel<<<rows, 256, 0, stream>>>(x, out, V);
+  if (n_chunks == 1 || ws_val == nullptr || ws_idx == nullptr) {
+    argmax_f32_kernel<<<rows, 256, 0, stream>>>(x, out, V);
+    MB_CHECK_CUDA(cudaGetLastError());
+    return MB_OK;
+  }
+  const int chunk = (V + n_chunks - 1) / n_chunks;
+  argmax_partial_kernel<<<dim3(n_chunks, rows), 256, 0, stream>>>(x, ws_val, ws_idx, V, chunk);
+  MB_CHECK_CUDA(cudaGetLastError());
+  argmax_final_kernel<<<rows, 32, 0, stream>>>(ws_val, ws_idx, out, n_chunks);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }
@@ -594,16 +688,33 @@ extern "C" int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, v
 
 extern "C" int mb_attn_decode_gqa(const void* q, const void* kcache, const void* vcache, const int32_t* key_mask,
                                   int64_t mask_stride, void* out, int B, int H, int Hkv, int hd, int Tmax,
-                                  const int32_t* t_dev, int t_host, float scale, void* stream_) {
+                                  const int32_t* t_dev, int t_host, float scale, float* workspace, int n_splits,
+                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_attn_decode_gqa: no sm_100 device");
   MB_CHECK_ARG(hd == 128 && H % Hkv == 0, MB_ERR_SHAPE, "mb_attn_decode_gqa: head_dim must be 128 and H %% Hkv == 0");
   MB_CHECK_ARG(t_dev != nullptr || (t_host >= 0 && t_host <= Tmax), MB_ERR_SHAPE, "mb_attn_decode_gqa: bad length");
+  MB_CHECK_ARG(n_splits >= 1 && n_splits <= 65535 && (n_splits == 1 || workspace != nullptr), MB_ERR_SHAPE,
+               "mb_attn_decode_gqa: n_splits > 1 needs a workspace of B * H * n_splits * 130 floats");
   if (B == 0) return MB_OK;
-  attn_decode_gqa128_kernel<<<B * H, 128, 0, stream>>>(
+  if (n_splits == 1) {
+    attn_decode_gqa128_kernel<<<B * H, 128, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+        static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
+        Tmax, t_dev, t_host, scale, nullptr, 0);
+    MB_CHECK_CUDA(cudaGetLastError());
+    return MB_OK;
+  }
+  // the longest context this call can see: the host length, or the whole cache when the length lives on the device
+  const int t_bound = (t_dev != nullptr) ? Tmax : t_host;
+  const int chunk = ((t_bound + n_splits - 1) / n_splits + 15) / 16 * 16;
+  attn_decode_gqa128_kernel<<<dim3(B * H, n_splits), 128, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
       static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
-      Tmax, t_dev, t_host, scale);
+      Tmax, t_dev, t_host, scale, workspace, chunk < 16 ? 16 : chunk);
+  MB_CHECK_CUDA(cudaGetLastError());
+  attn_decode_merge_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(workspace, static_cast<__nv_bfloat16*>(out), B * H,
+                                                                n_splits);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

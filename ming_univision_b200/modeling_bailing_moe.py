@@ -427,12 +427,14 @@ class BailingMoeForCausalLM(nn.Module):
         self._pk = None
         self.use_cuda_graph = True
         self._gen_ws = {}
+        self._txt_ws = {}
         for p in self.parameters():
             p.requires_grad_(False)
 
     def _apply(self, fn, *a, **k):
         self._pk = None
         self._gen_ws = {}
+        self._txt_ws = {}
         return super()._apply(fn, *a, **k)
 
     def setup_vishead_diffloss(self, diffloss_w=3072, diffloss_d=12, num_sampling_steps="16",
@@ -559,6 +561,80 @@ class BailingMoeForCausalLM(nn.Module):
         final_mask = mask[:, :t_now + n_tok]
         image_tensor = sem_to_pix_func(torch.cat(output_tokens, dim=1))
         return image_tensor, hidden, final_mask
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # Greedy text decoding (HF GenerationMixin.generate with do_sample = false, mingunivision/config.json:30, as driven by
+    # MingUniVisionForConditionalGeneration.generate, modeling_bailingmm.py:249-270): one CUDA-graph replay per token
+    # ---------------------------------------------------------------------------------------------------------------
+    def _text_step(self, ws) -> None:
+        """hidden(last token) -> lm_head logits (fp32) -> argmax -> embedding of the chosen token -> one cached LLM step,
+        on static buffers with the cache position read from device memory."""
+        logits = self.compute_logit(ws["last"])
+        ws["tok"].copy_(ops.argmax_rows(logits.reshape(1, -1)))
+        ws["embeds"].copy_(self.model.embed(ws["tok"].view(1, 1).long()))
+        hidden = self.model.forward_tokens(ws["embeds"], ws["pos"], ws["cache"], key_mask=None, t_dev=ws["t_llm"])
+        ws["last"].copy_(hidden[:, -1])
+        ws["t_llm"].add_(1)
+        ws["pos"].add_(1)
+
+    @torch.no_grad()
+    def greedy_decode(self, last_hidden: torch.Tensor, cache: "BailingKVCache", max_new_tokens: int,
+                      stop_ids=()) -> list:
+        """Greedy continuation after a prefill: `last_hidden` [1, D] is the final-norm hidden state of the last prompt
+        token, `cache` holds the prompt.  Returns the new token ids (stops after emitting any id in `stop_ids`; the
+        per-token stop check reads the token on the host, as HF generate does).  The cache ends up holding the prompt
+        plus every emitted token but the last (HF generate never feeds the final token back either)."""
+        dev = last_hidden.device
+        if cache.batch != 1:
+            raise ValueError("text decoding runs on one row")
+        if cache.seq_len + max_new_tokens > cache.max_len:
+            raise ValueError("KV cache too small for max_new_tokens")
+        use_graph = self.use_cuda_graph and getattr(self.model, "ep_size", 1) == 1
+        key = (id(cache), cache.max_len)
+        ws = self._txt_ws.get(key) if use_graph else None
+        if ws is None:
+            D = self.config.hidden_size
+            ws = dict(cache=cache, last=torch.zeros((1, D), dtype=BF16, device=dev),
+                      embeds=torch.zeros((1, 1, D), dtype=BF16, device=dev),
+                      tok=torch.zeros((1,), dtype=torch.int32, device=dev),
+                      pos=torch.zeros((1, 1), dtype=torch.int32, device=dev),
+                      t_llm=torch.zeros((1,), dtype=torch.int32, device=dev), graph=None)
+            if use_graph:
+                self._txt_ws = {key: ws}
+
+        def reset_state():
+            ws["last"].copy_(last_hidden.reshape(1, -1).to(BF16))
+            ws["pos"].fill_(cache.seq_len)
+            ws["t_llm"].fill_(cache.seq_len)
+
+        reset_state()
+        if use_graph and ws["graph"] is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):  # warm-up outside capture; its cache write is overwritten by the real run
+                self._text_step(ws)
+            torch.cuda.current_stream().wait_stream(side)
+            reset_state()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._text_step(ws)
+            ws["graph"] = g
+            reset_state()
+        out = []
+        stop = set(int(t) for t in stop_ids)
+        for _ in range(max_new_tokens):
+            if use_graph:
+                ws["graph"].replay()
+            else:
+                self._text_step(ws)
+            t = int(ws["tok"].item())
+            out.append(t)
+            cache.seq_len += 1  # the step that chose `t` also fed it through the model
+            if t in stop:
+                break
+        if out:
+            cache.seq_len -= 1  # as with HF generate, the last emitted token is not part of the cached context
+        return out
 
     # ---------------------------------------------------------------------------------------------------------------
     # CUDA-graph fast path of the AR visual-token loop: one replay per generated token

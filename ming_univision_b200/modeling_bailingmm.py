@@ -147,20 +147,12 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         cache = getattr(self, "_ws_cache", None)
         if cache is None or cache.max_len < need or cache.k[0].device != dev:
             cache = self._ws_cache = llm.new_cache(max_len=max(need, 512))
-            llm._gen_ws = {}
+            llm._gen_ws, llm._txt_ws = {}, {}
         cache.seq_len, cache.batch = 0, 1
         pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0)
         hidden = llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
-        out_ids = []
-        last = hidden[:, -1]
-        for _ in range(max_new_tokens):
-            tok = ops.argmax_rows(llm.compute_logit(last).reshape(1, -1))
-            t = int(tok.item())  # per-token EOS check on the host, as HF generate does
-            out_ids.append(t)
-            if t == eos or t == cfg.image_start_token:
-                break
-            e = llm.model.embed(tok.view(1, 1).long())
-            p1 = torch.full((1, 1), cache.seq_len, dtype=torch.int32, device=dev)
-            last = llm.model.forward_tokens(e, p1, cache, key_mask=None)[:, -1]
+        # greedy decoding, one CUDA-graph replay per token (BailingMoeForCausalLM.greedy_decode); the per-token EOS check
+        # reads the token on the host, as HF generate does
+        out_ids = llm.greedy_decode(hidden[:, -1], cache, max_new_tokens, stop_ids=(eos, cfg.image_start_token))
         self.past_key_values = cache
         return out_ids

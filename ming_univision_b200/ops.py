@@ -419,15 +419,19 @@ def rope_kv_append(qkv: torch.Tensor, position_ids: torch.Tensor, kcache: torch.
 
 def attn_decode_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, key_mask: torch.Tensor | None,
                     H: int, T: int, t_dev: torch.Tensor | None = None) -> torch.Tensor:
-    """q [B, H*128] against cache slots 0..T-1 (key_mask int32 [B, >=T], 0 = skip)."""
+    """q [B, H*128] against cache slots 0..T-1 (key_mask int32 [B, >=T], 0 = skip).  Contexts longer than a few
+    hundred keys are split over several CTAs per head (flash-decoding) so that B * H = 16..48 heads fill the GPU."""
     _check_bf16(q, kcache, vcache)
     lib = _lib.load()
     B, Hkv, Tmax, hd = kcache.shape
     B = q.shape[0]
     out = torch.empty((B, H * hd), dtype=BF16, device=q.device)
+    t_bound = Tmax if t_dev is not None else int(T)   # static upper bound of the context length of this call
+    n_splits = max(1, min((t_bound + 63) // 64, max(1, 592 // (B * H))))
+    ws = torch.empty((B * H * n_splits * 130,), dtype=torch.float32, device=q.device) if n_splits > 1 else None
     rc = lib.mb_attn_decode_gqa(q.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), _iptr(key_mask),
                                 key_mask.stride(0) if key_mask is not None else 0, out.data_ptr(), B, H, Hkv, hd, Tmax,
-                                _iptr(t_dev), int(T), hd ** -0.5, _stream())
+                                _iptr(t_dev), int(T), hd ** -0.5, _ptr(ws), n_splits, _stream())
     _lib.check(rc, "mb_attn_decode_gqa")
     return out
 
@@ -598,5 +602,9 @@ def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     rows, V = logits.shape
     out = torch.empty((rows,), dtype=torch.int32, device=logits.device)
-    _lib.check(lib.mb_argmax_f32(logits.data_ptr(), out.data_ptr(), rows, V, _stream()), "mb_argmax_f32")
+    n_chunks = max(1, min(128, V // 1024))
+    wv = torch.empty((rows * n_chunks,), dtype=torch.float32, device=logits.device) if n_chunks > 1 else None
+    wi = torch.empty((rows * n_chunks,), dtype=torch.int32, device=logits.device) if n_chunks > 1 else None
+    _lib.check(lib.mb_argmax_f32(logits.data_ptr(), out.data_ptr(), rows, V, _ptr(wv), _ptr(wi), n_chunks, _stream()),
+               "mb_argmax_f32")
     return out

@@ -77,6 +77,50 @@ def test_rope_kv_append_and_decode_attention(cuda_device):
     assert (a.float().cpu() - ref).abs().max() < 3e-2
 
 
+@pytest.mark.parametrize("B,T,Tmax,dev_len", [(1, 1552, 1616, False), (3, 700, 2048, True), (2, 33, 64, False),
+                                              (2, 1, 512, True)])
+def test_decode_attention_long_context(cuda_device, B, T, Tmax, dev_len):
+    """q_len = 1 GQA attention over a long static cache: the keys are split over several CTAs per head and merged
+    (flash-decoding); per-row key masks; the length given on the host or read from device memory (CUDA-graph form)."""
+    from ming_univision_b200 import ops
+
+    H, Hkv, hd = 16, 4, 128
+    q = _rand((B, H * hd), cuda_device, 1.0, 50)
+    kc = _rand((B, Hkv, Tmax, hd), cuda_device, 1.0, 51)
+    vc = _rand((B, Hkv, Tmax, hd), cuda_device, 1.0, 52)
+    g = torch.Generator().manual_seed(53)
+    mask = (torch.rand((B, Tmax), generator=g) > 0.2).to(torch.int32)
+    mask[:, T - 1] = 1
+    mask[0] = 1
+    mask = mask.to(cuda_device)
+    if dev_len:
+        t_dev = torch.tensor([T - 5], dtype=torch.int32, device=cuda_device)
+        out = ops.attn_decode_gqa(q, kc, vc, mask, H, 5, t_dev)
+    else:
+        out = ops.attn_decode_gqa(q, kc, vc, mask, H, T)
+    qf = q.float().view(B, H, 1, hd)
+    kf = kc[:, :, :T].float().repeat_interleave(H // Hkv, dim=1)
+    vf = vc[:, :, :T].float().repeat_interleave(H // Hkv, dim=1)
+    att = (qf @ kf.transpose(-1, -2)) * hd ** -0.5
+    att = att.masked_fill(mask[:, None, None, :T] == 0, float("-inf"))
+    ref = (att.softmax(-1) @ vf).reshape(B, H * hd)
+    assert (out.float() - ref).abs().max().item() < 2e-2
+    assert rel_l2(out.cpu(), ref.cpu()) < 8e-3
+
+
+def test_argmax_rows_large_vocab(cuda_device):
+    from ming_univision_b200 import ops
+
+    g = torch.Generator().manual_seed(60)
+    x = torch.randn((3, 126464), generator=g).to(cuda_device)
+    x[1, 77777] = x[1].max() + 1
+    x[2, 500] = 9.0
+    x[2, 90000] = 9.0  # tie: the first index wins (torch.argmax)
+    assert ops.argmax_rows(x).tolist() == x.argmax(-1).tolist()
+    y = torch.randn((2, 300), generator=g).to(cuda_device)
+    assert ops.argmax_rows(y).tolist() == y.argmax(-1).tolist()
+
+
 def test_router_topk(cuda_device):
     from ming_univision_b200 import ops
 
@@ -327,3 +371,30 @@ def test_greedy_text_decode_vs_oracle(tiny_model, cuda_device):
                 agree += 1
             h = L.model_forward(sd, cfg, sd["model.word_embeddings.weight"][torch.tensor([[t]])], None, None, caches)
     assert agree >= 1
+
+
+def test_greedy_text_decode_graph_equals_eager(tiny_model, cuda_device):
+    """The one-graph-replay-per-token decoder must emit exactly the tokens of the eager step loop, leave the same
+    cache length behind, and be re-usable for a second prompt (graph replayed on the re-initialised static buffers)."""
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    llm = tiny_model.model
+    outs = {}
+    for mode in (True, False, True):
+        llm.use_cuda_graph = mode
+        toks = tiny_model.generate_text(ids, max_new_tokens=7, eos_token_id=-1)
+        outs.setdefault(mode, []).append((toks, tiny_model.past_key_values.seq_len))
+    llm.use_cuda_graph = True
+    assert outs[True][0] == outs[False][0] == outs[True][1]
+    assert outs[True][0][1] == ids.shape[1] + 7 - 1
+    # a different prompt through the already captured graph
+    ids2 = torch.flip(ids, dims=[1]).contiguous()
+    a = tiny_model.generate_text(ids2, max_new_tokens=5, eos_token_id=-1)
+    llm.use_cuda_graph = False
+    b = tiny_model.generate_text(ids2, max_new_tokens=5, eos_token_id=-1)
+    llm.use_cuda_graph = True
+    assert a == b
+    # stop token: generation ends right after emitting it
+    stop = a[2]
+    c = tiny_model.generate_text(ids2, max_new_tokens=5, eos_token_id=stop)
+    assert c == a[:a.index(stop) + 1]

@@ -132,16 +132,16 @@ def main():
     last = hidden[:, -1]
 
     def decode():
-        nonlocal last
         cache.seq_len = S
-        for _ in range(n_new):
-            tok = ops.argmax_rows(llm.compute_logit(last).reshape(1, -1))
-            e_ = llm.model.embed(tok.view(1, 1).long())
-            p1 = torch.full((1, 1), cache.seq_len, dtype=torch.int32, device=dev)
-            last = llm.model.forward_tokens(e_, p1, cache, key_mask=None)[:, -1]
+        llm.greedy_decode(last, cache, n_new, stop_ids=())
 
     ms = timeit(decode, iters=2, warm=1)
-    res["decode"] = {"ms_per_token": round(ms / n_new, 3), "tokens_per_s": round(n_new / ms * 1e3, 1)}
+    res["decode"] = {"ms_per_token": round(ms / n_new, 3), "tokens_per_s": round(n_new / ms * 1e3, 1),
+                     "note": "greedy, one CUDA-graph replay + one host read per token"}
+    llm.use_cuda_graph = False
+    ms_e = timeit(decode, iters=1, warm=1)
+    llm.use_cuda_graph = True
+    res["decode_eager"] = {"ms_per_token": round(ms_e / n_new, 3), "tokens_per_s": round(n_new / ms_e * 1e3, 1)}
     print(res["decode"], flush=True)
     res["mem_gb"] = round(torch.cuda.max_memory_allocated() / 1e9, 1)
     os.makedirs("gpurun_out", exist_ok=True)
