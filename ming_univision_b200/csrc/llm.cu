@@ -404,7 +404,7 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   for (int p0 = beg; p0 < end; p0 += 8) {
     const int cnt = min(8, end - p0);
     __syncthreads();  // previous chunk fully consumed
-    for (int i = tid; i < (cnt + 1) * (row_bytes / 16); i += 256) {
+    for (int i = tid; i < (cnt + 1) * (row_bytes / 16); i += blockDim.x) {
       const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
       uint4 v = make_uint4(0, 0, 0, 0);
       if (m < cnt && c < kchunks) {
@@ -416,7 +416,8 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
     }
     __syncthreads();
     const uint8_t* xrow = moe_smem + min(g, cnt) * row_bytes + t * 16;
-    for (int item = blockIdx.x * 8 + warp; item < n_items; item += gridDim.x * 8) {
+    const int nwarps = blockDim.x >> 5;
+    for (int item = blockIdx.x * nwarps + warp; item < n_items; item += gridDim.x * nwarps) {
       const int n0 = item * 16;
       const __nv_bfloat16* wr[kTiles][2];
 #pragma unroll
@@ -743,7 +744,8 @@ extern "C" int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t*
 }
 
 static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
-                            void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, cudaStream_t stream) {
+                            void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, int active_max,
+                            cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(9) * (((K / 8 + 3) / 4) * 64 + 64);
   MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= 8192");
   static bool attr_set[2] = {false, false};
@@ -754,17 +756,25 @@ static int launch_moe_phase(int phase, const void* A, const void* W, const int32
       MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[phase] = true;
   }
-  int xblocks = ((n_cols + 15) / 16 + 7) / 8;  // one 16-row weight tile per warp
+  // One 16-row weight tile per warp.  Only the experts that received pairs do any work (at most `active_max` of the E
+  // CTA columns): with a single decode row (<= 8 active experts) eight-warp CTAs would leave more than half of the SMs
+  // idle, so that case runs four-warp CTAs (measured: 3.47 -> 3.33 ms per text token); two or more CFG rows keep the
+  // eight-warp shape (smaller CTAs measured slower there: the activation rows are re-staged by every CTA).
+  const int n_items = (n_cols + 15) / 16;
+  const int warps = (active_max <= 8) ? 4 : 8;
+  int xblocks = (n_items + warps - 1) / warps;
   if (xblocks < 1) xblocks = 1;
   dim3 grid(xblocks, E);
   if (phase == 0)
-    moe_expert_kernel<0><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
-                                                      static_cast<const __nv_bfloat16*>(W), offs, sorted,
-                                                      static_cast<__nv_bfloat16*>(dst), topk, K, n_cols, expert_stride);
+    moe_expert_kernel<0><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
+                                                             static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                                                             static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
+                                                             expert_stride);
   else
-    moe_expert_kernel<1><<<grid, 256, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
-                                                      static_cast<const __nv_bfloat16*>(W), offs, sorted,
-                                                      static_cast<__nv_bfloat16*>(dst), topk, K, n_cols, expert_stride);
+    moe_expert_kernel<1><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
+                                                             static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                                                             static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
+                                                             expert_stride);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }
@@ -774,7 +784,7 @@ extern "C" int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* exp
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_gate_up: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(0, x, Wgu, expert_offsets, sorted_pair, hid, k, E, D, I, static_cast<int64_t>(2) * I * D,
-                          static_cast<cudaStream_t>(stream_));
+                          T * k < E ? T * k : E, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
@@ -782,7 +792,7 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_down: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(1, hid, Wd, expert_offsets, sorted_pair, out_pairs, k, E, I, D, static_cast<int64_t>(D) * I,
-                          static_cast<cudaStream_t>(stream_));
+                          T * k < E ? T * k : E, static_cast<cudaStream_t>(stream_));
 }
 
 
