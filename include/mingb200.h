@@ -104,6 +104,16 @@ int mb_row_stats(const void* x, int64_t ldx, float* stats, int rows, int dim, vo
 int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
                  int M, int N, int K, int epi, const void* residual, int64_t ldr, const void* gate, int64_t ldg,
                  void* out_f32, void* stream);
+/* Same with the input normalisation FUSED into the staging of the activation rows (no separate row kernel in front
+ * of the streaming GEMM):
+ *   norm = 1  adaLN   : a' = (LN(a) * gamma + beta) * bf16(1 + scale[m]) + shift[m]   (gamma / beta may be NULL;
+ *                       ResBlock / FinalLayer of the RF head, diff_loss_rf_swiglu.py:184-185, 270, 290)
+ *   norm = 2  RMSNorm : a' = gamma * bf16(a * rsqrt(mean(a^2) + eps))                  (modeling_bailing_moe.py:131-136)
+ * statistics in fp32, a' rounded to bf16 before the product, exactly as mb_adaln_modulate / mb_rmsnorm round. */
+int mb_gemv_bf16_norm(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out, int64_t ldo,
+                      int M, int N, int K, int epi, const void* residual, int64_t ldr, const void* gate, int64_t ldg,
+                      void* out_f32, int norm, const void* gamma, const void* beta, const void* shift, int64_t ld_shift,
+                      const void* scale, int64_t ld_scale, float eps, void* stream);
 
 /* Tuning / test hook: pin the GEMM tile shape instead of the built-in heuristic.  cta_group: 1 = one CTA per
  * 128 x bn tile, 2 = CTA pair (tcgen05 cta_group::2) per 256 x bn tile, 0 = automatic; bn: 128, 256 or 0 = automatic.

@@ -28,6 +28,8 @@ SIGNATURES = {
     "mb_attn_set_backend": [_i],
     "mb_attn_set_debug": [_vp],
     "mb_gemv_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
+    "mb_gemv_bf16_norm": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i, _vp, _vp,
+                          _vp, _i64, _vp, _i64, _f, _vp],
     "mb_adaln_modulate": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],

@@ -25,6 +25,18 @@ struct GemvParams {
   const __nv_bfloat16* gate; int64_t ldg;   // GATED: per-element gate
   float* out_f32;                            // optional fp32 copy of the output (may be null)
   int M, N, K;
+  // Fused input normalisation (mb_gemv_bf16_norm): the activation rows are normalised while they are staged in shared
+  // memory, so the separate row kernel (and its launch + dependency gap in front of EVERY streaming GEMM of the RF
+  // head / the LLM step) disappears.  Each CTA redoes the M <= 8 row statistics: ~K flops per row, nothing next to
+  // the weight tile it streams.
+  //   pro = 1  adaLN    : bf16( (LN(a) * gamma + beta) * bf16(1 + scale[m]) + shift[m] )   diff_loss_rf_swiglu.py:184-185, 270, 290
+  //   pro = 2  RMSNorm  : bf16( gamma * bf16(a * rsqrt(mean(a^2) + eps)) )                  modeling_bailing_moe.py:131-136
+  int pro;
+  const __nv_bfloat16* pro_gamma;
+  const __nv_bfloat16* pro_beta;
+  const __nv_bfloat16* pro_shift; int64_t ld_shift;
+  const __nv_bfloat16* pro_scale; int64_t ld_scale;
+  float pro_eps;
 };
 
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
@@ -117,11 +129,87 @@ gemv_bf16_kernel(const GemvParams p) {
   pdl_wait();
 
   // stage the activations: rows 0..M-1, then one zero row shared by the unused MMA columns
-  for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
-    const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (m < p.M && c < kchunks) v = *reinterpret_cast<const uint4*>(p.A + m * p.lda + c * 8);
-    *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = v;
+  if (p.pro == 0) {
+    for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
+      const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < p.M && c < kchunks) v = *reinterpret_cast<const uint4*>(p.A + m * p.lda + c * 8);
+      *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = v;
+    }
+  } else {
+    // warp m normalises row m (M <= 8 = warps per CTA); two-pass statistics in fp32 as the row kernels do
+    if (warp <= p.M) {
+      const int m = warp;
+      uint8_t* dst = gemv_smem + m * row_bytes;
+      if (m == p.M) {
+        for (int c = lane; c < row_bytes / 16; c += 32) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0, 0, 0, 0);
+      } else {
+        const __nv_bfloat16* ar = p.A + m * p.lda;
+        float s1 = 0.f;
+        for (int c = lane; c < kchunks; c += 32) {
+          const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
+          const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+          if (p.pro == 1) s1 += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+          else s1 += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y) + (f2.x * f2.x + f2.y * f2.y) +
+                     (f3.x * f3.x + f3.y * f3.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        float mean = 0.f, rstd;
+        if (p.pro == 1) {
+          mean = s1 / K;
+          float s2 = 0.f;
+          for (int c = lane; c < kchunks; c += 32) {
+            const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
+            const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+            const float d0 = f0.x - mean, d1 = f0.y - mean, d2 = f1.x - mean, d3 = f1.y - mean, d4 = f2.x - mean,
+                        d5 = f2.y - mean, d6 = f3.x - mean, d7 = f3.y - mean;
+            s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          rstd = rsqrtf(s2 / K + p.pro_eps);
+        } else {
+          rstd = rsqrtf(s1 / K + p.pro_eps);
+        }
+        for (int c = lane; c < row_bytes / 16; c += 32) {
+          uint4 o4 = make_uint4(0, 0, 0, 0);
+          if (c < kchunks) {
+            const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
+            float v[8];
+            {
+              const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+              v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
+            }
+            __nv_bfloat16 gm[8], bt[8], sh[8], sc[8];
+            if (p.pro_gamma) *reinterpret_cast<uint4*>(gm) = *reinterpret_cast<const uint4*>(p.pro_gamma + c * 8);
+            if (p.pro_beta) *reinterpret_cast<uint4*>(bt) = *reinterpret_cast<const uint4*>(p.pro_beta + c * 8);
+            if (p.pro == 1) {
+              *reinterpret_cast<uint4*>(sh) = *reinterpret_cast<const uint4*>(p.pro_shift + m * p.ld_shift + c * 8);
+              *reinterpret_cast<uint4*>(sc) = *reinterpret_cast<const uint4*>(p.pro_scale + m * p.ld_scale + c * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (p.pro == 1) {
+                float x = (v[i] - mean) * rstd;
+                if (p.pro_gamma) x = x * __bfloat162float(gm[i]) + (p.pro_beta ? __bfloat162float(bt[i]) : 0.f);
+                x = x * bf16_round(1.f + __bfloat162float(sc[i])) + __bfloat162float(sh[i]);
+                v[i] = x;
+              } else {
+                v[i] = __bfloat162float(gm[i]) * bf16_round(v[i] * rstd);
+              }
+            }
+            o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
+            o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
+          }
+          *reinterpret_cast<uint4*>(dst + c * 16) = o4;
+        }
+      }
+    }
+    if (p.M == 8 && warp == 0) {  // 9th (zero) row when all eight warps were busy with data rows
+      uint8_t* dst = gemv_smem + 8 * row_bytes;
+      for (int c = lane; c < row_bytes / 16; c += 32) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0, 0, 0, 0);
+    }
   }
   __syncthreads();
   const uint8_t* xrow = gemv_smem + min(g, p.M) * row_bytes + t * 16;
@@ -234,9 +322,11 @@ static int launch_gemv_ks(const GemvParams& p, int epi, int grid, size_t smem, c
 
 using namespace mb;
 
-extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
-                            int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
-                            const void* gate, int64_t ldg, void* out_f32, void* stream_) {
+static int gemv_impl(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                     int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
+                     const void* gate, int64_t ldg, void* out_f32, int pro, const void* gamma, const void* beta,
+                     const void* shift, int64_t ld_shift, const void* scale, int64_t ld_scale, float eps,
+                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_gemv_bf16: no sm_100 device");
   MB_CHECK_ARG(M >= 0 && M <= 8 && N >= 1 && K >= 8, MB_ERR_SHAPE, "mb_gemv_bf16: need 0 <= M <= 8 (M=%d N=%d K=%d)", M,
@@ -262,6 +352,12 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.gate = static_cast<const __nv_bfloat16*>(gate); p.ldg = ldg;
   p.out_f32 = static_cast<float*>(out_f32);
   p.M = M; p.N = N; p.K = K;
+  p.pro = pro;
+  p.pro_gamma = static_cast<const __nv_bfloat16*>(gamma);
+  p.pro_beta = static_cast<const __nv_bfloat16*>(beta);
+  p.pro_shift = static_cast<const __nv_bfloat16*>(shift); p.ld_shift = ld_shift;
+  p.pro_scale = static_cast<const __nv_bfloat16*>(scale); p.ld_scale = ld_scale;
+  p.pro_eps = eps;
   const int n_out = (epi == MB_EPI_SWIGLU) ? N / 2 : N;
   // K-split: enough (row tile, K-slice) work items to give every SM ~8 busy warps, but >= 8 k-groups per slice
   const int n_items = (n_out + 15) / 16;
@@ -271,6 +367,8 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
     ksplit *= 2;
   const int items_per_iter = (kGemvThreads / 32) / ksplit;
   const int units = (n_items + items_per_iter - 1) / items_per_iter;
+  // (a software-pipelined variant with two weight batches in flight per warp needs ~170 registers, i.e. one CTA per
+  // SM, and measured SLOWER: 8.25 -> 10.97 ms per RF sample — occupancy hides the HBM latency better than depth)
   const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
   int grid = num_sms() * per_sm;
   if (grid > units) grid = units;
@@ -280,4 +378,29 @@ extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t l
     case 4: return launch_gemv_ks<4>(p, epi, grid, smem, stream);
     default: return launch_gemv_ks<8>(p, epi, grid, smem, stream);
   }
+}
+
+extern "C" int mb_gemv_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                            int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
+                            const void* gate, int64_t ldg, void* out_f32, void* stream_) {
+  return gemv_impl(A, lda, W, ldw, bias, out, ldo, M, N, K, epi, residual, ldr, gate, ldg, out_f32, 0, nullptr, nullptr,
+                   nullptr, 0, nullptr, 0, 0.f, stream_);
+}
+
+extern "C" int mb_gemv_bf16_norm(const void* A, int64_t lda, const void* W, int64_t ldw, const void* bias, void* out,
+                                 int64_t ldo, int M, int N, int K, int epi, const void* residual, int64_t ldr,
+                                 const void* gate, int64_t ldg, void* out_f32, int norm, const void* gamma,
+                                 const void* beta, const void* shift, int64_t ld_shift, const void* scale,
+                                 int64_t ld_scale, float eps, void* stream_) {
+  MB_CHECK_ARG(norm == 1 || norm == 2, MB_ERR_SHAPE, "mb_gemv_bf16_norm: norm must be 1 (adaLN) or 2 (RMSNorm)");
+  if (norm == 1)
+    MB_CHECK_ARG(shift != nullptr && scale != nullptr && ld_shift % 8 == 0 && ld_scale % 8 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale) |
+                       reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+                 MB_ERR_ALIGN, "mb_gemv_bf16_norm: adaLN needs 16-byte aligned shift / scale rows (ld %% 8 == 0)");
+  if (norm == 2)
+    MB_CHECK_ARG(gamma != nullptr && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0, MB_ERR_ALIGN,
+                 "mb_gemv_bf16_norm: RMSNorm needs a 16-byte aligned weight");
+  return gemv_impl(A, lda, W, ldw, bias, out, ldo, M, N, K, epi, residual, ldr, gate, ldg, out_f32, norm, gamma, beta,
+                   shift, ld_shift, scale, ld_scale, eps, stream_);
 }

@@ -21,7 +21,7 @@ import torch.nn as nn
 from transformers import PretrainedConfig
 
 from . import ops
-from .diff_loss_rf_swiglu import RectifiedFlowLoss
+from .diff_loss_rf_swiglu import FUSED_NORM, RectifiedFlowLoss
 
 BF16 = torch.bfloat16
 
@@ -394,8 +394,10 @@ class BailingMoeModel(nn.Module):
         eps = cfg.rms_norm_eps
         im = None if image_mask is None else image_mask.reshape(-1)
         for li, (lp, lyr) in enumerate(zip(pk["layers"], self.layers)):
-            x = ops.rmsnorm(h, lp["ln1"], eps)
-            qkv = _dense(x, lp["qkv_w"], lp["qkv_b"])
+            if B * S <= 8 and FUSED_NORM:  # decode: RMSNorm fused into the staging of the qkv streaming GEMM
+                qkv = ops.gemv_norm(h, lp["qkv_w"], lp["qkv_b"], norm="rms", gamma=lp["ln1"], eps=eps)
+            else:
+                qkv = _dense(ops.rmsnorm(h, lp["ln1"], eps), lp["qkv_w"], lp["qkv_b"])
             # rows 0..B-1 of the [Bmax, Hkv, Tmax, hd] cache are a contiguous prefix the kernels index directly
             q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta, t_dev)
             if S == 1:

@@ -344,6 +344,37 @@ def gemv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None
     return out
 
 
+def gemv_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, *, norm: str,
+              gamma: torch.Tensor | None = None, beta: torch.Tensor | None = None, shift: torch.Tensor | None = None,
+              scale: torch.Tensor | None = None, eps: float = 1e-6, epi: int = EPI_BIAS,
+              residual: torch.Tensor | None = None, gate: torch.Tensor | None = None, out: torch.Tensor | None = None,
+              out_f32: torch.Tensor | None = None) -> torch.Tensor:
+    """gemv() with the input normalisation fused into the kernel (mb_gemv_bf16_norm): norm = "adaln" computes
+    (LN(x) * gamma + beta) * (1 + scale) + shift, norm = "rms" computes gamma * (x * rsqrt(mean(x^2) + eps))."""
+    _check_bf16(x, weight, bias, residual, gate, out, gamma, beta, shift, scale)
+    lib = _lib.load()
+    a = _rows2d(x)
+    M, K = a.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K or weight.stride(1) != 1:
+        raise ValueError(f"weight shape {tuple(weight.shape)} incompatible with input K={K}")
+    n_out = N // 2 if epi == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=BF16, device=x.device)
+    for t in (residual, gate, shift, scale):
+        if t is not None and t.stride(-1) != 1:
+            raise ValueError("residual / gate / shift / scale must have a unit inner stride")
+    code = {"adaln": 1, "rms": 2}[norm]
+    rc = lib.mb_gemv_bf16_norm(a.data_ptr(), a.stride(0), weight.data_ptr(), weight.stride(0), _ptr(bias),
+                               out.data_ptr(), out.stride(0), M, N, K, epi, _ptr(residual),
+                               residual.stride(0) if residual is not None else 0, _ptr(gate),
+                               gate.stride(0) if gate is not None else 0, _ptr(out_f32), code, _ptr(gamma), _ptr(beta),
+                               _ptr(shift), shift.stride(0) if shift is not None else 0, _ptr(scale),
+                               scale.stride(0) if scale is not None else 0, float(eps), _stream())
+    _lib.check(rc, "mb_gemv_bf16_norm")
+    return out
+
+
 def adaln_modulate(x: torch.Tensor, gamma: torch.Tensor | None, beta: torch.Tensor | None, shift: torch.Tensor,
                    scale: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """bf16((LN(x) * gamma + beta) * bf16(1 + scale) + shift) row-wise; shift / scale may be strided row views."""

@@ -151,3 +151,41 @@ def test_rf_sample_vs_reference_golden(cuda_device, name):
         x3 = m.sample(z * 0.5, temperature=temp, text_cfg=tc, image_cfg=ic, noise=noise)
         assert not torch.equal(x3, x)
         assert torch.equal(m.sample(z, temperature=temp, text_cfg=tc, image_cfg=ic, noise=noise), x)
+
+
+@pytest.mark.parametrize("M", [1, 3, 8])
+@pytest.mark.parametrize("norm", ["adaln", "adaln_noaffine", "rms"])
+def test_gemv_fused_norm_equals_two_kernels(cuda_device, M, norm):
+    """mb_gemv_bf16_norm (normalisation fused into the staging of the activation rows) against the separate row kernel
+    followed by the plain streaming GEMM: same rounding points, so the outputs agree to one bf16 ulp of the accumulated
+    sums (the row statistics are reduced in a different order)."""
+    from ming_univision_b200 import ops
+
+    K, N = 3072, 640
+    g = torch.Generator().manual_seed(70 + M)
+    rnd = lambda *sh, s=1.0: (torch.randn(sh, generator=g) * s).to(cuda_device).to(torch.bfloat16)  # noqa: E731
+    x, w, b = rnd(M, K, s=2.0), rnd(N, K, s=K ** -0.5), rnd(N)
+    gamma, beta = (rnd(K, s=0.1).float() + 1).to(torch.bfloat16), rnd(K, s=0.1)
+    mod = rnd(M, 2 * K + 8, s=0.3)
+    if norm == "rms":
+        a = ops.rmsnorm(x, gamma, 1e-5)
+        fused = ops.gemv_norm(x, w, b, norm="rms", gamma=gamma, eps=1e-5)
+    elif norm == "adaln":
+        a = ops.adaln_modulate(x, gamma, beta, mod[:, :K], mod[:, K:2 * K])
+        fused = ops.gemv_norm(x, w, b, norm="adaln", gamma=gamma, beta=beta, shift=mod[:, :K], scale=mod[:, K:2 * K])
+    else:
+        a = ops.adaln_modulate(x, None, None, mod[:, :K], mod[:, K:2 * K])
+        fused = ops.gemv_norm(x, w, b, norm="adaln", shift=mod[:, :K], scale=mod[:, K:2 * K])
+    two = ops.gemv(a, w, b)
+    assert fused.shape == two.shape
+    err = (fused.float() - two.float()).abs()
+    assert (err <= 2.0 ** -6 * two.float().abs() + 2e-2).all(), float(err.max())
+    assert float((fused.float() - two.float()).norm() / two.float().norm()) < 3e-3
+    # fused SwiGLU variant (the RF ResBlock form)
+    w12, b12 = rnd(2 * 256, K, s=K ** -0.5), rnd(2 * 256)
+    if norm != "rms":
+        gm, bt = (gamma, beta) if norm == "adaln" else (None, None)
+        f2 = ops.gemv_norm(x, w12, b12, norm="adaln", gamma=gm, beta=bt, shift=mod[:, :K], scale=mod[:, K:2 * K],
+                           epi=ops.EPI_SWIGLU)
+        t2 = ops.gemv(a, w12, b12, epi=ops.EPI_SWIGLU)
+        assert float((f2.float() - t2.float()).norm() / t2.float().norm()) < 5e-3
