@@ -328,10 +328,18 @@ def run_ours(args, world, rank, local):
     torch.cuda.synchronize()
     step_ms = t0.elapsed_time(t1)
     peaks = _peaks()
+    traffic, traffic_src = None, None
+    try:  # DRAM traffic per launch from the committed ncu --set full capture of the pixel-decoder GEMMs
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["mean_dram_bytes_per_launch"], tj["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
     roofline = {"bound": "tensor", "kernel": "mb::gemm_bf16_kernel (tcgen05.mma + TMA)", "achieved": achieved,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops"],
-                "peak_source": peaks["source"], "traffic": None, "gemm_launches_per_step": len(prof),
+                "peak_source": peaks["source"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
+                "traffic_source": traffic_src, "gemm_launches_per_step": len(prof),
                 "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / step_ms,
                 "gemm_flops_per_step": gemm_flops,
                 "step_flops_algorithmic": 213.0e9 * BATCH,

@@ -161,6 +161,8 @@ int mb_attn_set_backend(int backend);
 /* Development aid: device buffer (>= 64 x 16 int64) receiving clock64() phase stamps of CTA 0 of the tcgen05 attention
  * kernel; NULL switches it off. */
 int mb_attn_set_debug(void* dev_buf);
+/* Same for the GEMM kernel: >= 16 x 8 int64, stamps of the first CTA's MMA-issue and epilogue roles per tile. */
+int mb_gemm_set_debug(void* dev_buf);
 /* Decode-step attention against a static KV cache (semantic decoder, q_len = 1; layers/attention.py:213-239 with
  * past_key_value).  qkv[B, 3, H, 64] holds the new token; its K/V are appended at position `t` of
  * kcache/vcache[B, H, Tmax, 64] (DynamicCache.update, vision_transformer.py:396) and q attends to positions 0..t.

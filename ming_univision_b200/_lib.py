@@ -27,6 +27,7 @@ SIGNATURES = {
     "mb_gemm_force_tile": [_i, _i],
     "mb_attn_set_backend": [_i],
     "mb_attn_set_debug": [_vp],
+    "mb_gemm_set_debug": [_vp],
     "mb_gemv_bf16": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _vp],
     "mb_gemv_bf16_norm": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _i64, _vp, _i, _vp, _vp,
                           _vp, _i64, _vp, _i64, _f, _vp],

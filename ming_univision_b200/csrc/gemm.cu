@@ -58,6 +58,7 @@ struct GemmParams {
   const int32_t* grp_num_m_tiles;  // device scalar
   int grp_w_rows;             // rows of W per expert (N, or 2I for the [gate; up] slab)
   int grp_n_out;              // output width (I or N)
+  long long* dbg;             // optional clock64() stamps of worker 0 (mb_gemm_set_debug; development only)
   int grp_split;              // > 0: the B tile is two (BN/2)-row boxes, rows n_tile*BN/2 and grp_split + n_tile*BN/2 of
                               //      the expert's [gate; up] slab, so the SwiGLU epilogue needs no interleaved repack
 };
@@ -182,7 +183,10 @@ __device__ __forceinline__ void epi_math(const GemmParams& p, uint32_t t_row, in
     }
     if constexpr (EPI == MB_EPI_GELU) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = gelu_erf(bf16_round(v[i]));
+      for (int i = 0; i < 16; ++i) {  // bf16(acc + bias) as the reference's Linear output, then GELU on packed pairs
+        bf16x2_to_f32(pack_bf16x2(v[2 * i], v[2 * i + 1]), v[2 * i], v[2 * i + 1]);
+        gelu_erf_x2(v[2 * i], v[2 * i + 1]);
+      }
     }
   }
 }
@@ -312,13 +316,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint64_t db_base = umma_desc_sw128_kmajor(smem_u32(smem_b));
       const uint32_t desc_hi = static_cast<uint32_t>(da_base >> 32);
       const uint32_t a_lo0 = static_cast<uint32_t>(da_base), b_lo0 = static_cast<uint32_t>(db_base);
-      for (int tile = worker; tile < num_tiles; tile += num_workers) {
+      int tcount = 0;
+      for (int tile = worker; tile < num_tiles; tile += num_workers, ++tcount) {
+        const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && tcount < 16;
+        if (stamp) p.dbg[tcount * 8 + 0] = clock64();
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (stamp) p.dbg[tcount * 8 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (stamp && kb == 0) p.dbg[tcount * 8 + 2] = clock64();
           const uint32_t a_lo = a_lo0 + stage * (Cfg::kABytes >> 4);
           const uint32_t b_lo = b_lo0 + stage * (Cfg::kBBytes >> 4);
 #pragma unroll
@@ -333,6 +342,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         // accumulator complete -> epilogue warps (of both CTAs)
         if constexpr (CG == 2) umma_commit_cg2_mc(&tmem_full[acc], 0x3); else umma_commit(&tmem_full[acc]);
+        if (stamp) p.dbg[tcount * 8 + 3] = clock64();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -349,11 +359,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t epi_phase = 0;
     pdl_wait();  // the epilogue reads bias / residual / statistics and overwrites buffers earlier kernels may still read
     const int num_tiles = tile_count();
-    for (int tile = worker; tile < num_tiles; tile += num_workers) {
+    int tcount = 0;
+    for (int tile = worker; tile < num_tiles; tile += num_workers, ++tcount) {
       const int m_tile = tile / num_n_tiles;
       const int n_tile = tile % num_n_tiles;
+      const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 16;
+      if (stamp) p.dbg[tcount * 8 + 4] = clock64();
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (stamp) p.dbg[tcount * 8 + 5] = clock64();
       const int row = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       int64_t out_row = row;
@@ -399,38 +413,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float v[32];
             epi_math<BN, EPI>(p, t_row, tc, n_tile, n_tile * kOutTileN + tc, n_out_total - (n_tile * kOutTileN + tc),
                               ln_mean, ln_rstd, v);
+            uint32_t packed[16];  // the 32 output values of this chunk as bf16 pairs
             if constexpr (EPI == MB_EPI_RESIDUAL) {
               if (cc == 0) mbar_wait(&epi_bar[ew], epi_phase);
+              // out = bf16( bf16(acc + bias) + residual ), statistics of the stored values: all on packed fp32 pairs
+              // (6 issue slots per element instead of 11 — this epilogue outlasted the K = 1024 main loop)
+              const bool want_stats = p.ln_stats_out != nullptr;
+              const int nv = n_out_total - (n_tile * kOutTileN + tc);
+              uint64_t s2 = pack_f32x2(0.f, 0.f), q2 = s2;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4));
-                const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z),
-                             f3 = unpack_bf16x2(q.w);
-                v[8 * j + 0] = bf16_round(v[8 * j + 0]) + f0.x; v[8 * j + 1] = bf16_round(v[8 * j + 1]) + f0.y;
-                v[8 * j + 2] = bf16_round(v[8 * j + 2]) + f1.x; v[8 * j + 3] = bf16_round(v[8 * j + 3]) + f1.y;
-                v[8 * j + 4] = bf16_round(v[8 * j + 4]) + f2.x; v[8 * j + 5] = bf16_round(v[8 * j + 5]) + f2.y;
-                v[8 * j + 6] = bf16_round(v[8 * j + 6]) + f3.x; v[8 * j + 7] = bf16_round(v[8 * j + 7]) + f3.y;
-              }
-            }
-            if constexpr (EPI == MB_EPI_RESIDUAL) {
-              if (p.ln_stats_out != nullptr) {  // statistics of the rows as stored (bf16), for the LayerNorm that follows
-                const int nv = n_out_total - (n_tile * kOutTileN + tc);
+                const uint32_t rr[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float r = (i < nv) ? bf16_round(v[i]) : 0.f;
-                  st_sum += r;
-                  st_sq = fmaf(r, r, st_sq);
+                for (int h2 = 0; h2 < 4; ++h2) {
+                  const int i = 8 * j + 2 * h2;
+                  float a0, a1, r0, r1;
+                  bf16x2_to_f32(pack_bf16x2(v[i], v[i + 1]), a0, a1);
+                  bf16x2_to_f32(rr[h2], r0, r1);
+                  float o0, o1;
+                  unpack_f32x2(add_f32x2(pack_f32x2(a0, a1), pack_f32x2(r0, r1)), o0, o1);
+                  const uint32_t pk = pack_bf16x2(o0, o1);
+                  packed[4 * j + h2] = pk;
+                  if (want_stats) {
+                    float b0, b1;
+                    bf16x2_to_f32(pk, b0, b1);
+                    if (i >= nv) b0 = 0.f;
+                    if (i + 1 >= nv) b1 = 0.f;
+                    const uint64_t b = pack_f32x2(b0, b1);
+                    s2 = add_f32x2(s2, b);
+                    q2 = fma_f32x2(b, b, q2);
+                  }
                 }
               }
+              if (want_stats) {
+                float a, b;
+                unpack_f32x2(s2, a, b);
+                st_sum += a + b;
+                unpack_f32x2(q2, a, b);
+                st_sq += a + b;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) packed[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              uint4 q;
-              q.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              q.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              q.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              q.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4)) = q;
+              *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4)) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
             }
           }
           if constexpr (EPI == MB_EPI_RESIDUAL) {
@@ -480,6 +510,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
+      if (stamp) p.dbg[tcount * 8 + 6] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -531,6 +562,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 // Tile shape choice.  A "worker" is a CTA (CG = 1, 128 x BN tile) or a CTA pair (CG = 2, 256 x BN tile); the model is
 // waves x per-tile MMA time x a measured penalty for the L2 -> SM traffic of the narrower shapes (bench_ops.py).
 struct TileChoice { int cg, bn; };
+static long long* g_gemm_dbg = nullptr;
 static int g_force_cg = getenv("MB_GEMM_CG") ? atoi(getenv("MB_GEMM_CG")) : 0;
 static int g_force_bn = getenv("MB_GEMM_BN") ? atoi(getenv("MB_GEMM_BN")) : 0;
 static int g_no_tma_epi = getenv("MB_GEMM_NO_TMA_EPI") ? atoi(getenv("MB_GEMM_NO_TMA_EPI")) : 0;
@@ -560,6 +592,12 @@ static TileChoice choose_tile(int M, int N, int sms, bool swiglu) {
 }  // namespace mb
 
 using namespace mb;
+
+// Development aid: device buffer of >= 16 * 8 int64 receiving clock64() stamps of the first CTA's MMA / epilogue roles.
+extern "C" int mb_gemm_set_debug(void* dev_buf) {
+  mb::g_gemm_dbg = static_cast<long long*>(dev_buf);
+  return MB_OK;
+}
 
 extern "C" int mb_gemm_force_tile(int cta_group, int bn) {
   MB_CHECK_ARG(((cta_group & 3) <= 2) && (cta_group & ~0x13) == 0 && (bn == 0 || bn == 128 || bn == 256), MB_ERR_SHAPE,
@@ -634,6 +672,7 @@ extern "C" int mb_gemm_bf16_ex(const void* A, int64_t lda, const void* W, int64_
   p.ln_stats_out = ln_stats_out;
   p.grp_tile_expert = nullptr;
   p.grp_num_m_tiles = nullptr;
+  p.dbg = g_gemm_dbg;
   p.grp_split = 0;
   p.grp_w_rows = 0;
   p.grp_n_out = 0;

@@ -1,0 +1,114 @@
+"""Inference façade with the reference's surface (mingunivision/mingunivisioninfer.py:28-120):
+
+    MingUniVisionInfer(model_name_or_path, dtype="bf16").generate(messages, max_new_tokens=512,
+                                                                  output_image_prefix="output", for_edit=False) -> str
+    .reset_inner_state()
+
+The chat template, image fetching / resizing and tokenisation stay the reference's own CPU code
+(`processing_bailingmm.BailingMMProcessor`, `tokenization_bailing`; SURVEY.md §2.1 marks them API-only): they are
+imported from the reference checkout given by `reference_dir` (default: the directory holding the tokenizer files, as
+the reference's "./mingunivision").  Everything behind `self.model.generate(...)` is the B200-native path of this repo.
+`dtype="int4" / "int8"` (bitsandbytes / quanto) are out of scope and raise.
+
+Tests inject `model`, `processor` and `tokenizer` directly; no pretrained checkpoint exists offline, so the checkpoint
+loader below (`load_checkpoint`: config.json + *.safetensors of the HF layout, `mingunivisioninfer.py:72-78`) is exercised
+on synthetic state dicts only.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+import sys
+
+import torch
+
+from .mingtok.modeling_mingtok import MingTokConfig
+from .modeling_bailing_moe import BailingMoeConfig
+from .modeling_bailingmm import MingUniVisionForConditionalGeneration
+
+
+def load_checkpoint(model_dir: str, device="cuda") -> MingUniVisionForConditionalGeneration:
+    """Builds the wrapper from an HF-layout checkpoint directory: `config.json` with `llm_config`,
+    `vishead_diffloss_config` (modeling_bailingmm.py:93-129) and the MingTok config either inline (`mingtok_config`) or
+    in `models/MingTok-Vision/config.json` (the reference's hard-wired relative path, :102); weights from every
+    `*.safetensors` shard (reference key schema)."""
+    from safetensors.torch import load_file
+
+    with open(os.path.join(model_dir, "config.json")) as f:
+        cfg = json.load(f)
+    tok_cfg = cfg.get("mingtok_config")
+    if tok_cfg is None:
+        with open(os.path.join(model_dir, "models", "MingTok-Vision", "config.json")) as f:
+            tok_cfg = json.load(f)
+    llm_cfg = {k: v for k, v in cfg["llm_config"].items() if k not in ("architectures", "model_type", "torch_dtype",
+                                                                       "transformers_version", "auto_map")}
+    llm_cfg["rope_scaling"] = None  # the path uses the 1-D legacy rotary
+    with torch.device(device):
+        model = MingUniVisionForConditionalGeneration(BailingMoeConfig(**llm_cfg), MingTokConfig(**tok_cfg),
+                                                      cfg["vishead_diffloss_config"])
+    sd = {}
+    for shard in sorted(glob.glob(os.path.join(model_dir, "*.safetensors"))):
+        sd.update(load_file(shard, device=str(device)))
+    tok_dir = os.path.join(model_dir, "models", "MingTok-Vision")
+    for shard in sorted(glob.glob(os.path.join(tok_dir, "*.safetensors"))):
+        sd.update({"vision." + k: v for k, v in load_file(shard, device=str(device)).items()})
+    # only the three sub-trees of the continuous-visual-token path (audio encoder / talker weights of an omni checkpoint
+    # are ignored); the reference-only rotary buffers are derived from rope_theta here
+    sd = {k: v for k, v in sd.items()
+          if k.split(".")[0] in ("model", "vision", "linear_proj") and not k.endswith("rotary_emb.inv_freq")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    if missing or unexpected:
+        raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")
+    return model.to(torch.bfloat16)
+
+
+class MingUniVisionInfer:
+    def __init__(self, model_name_or_path, dtype="bf16", *, model=None, processor=None, tokenizer=None,
+                 reference_dir="./mingunivision"):
+        if dtype != "bf16":
+            raise NotImplementedError("int4 / int8 loading (bitsandbytes / quanto) is outside the B200-native path")
+        self.model_name_or_path = model_name_or_path
+        self.dtype = dtype
+        if processor is None or tokenizer is None:
+            tokenizer, processor = self._load_reference_processor(reference_dir)
+        self.tokenizer, self.processor = tokenizer, processor
+        self.model = model if model is not None else load_checkpoint(model_name_or_path)
+        self.model.tokenizer = self.tokenizer
+        self.model.model.tokenizer = self.tokenizer
+
+    @staticmethod
+    def _load_reference_processor(reference_dir: str):
+        """The reference's own CPU pre/post-processing (mingunivisioninfer.py:43-44), imported from its checkout."""
+        ref = os.path.abspath(reference_dir)
+        if not os.path.isdir(ref):
+            raise RuntimeError(f"{ref}: the reference's processor / tokenizer files are needed for the chat template "
+                               "(pass processor= and tokenizer= to inject your own)")
+        if ref not in sys.path:
+            sys.path.insert(0, ref)
+        from transformers import AutoProcessor, AutoTokenizer
+
+        return (AutoTokenizer.from_pretrained(ref, trust_remote_code=True),
+                AutoProcessor.from_pretrained(ref, trust_remote_code=True))
+
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    @torch.no_grad()
+    def generate(self, messages, max_new_tokens=512, output_image_prefix="output", for_edit=False):
+        """mingunivisioninfer.py:82-117, call for call."""
+        text = self.processor.apply_chat_template(messages, tokenize=False, add_generation_prompt=True, use_system=True)
+        image_inputs, _, _ = self.processor.process_vision_info(messages)
+        inputs = self.processor(text=[text], images=image_inputs, return_tensors="pt",
+                                image_patch_size=self.model.vision.patch_size, for_edit=for_edit).to(self.device)
+        kw = dict(inputs)
+        if kw.get("pixel_values") is not None:
+            kw["pixel_values"] = kw["pixel_values"].to(dtype=torch.bfloat16)
+        generated_ids = self.model.generate(**kw, max_new_tokens=max_new_tokens, use_cache=True,
+                                            output_image_prefix=output_image_prefix)
+        trimmed = [out_ids[len(in_ids):] for in_ids, out_ids in zip(inputs["input_ids"], generated_ids)]
+        return self.processor.batch_decode(trimmed, skip_special_tokens=True, clean_up_tokenization_spaces=False)[0]
+
+    def reset_inner_state(self):
+        self.model.reset_inner_state()

@@ -374,7 +374,8 @@ class BailingMoeModel(nn.Module):
         """BailingMoeModel.forward (:1391-1540) for this path's two regimes.
         inputs_embeds [B, S, D]; position_ids int [B, S]; the S new tokens are appended at cache slots seq_len..;
         S == 1: cached decode of B rows, `key_mask` int32 [B, >= seq_len+1] marks attendable slots (2-D padding mask of
-        the CFG rows); S > 1: causal prefill into an empty cache (all-ones mask).  Returns final-norm hidden [B, S, D].
+        the CFG rows); S > 1: causal prefill behind whatever the cache already holds (all-ones mask; the first round
+        starts from an empty cache, later rounds append their prompt).  Returns final-norm hidden [B, S, D].
         With `t_dev` (device int32 scalar = current cache length, S must be 1) the call has fixed shapes and reads the
         position from device memory, so it can be captured in a CUDA graph; the caller advances cache.seq_len."""
         pk = self._pack()
@@ -387,8 +388,9 @@ class BailingMoeModel(nn.Module):
         t0 = 0 if graph_mode else cache.seq_len
         if not graph_mode and t0 + S > cache.max_len:
             raise ValueError(f"KV cache overflow: {t0}+{S} > {cache.max_len}")
-        if S > 1 and (t0 != 0 or (key_mask is not None and bool((key_mask[:, :S] == 0).any()))):
-            raise NotImplementedError("multi-token forward is implemented for a causal prefill into an empty cache")
+        if S > 1 and key_mask is not None and bool((key_mask[:, :t0 + S] == 0).any()):
+            raise NotImplementedError("multi-token forward needs an all-ones key mask (causal prefill; a later round's "
+                                      "prompt appended behind the cached context)")
         h = inputs_embeds.to(BF16).reshape(B * S, D).contiguous().clone()
         pos = position_ids.reshape(-1).to(torch.int32).contiguous()
         eps = cfg.rms_norm_eps
@@ -403,7 +405,7 @@ class BailingMoeModel(nn.Module):
             if S == 1:
                 a = ops.attn_decode_gqa(q, cache.k[li], cache.v[li], key_mask, H, t0 + 1, t_dev)
             else:
-                a = ops.attn_prefill_gqa(q, cache.k[li], cache.v[li], B, S, H)
+                a = ops.attn_prefill_gqa(q, cache.k[li], cache.v[li], B, S, H, t0)
             _dense(a, lp["dense_w"], lp["dense_b"], epi=ops.EPI_RESIDUAL, residual=h, out=h)
             x = ops.rmsnorm(h, lp["ln2"], eps)
             h, _, _ = lyr.mlp._run(x, h, im)
@@ -438,6 +440,13 @@ class BailingMoeForCausalLM(nn.Module):
         self._gen_ws = {}
         self._txt_ws = {}
         return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts the reference's checkpoints unchanged: its per-layer `rotary_emb.inv_freq` buffers
+        (BailingMoeRotaryEmbeddingLegacy, modeling_bailing_moe.py:213-237) are derived from `rope_theta` here (the RoPE
+        kernel recomputes them), so those keys are dropped instead of being reported as unexpected."""
+        sd = {k: v for k, v in state_dict.items() if not k.endswith("rotary_emb.inv_freq")}
+        return super().load_state_dict(sd, strict=strict, **kw)
 
     def setup_vishead_diffloss(self, diffloss_w=3072, diffloss_d=12, num_sampling_steps="16",
                                gen_method="flow_matching_swiglu-4", hidden_size=2048, vis_head_arch="linear2-norm",

@@ -1,12 +1,14 @@
 """B200-native multimodal wrapper: the continuous-visual-token surface of the reference's
 ``mingunivision/modeling_bailingmm.py`` (MingUniVisionForConditionalGeneration :85-308) — `vision` (MingTok), `model`
 (BailingMoeForCausalLM with vis_head + diffloss), `linear_proj`, `extract_image_feature`, `prompt_wrap_vision`,
-`reset_inner_state`, and the image-generation entry that the reference reaches through HF `generate`
-(forward :1769-1796 -> generate_image).  HF GenerationMixin text decoding is glue outside SURVEY.md §8(a)-(e) (row f.1);
-`generate_image_from_prompt` drives prefill + generate_image directly, as SURVEY.md §7 recommends.
+`reset_inner_state`, and `generate` with its multi-round state (KV cache + three attention masks carried across calls,
+:206-301).  HF GenerationMixin is not used (its transformers-5 internals no longer match the reference's 4.52 code,
+SURVEY.md §7): `generate` runs prefill, CUDA-graphed greedy decoding and — when the model emits `<image>` —
+`generate_image` itself; `generate_text` / `generate_image_from_prompt` are the single-purpose entries.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -63,6 +65,9 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         self.model.setup_vishead_diffloss(**vh)
         self.past_key_values = None
         self.past_attention_mask = None
+        self.past_text_uncond_attention_mask = None
+        self.past_uncond_attention_mask = None
+        self.generated_images = []
         for p in self.parameters():
             p.requires_grad_(False)
 
@@ -70,6 +75,8 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         """modeling_bailingmm.py:303-308."""
         self.past_key_values = None
         self.past_attention_mask = None
+        self.past_text_uncond_attention_mask = None
+        self.past_uncond_attention_mask = None
         self.model.reset_image_gen_status()
 
     @torch.no_grad()
@@ -94,6 +101,107 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         out = inputs_embeds.clone()
         out[image_mask] = vision_embeds.to(out.dtype)
         return out, image_mask
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask=None, uncond_attention_mask=None, text_uncond_attention_mask=None,
+                 pixel_values=None, image_grid_thw=None, max_new_tokens: int = 512, eos_token_id=None,
+                 output_image_prefix=None, image_gen_temperature=1.0, image_gen_text_cfg=3.0, image_gen_image_cfg=1.1,
+                 max_cache_len: int = 4096, **generate_kwargs):
+        """MingUniVisionForConditionalGeneration.generate (modeling_bailingmm.py:206-301) with its multi-round state:
+        the KV cache and the three attention masks persist across calls (`reset_inner_state()` clears them), so a later
+        call only prefills ITS prompt behind the cached context (in-context editing, test_infer_unified.py:30-56).
+
+        One call = what HF GenerationMixin.generate does with do_sample = false on this model: prefill, then greedy
+        tokens; when the model emits the `<image>` start token the next step is `generate_image` (256 visual tokens through
+        the LLM + RF head + semantic decoder with CFG rows built from `uncond_attention_mask` /
+        `text_uncond_attention_mask`, modeling_bailing_moe.py:1769-1796), after which text decoding resumes from the
+        cond row's last hidden state; stops at `eos_token_id` or after `max_new_tokens` text tokens.  Returns the full
+        token sequence [1, prompt + new]; generated images are collected in `self.generated_images` (and written to
+        `{output_image_prefix}[_{i}].png` when a prefix is given, as the reference does from inside forward()).
+        As in the reference, the CFG scales never reach the sampler (kwargs bug)."""
+        llm, cfg = self.model, self.model.config
+        dev = input_ids.device
+        if input_ids.shape[0] != 1:
+            raise ValueError("generation runs on one sequence (the reference asserts batch 1, modeling_bailing_moe.py:1865)")
+        eos = cfg.pad_token_id if eos_token_id is None else eos_token_id
+        S = input_ids.shape[1]
+        ones = lambda n: torch.ones((1, n), dtype=torch.int32, device=dev)  # noqa: E731
+        attention_mask = ones(S) if attention_mask is None else attention_mask.to(dev, torch.int32)
+        uncond_attention_mask = torch.zeros_like(attention_mask) if uncond_attention_mask is None \
+            else uncond_attention_mask.to(dev, torch.int32)
+        text_uncond_attention_mask = torch.zeros_like(attention_mask) if text_uncond_attention_mask is None \
+            else text_uncond_attention_mask.to(dev, torch.int32)
+        if self.past_attention_mask is not None:  # :229-234
+            attention_mask = torch.cat((self.past_attention_mask, attention_mask), dim=1)
+            uncond_attention_mask = torch.cat((self.past_uncond_attention_mask, uncond_attention_mask), dim=1)
+            text_uncond_attention_mask = torch.cat((self.past_text_uncond_attention_mask, text_uncond_attention_mask), dim=1)
+        cache = self.past_key_values
+        if cache is None:
+            need = S + max_new_tokens + 2 * (cfg.num_image_tokens_for_gen + 1) + 8
+            cache = llm.new_cache(max_len=max(need, max_cache_len))
+            cache.seq_len, cache.batch = 0, 1
+            llm._gen_ws, llm._txt_ws = {}, {}
+        t0 = cache.seq_len
+        if attention_mask.shape[1] != t0 + S:
+            raise ValueError(f"attention mask length {attention_mask.shape[1]} != cached context {t0} + prompt {S}")
+        if bool((attention_mask == 0).any()):
+            raise NotImplementedError("the cond row's attention mask is all ones on this path (left padding is not used)")
+        emb = llm.model.embed(input_ids.clamp(0, cfg.vocab_size - 1))
+        image_mask = None
+        if pixel_values is not None and S > 1:
+            emb, image_mask = self.prompt_wrap_vision(input_ids, emb, self.extract_image_feature(pixel_values, image_grid_thw))
+        pos = torch.arange(t0, t0 + S, device=dev, dtype=torch.int32).unsqueeze(0)
+        hidden = llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
+        last = hidden[:, -1]
+        new_ids: list = []
+        self.generated_images = []
+        budget = max_new_tokens
+        while budget > 0:
+            out = llm.greedy_decode(last, cache, budget, stop_ids=(eos, cfg.image_start_token))
+            new_ids += out
+            budget -= len(out)
+            if not out or out[-1] != cfg.image_start_token:
+                break
+            # the model asked for an image: `<image>` is the first input of generate_image (:1769-1796)
+            am = ones(cache.seq_len + 1)
+            start = llm.model.embed(torch.tensor([[cfg.image_start_token]], device=dev))
+            img, hid, _ = llm.generate_image(
+                input_embeds=start, past_key_values=cache, attention_mask=am,
+                uncond_attention_mask=uncond_attention_mask, text_uncond_attention_mask=text_uncond_attention_mask,
+                latent_to_sem_func=self.vision.forward_feature_decoder, linear_proj=self.linear_proj,
+                sem_to_pix_func=self.vision.forward_pixel_decoder, image_gen_text_cfg=image_gen_text_cfg,
+                image_gen_image_cfg=image_gen_image_cfg, image_gen_temperature=image_gen_temperature)
+            self.generated_images.append(img[0:1])
+            llm.num_generated_images += 1
+            if output_image_prefix is not None:
+                self._save_image(img[0], output_image_prefix, len(self.generated_images) - 1)
+            last = hid[0:1, -1]  # cond row: its logits choose the token after the image (:1783-1787)
+        # ---- state for the next round (:272-299)
+        self.past_key_values = cache
+        pad_n = cache.seq_len - attention_mask.shape[1]
+        pad1 = ones(pad_n)
+        pad0 = torch.zeros((1, pad_n), dtype=torch.int32, device=dev)
+        past_mode = os.environ.get("PAST_MODE", "DROP")
+        if past_mode == "KEEP":
+            self.past_attention_mask = torch.cat((attention_mask, pad1), dim=1)
+            self.past_text_uncond_attention_mask = torch.cat((text_uncond_attention_mask, pad1), dim=1)
+            self.past_uncond_attention_mask = torch.cat((uncond_attention_mask, pad0), dim=1)
+        elif past_mode == "DROP":
+            self.past_attention_mask = torch.cat((attention_mask, pad1), dim=1)
+            self.past_text_uncond_attention_mask = torch.cat((attention_mask, pad1), dim=1)
+            self.past_uncond_attention_mask = torch.cat((attention_mask, pad0), dim=1)
+        else:
+            raise ValueError("PAST_MODE must be KEEP or DROP")
+        llm.reset_image_gen_status()
+        return torch.cat((input_ids, torch.tensor([new_ids], dtype=input_ids.dtype, device=dev)), dim=1)
+
+    @staticmethod
+    def _save_image(img: torch.Tensor, prefix: str, index: int) -> None:
+        """[-1, 1] CHW tensor -> `{prefix}.png` / `{prefix}_{i}.png` (modeling_bailing_moe.py:1788-1796)."""
+        from PIL import Image
+
+        arr = ((img.float().clamp(-1, 1) + 1) * 127.5).round().to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        Image.fromarray(arr).save(f"{prefix}.png" if index == 0 else f"{prefix}_{index}.png")
 
     @torch.no_grad()
     def generate_image_from_prompt(self, input_ids, pixel_values=None, uncond_attention_mask=None,

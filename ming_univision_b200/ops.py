@@ -467,15 +467,17 @@ def attn_decode_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor,
     return out
 
 
-def attn_prefill_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, B: int, S: int, H: int) -> torch.Tensor:
-    """Causal GQA attention of S new tokens (already appended at slots 0..S-1) for head_dim 64/128: q [B*S, H*hd]."""
+def attn_prefill_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, B: int, S: int, H: int,
+                     t0: int = 0) -> torch.Tensor:
+    """Causal GQA attention of S new tokens, already appended at cache slots t0..t0+S-1, over keys 0..t0+S-1 (bottom-right
+    aligned causal mask: a later round's prompt sees the whole earlier context) for head_dim 64/128: q [B*S, H*hd]."""
     _check_bf16(q, kcache, vcache)
     lib = _lib.load()
     _, Hkv, Tmax, hd = kcache.shape
     out = torch.empty((B * S, H * hd), dtype=BF16, device=q.device)
     rc = lib.mb_attn_fwd(q.data_ptr(), S * H * hd, H * hd, hd, kcache.data_ptr(), Hkv * Tmax * hd, hd, Tmax * hd,
                          vcache.data_ptr(), Hkv * Tmax * hd, hd, Tmax * hd, out.data_ptr(), S * H * hd, H * hd, hd,
-                         B, S, S, H, Hkv, hd, hd ** -0.5, 1, _stream())
+                         B, S, t0 + S, H, Hkv, hd, hd ** -0.5, 1, _stream())
     _lib.check(rc, "mb_attn_fwd")
     return out
 

@@ -102,3 +102,63 @@ def test_rf_state_dict_schema_live():
                     str(cfg["num_sampling_steps"]), mlp_mult=cfg["mlp_mult"])
     rsd = ref.state_dict()
     assert set(rsd) == set(shapes) and all(tuple(rsd[k].shape) == tuple(shapes[k]) for k in shapes)
+
+
+def test_llm_state_dict_schema_live():
+    """BailingMoeForCausalLM (+ vis_head + diffloss) keys / shapes == the reference module's == the synthetic factory's."""
+    from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig, BailingMoeForCausalLM
+    from oracle import ref_shims
+
+    cfg, vh = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG
+    m = BailingMoeForCausalLM(BailingMoeConfig(**cfg))
+    m.setup_vishead_diffloss(**vh)
+    shapes = synthetic.llm_param_shapes(cfg, vh)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes), (sorted(set(sd) ^ set(shapes))[:6])
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    if not ref_shims.reference_available():
+        return
+    ref, _ = ref_shims.build_reference_llm(cfg, vh)
+    rsd = ref.state_dict()
+    # the reference also stores the rotary inv_freq buffers; ours are derived from rope_theta and dropped on load
+    extra = {k for k in rsd if k.endswith("rotary_emb.inv_freq")}
+    assert set(rsd) - extra == set(shapes), (sorted((set(rsd) - extra) ^ set(shapes))[:6])
+    assert all(tuple(rsd[k].shape) == tuple(shapes[k]) for k in shapes)
+    res = m.load_state_dict(rsd, strict=True)  # a reference checkpoint loads unchanged
+    assert not res.missing_keys and not res.unexpected_keys
+
+
+def test_load_checkpoint_hf_layout(tmp_path):
+    """mingunivisioninfer.load_checkpoint: config.json + *.safetensors in the reference's HF layout (LLM + vis_head +
+    diffloss + linear_proj shards at the top level, MingTok under models/MingTok-Vision) -> the wrapper module, with the
+    reference-only buffers (rotary inv_freq) ignored.  Synthetic tiny checkpoint (no pretrained weights exist offline)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from ming_univision_b200.mingunivisioninfer import load_checkpoint
+
+    cfg, vh, tok = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG, synthetic.MINGTOK_TINY_CONFIG
+    llm_sd = synthetic.llm_state_dict(cfg, vh, tok["semantic_decoder"]["embed_dim"], 0)
+    top = {(k if k.startswith("linear_proj.") else "model." + k): v.contiguous() for k, v in llm_sd.items()}
+    top["model.model.layers.0.attention.rotary_emb.inv_freq"] = torch.ones(4)
+    keys = sorted(top)
+    save_file({k: top[k] for k in keys[: len(keys) // 2]}, str(tmp_path / "model-00001-of-00002.safetensors"))
+    save_file({k: top[k] for k in keys[len(keys) // 2:]}, str(tmp_path / "model-00002-of-00002.safetensors"))
+    (tmp_path / "models" / "MingTok-Vision").mkdir(parents=True)
+    save_file({k: v.contiguous() for k, v in synthetic.mingtok_state_dict(tok, 0).items()},
+              str(tmp_path / "models" / "MingTok-Vision" / "model.safetensors"))
+    with open(tmp_path / "models" / "MingTok-Vision" / "config.json", "w") as f:
+        json.dump(tok, f)
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump({"llm_config": dict(cfg, architectures=["BailingMoeForCausalLM"], torch_dtype="bfloat16"),
+                   "vishead_diffloss_config": vh}, f)
+    m = load_checkpoint(str(tmp_path), device="cpu")
+    sd = m.state_dict()
+    assert sd["model.lm_head.weight"].dtype == torch.bfloat16
+    for k, v in top.items():
+        if k.endswith("inv_freq"):
+            continue
+        assert torch.equal(sd[k].float(), v.to(torch.bfloat16).float()), k
+    assert torch.equal(sd["vision.sem_to_pix.weight"].float(),
+                       synthetic.mingtok_state_dict(tok, 0)["sem_to_pix.weight"].to(torch.bfloat16).float())

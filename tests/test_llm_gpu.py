@@ -398,3 +398,130 @@ def test_greedy_text_decode_graph_equals_eager(tiny_model, cuda_device):
     stop = a[2]
     c = tiny_model.generate_text(ids2, max_new_tokens=5, eos_token_id=stop)
     assert c == a[:a.index(stop) + 1]
+
+
+def test_generate_multi_round_state(tiny_model, cuda_device, monkeypatch):
+    """MingUniVisionForConditionalGeneration.generate across rounds (modeling_bailingmm.py:206-301): the second call only
+    prefills its own prompt behind the cached context, and must continue exactly like a fresh model that is given the
+    whole conversation at once; the three masks follow the reference's PAST_MODE=DROP bookkeeping."""
+    cfg = synthetic.LLM_TINY_CONFIG
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids1 = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    ids2 = torch.flip(ids1, dims=[1])[:, :9].contiguous()
+    m = tiny_model
+    m.reset_inner_state()
+    monkeypatch.delenv("PAST_MODE", raising=False)
+    S1, S2 = ids1.shape[1], ids2.shape[1]
+    un1 = torch.zeros((1, S1), dtype=torch.int32, device=cuda_device)
+    seq1 = m.generate(ids1, uncond_attention_mask=un1, text_uncond_attention_mask=un1.clone(), max_new_tokens=5,
+                      eos_token_id=-1)
+    assert seq1.shape == (1, S1 + 5) and torch.equal(seq1[:, :S1], ids1)
+    L1 = S1 + 5 - 1  # the last emitted token is not part of the cached context (HF generate semantics)
+    assert m.past_key_values.seq_len == L1
+    assert m.past_attention_mask.shape == (1, L1) and bool((m.past_attention_mask == 1).all())
+    assert torch.equal(m.past_text_uncond_attention_mask, m.past_attention_mask)           # DROP: copies of the cond mask
+    assert bool((m.past_uncond_attention_mask[:, :S1] == 1).all()) and bool((m.past_uncond_attention_mask[:, S1:] == 0).all())
+    # the second round's prompt, prefilled behind the cached context, must see exactly what a fresh model sees when it is
+    # given the whole conversation at once (hidden states compared: greedy tokens of a random tiny model sit on near-ties)
+    llm = m.model
+    cache = m.past_key_values
+    pos2 = torch.arange(L1, L1 + S2, device=cuda_device, dtype=torch.int32).unsqueeze(0)
+    h_inc = llm.model.forward_tokens(llm.model.embed(ids2), pos2, cache, key_mask=None).float().cpu()
+    full = torch.cat((seq1[:, :-1], ids2), dim=1)
+    fresh = llm.new_cache(max_len=256, max_batch=1)
+    posf = torch.arange(full.shape[1], device=cuda_device, dtype=torch.int32).unsqueeze(0)
+    h_full = llm.model.forward_tokens(llm.model.embed(full), posf, fresh, key_mask=None).float().cpu()
+    assert rel_l2(h_inc, h_full[:, -S2:]) < 2e-2
+    cache.seq_len = L1  # undo the probe, then run the real second round
+    un2 = torch.zeros((1, S2), dtype=torch.int32, device=cuda_device)
+    seq2 = m.generate(ids2, uncond_attention_mask=un2, text_uncond_attention_mask=un2.clone(), max_new_tokens=4,
+                      eos_token_id=-1)
+    assert seq2.shape == (1, S2 + 4) and m.past_key_values is cache
+    assert cache.seq_len == L1 + S2 + 4 - 1 == m.past_attention_mask.shape[1]
+    assert bool((m.past_uncond_attention_mask[:, L1 + S2:] == 0).all())
+    assert bool((m.past_uncond_attention_mask[:, L1:L1 + S2] == 1).all())  # DROP: the cond mask replaces the uncond one
+    m.reset_inner_state()
+    assert m.past_key_values is None and m.past_attention_mask is None
+
+
+def test_generate_emits_image_then_resumes_text(tiny_model, cuda_device, monkeypatch):
+    """When greedy decoding emits the `<image>` start token, `generate` runs generate_image (CFG rows from the uncond
+    masks), collects the image, and resumes text decoding from the cond row; the cache and masks grow by the 256 + 1
+    visual positions.  (The token stream is scripted: random weights never emit `<image>` on their own.)"""
+    cfg = synthetic.LLM_TINY_CONFIG
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"]).to(cuda_device)
+    m = tiny_model
+    llm = m.model
+    m.reset_inner_state()
+    n_tok = llm.config.num_image_tokens_for_gen
+    real = llm.greedy_decode
+    calls = []
+
+    def scripted(last, cache, max_new_tokens, stop_ids=()):
+        calls.append(cache.seq_len)
+        if len(calls) == 1:
+            out = real(last, cache, 3, stop_ids=())             # two ordinary tokens are fed back ...
+            out[-1] = llm.config.image_start_token              # ... and the third choice "asks" for an image
+            return out                                          # (the last emitted token is never fed: contract kept)
+        return real(last, cache, min(3, max_new_tokens), stop_ids=())
+
+    monkeypatch.setattr(llm, "greedy_decode", scripted)
+    S = ids.shape[1]
+    un = torch.zeros((1, S), dtype=torch.int32, device=cuda_device)
+    un[:, :2] = 1
+    seq = m.generate(ids, uncond_attention_mask=un, text_uncond_attention_mask=torch.zeros_like(un), max_new_tokens=16,
+                     eos_token_id=-1)
+    new = seq[0, S:].tolist()
+    assert new[2] == llm.config.image_start_token and len(new) == 3 + 3
+    assert len(m.generated_images) == 1 and m.generated_images[0].shape[0] == 1 and m.generated_images[0].shape[1] == 3
+    assert torch.isfinite(m.generated_images[0].float()).all()
+    # call 1 fed 2 text tokens; the image step fed `<image>` + n_tok visual tokens
+    assert calls[0] == S and calls[1] == S + 2 + (n_tok + 1)
+    assert m.past_key_values.seq_len == m.past_attention_mask.shape[1] == m.past_uncond_attention_mask.shape[1]
+    assert int(m.past_uncond_attention_mask[0, S:].sum()) == 0
+    m.reset_inner_state()
+
+
+def test_infer_facade_calls_like_the_reference(tiny_model, cuda_device):
+    """MingUniVisionInfer.generate (mingunivisioninfer.py:82-117) with an injected stand-in processor / tokenizer: chat
+    template -> vision info -> processor -> model.generate(**inputs) -> trim the prompt -> batch_decode."""
+    from ming_univision_b200.mingunivisioninfer import MingUniVisionInfer
+
+    g = np.load(os.path.join(GOLD, "llm_tiny.npz"))
+    ids = torch.from_numpy(g["prefill_ids"])
+    log = []
+
+    class Inputs(dict):
+        def to(self, device):
+            return Inputs({k: (v.to(device) if torch.is_tensor(v) else v) for k, v in self.items()})
+
+    class Proc:
+        def apply_chat_template(self, messages, tokenize, add_generation_prompt, use_system):
+            log.append(("template", add_generation_prompt, use_system))
+            return "<role>HUMAN</role>" + messages[0]["content"][0]["text"] + "<role>ASSISTANT</role>"
+
+        def process_vision_info(self, messages):
+            return None, None, None
+
+        def __call__(self, text, images, return_tensors, image_patch_size, for_edit):
+            log.append(("call", image_patch_size, for_edit, text[0]))
+            n = ids.shape[1]
+            return Inputs(input_ids=ids.clone(), attention_mask=torch.ones((1, n), dtype=torch.int64),
+                          uncond_attention_mask=torch.zeros((1, n), dtype=torch.int64),
+                          text_uncond_attention_mask=torch.zeros((1, n), dtype=torch.int64))
+
+        def batch_decode(self, seqs, skip_special_tokens, clean_up_tokenization_spaces):
+            log.append(("decode", [len(s_) for s_ in seqs]))
+            return [" ".join(str(int(t)) for t in seqs[0])]
+
+    tiny_model.reset_inner_state()
+    infer = MingUniVisionInfer("unused", model=tiny_model, processor=Proc(), tokenizer=object())
+    out = infer.generate([{"role": "HUMAN", "content": [{"type": "text", "text": "hi"}]}], max_new_tokens=4)
+    assert log[0] == ("template", True, True) and log[1][:3] == ("call", tiny_model.vision.patch_size, False)
+    assert log[2] == ("decode", [4]) and len(out.split()) == 4
+    assert tiny_model.past_key_values.seq_len == ids.shape[1] + 3 and tiny_model.tokenizer is infer.tokenizer
+    infer.reset_inner_state()
+    assert tiny_model.past_key_values is None
+    with pytest.raises(NotImplementedError):
+        MingUniVisionInfer("unused", dtype="int4", model=tiny_model, processor=Proc(), tokenizer=object())

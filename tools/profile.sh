@@ -11,3 +11,7 @@ MB_NCU_RANGE=1 timeout 600 ncu --profile-from-start off --metrics gpu__time_dura
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 147 -c 4 \
     -o gpurun_out/prof_gemm_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/ | tail -8
+# tcgen05 attention kernel: one pixel-decoder launch (12 encoder + 24 semantic-decoder launches come first in a pass)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 40 -c 1 \
+    -o gpurun_out/prof_attn_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_attn_${TAG}.log 2>&1
+ls -la gpurun_out/ | tail -4
