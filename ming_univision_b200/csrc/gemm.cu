@@ -63,18 +63,28 @@ struct GemmParams {
                               //      the expert's [gate; up] slab, so the SwiGLU epilogue needs no interleaved repack
 };
 
-template <int BN, int CG>
+template <int BN, int CG, int EPI>
 struct GemmCfg {
   static constexpr int kABytes = kBM * kBK * 2;           // this CTA's 128 rows of A
   static constexpr int kBRows = BN / CG;                  // this CTA's share of the W tile
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiStageBytes = kNumEpiWarps * 4096;  // one 32-row x 64-col bf16 box per epilogue warp
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  // epilogue staging: one 32-row x 64-col bf16 box (4 KB) per epilogue warp; the RESIDUAL epilogue keeps one box per
+  // 64-column slice of the warp's share so that every residual box of a tile is requested by TMA before the tile's
+  // accumulator is even complete (the load latency hides behind the main loop instead of in front of the math)
+  static constexpr int kOutTileN = (EPI == MB_EPI_SWIGLU) ? BN / 2 : BN;
+  static constexpr int kBoxesPerWarp = kOutTileN / 2 / 64;
+  static constexpr int kEpiBufs = (EPI == MB_EPI_RESIDUAL) ? kBoxesPerWarp : 1;
+  static constexpr int kEpiStageBytes = kNumEpiWarps * kEpiBufs * 4096;
+  static constexpr int kAuxBytes = 2 * BN * 4;            // per-column fp32 vectors of the current tile (bias, csum)
+  static constexpr int kBarBytes = 512;
+  static constexpr int kStages = ((232448 - kEpiStageBytes - kAuxBytes - kBarBytes) / kStageBytes) > 8
+                                     ? 8 : ((232448 - kEpiStageBytes - kAuxBytes - kBarBytes) / kStageBytes);
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + kAuxBytes + kBarBytes;
   static constexpr int kTileM = kBM * CG;
-  static_assert(kSmemBytes <= 232448, "shared memory budget");
+  static_assert(kSmemBytes <= 232448 && kStages >= 3, "shared memory budget");
+  static_assert((2 * kStages + 4 + kNumEpiWarps * 2) * 8 + 8 <= kBarBytes, "barrier area");
 };
 
 // Converts 32 fp32 values (one row segment) to bf16 and stores them; handles the N tail.
@@ -97,38 +107,20 @@ __device__ __forceinline__ void store_row_segment(__nv_bfloat16* dst, const floa
   }
 }
 
-__device__ __forceinline__ void load_bias32(const __nv_bfloat16* bias, int col0, int ncols_valid, float (&b)[32]) {
-  if (bias == nullptr) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = 0.f;
-    return;
-  }
-  if (ncols_valid >= 32) {
-    const uint4* p = reinterpret_cast<const uint4*>(bias + col0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 q = __ldg(p + i);
-      float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-      b[8 * i + 0] = f0.x; b[8 * i + 1] = f0.y; b[8 * i + 2] = f1.x; b[8 * i + 3] = f1.y;
-      b[8 * i + 4] = f2.x; b[8 * i + 5] = f2.y; b[8 * i + 6] = f3.x; b[8 * i + 7] = f3.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) b[i] = (i < ncols_valid) ? __bfloat162float(bias[col0 + i]) : 0.f;
-  }
-}
-
 // Accumulator chunk (this warp's 32 rows x 32 columns starting at tile column tc) -> bias / activation, fp32 in v[].
-// For MB_EPI_RESIDUAL the residual is added by the caller (it arrives either by TMA or by direct loads).
-// acc[i] -> rstd * (acc[i] - mean * csum[col + i]) + bias_f32[col + i]   (LayerNorm folded into the GEMM)
-__device__ __forceinline__ void ln_fold32(const GemmParams& p, int col, int ncols_valid, float mean, float rstd,
-                                          const uint32_t (&a)[32], float (&v)[32]) {
-  if (ncols_valid >= 32) {
-    const float4* cs = reinterpret_cast<const float4*>(p.ln_csum + col);
-    const float4* bs = reinterpret_cast<const float4*>(p.ln_bias + col);
+// The per-column vectors of the tile live in shared memory (aux_b: bias or the folded LayerNorm bias, aux_c: column
+// sums of the gamma-scaled weight), staged before the accumulator wait, zero past the matrix edge; every lane reads the
+// same addresses (broadcast LDS.128), so they cost no global-memory latency inside the epilogue.
+//   plain:  v = acc + aux_b[col]            LayerNorm fold:  v = rstd * (acc - mean * aux_c[col]) + aux_b[col]
+// For MB_EPI_RESIDUAL the residual is added by the caller.
+__device__ __forceinline__ void col_affine32(const float* aux_b, const float* aux_c, bool fold, int tcol, float mean,
+                                             float rstd, const uint32_t (&a)[32], float (&v)[32]) {
+  const float4* bs = reinterpret_cast<const float4*>(aux_b + tcol);
+  if (fold) {
+    const float4* cs = reinterpret_cast<const float4*>(aux_c + tcol);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 c = __ldg(cs + i), b = __ldg(bs + i);
+      const float4 c = cs[i], b = bs[i];
       v[4 * i + 0] = fmaf(rstd, __uint_as_float(a[4 * i + 0]) - mean * c.x, b.x);
       v[4 * i + 1] = fmaf(rstd, __uint_as_float(a[4 * i + 1]) - mean * c.y, b.y);
       v[4 * i + 2] = fmaf(rstd, __uint_as_float(a[4 * i + 2]) - mean * c.z, b.z);
@@ -136,51 +128,34 @@ __device__ __forceinline__ void ln_fold32(const GemmParams& p, int col, int ncol
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      v[i] = (i < ncols_valid) ? fmaf(rstd, __uint_as_float(a[i]) - mean * p.ln_csum[col + i], p.ln_bias[col + i]) : 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = bs[i];
+      v[4 * i + 0] = __uint_as_float(a[4 * i + 0]) + b.x;
+      v[4 * i + 1] = __uint_as_float(a[4 * i + 1]) + b.y;
+      v[4 * i + 2] = __uint_as_float(a[4 * i + 2]) + b.z;
+      v[4 * i + 3] = __uint_as_float(a[4 * i + 3]) + b.w;
+    }
   }
 }
 
 template <int BN, int EPI>
-__device__ __forceinline__ void epi_math(const GemmParams& p, uint32_t t_row, int tc, int n_tile, int out_col,
-                                         int ncols_valid, float ln_mean, float ln_rstd, float (&v)[32]) {
+__device__ __forceinline__ void epi_math(uint32_t t_row, int tc, const float* aux_b, const float* aux_c, bool fold,
+                                         float ln_mean, float ln_rstd, float (&v)[32]) {
   if constexpr (EPI == MB_EPI_SWIGLU) {
     uint32_t g[32], u[32];
     tmem_ld_32x32b_x32(t_row + tc, g);
     tmem_ld_32x32b_x32(t_row + BN / 2 + tc, u);
     tmem_ld_wait();
-    if (p.ln_stats_in != nullptr) {
-      float x1[32];
-      ln_fold32(p, n_tile * BN + tc, 32, ln_mean, ln_rstd, g, x1);
-      ln_fold32(p, n_tile * BN + BN / 2 + tc, 32, ln_mean, ln_rstd, u, v);
+    float x1[32];
+    col_affine32(aux_b, aux_c, fold, tc, ln_mean, ln_rstd, g, x1);
+    col_affine32(aux_b, aux_c, fold, BN / 2 + tc, ln_mean, ln_rstd, u, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(x1[i]))) * bf16_round(v[i]);
-    } else {
-      {
-        float bg[32];
-        load_bias32(p.bias, n_tile * BN + tc, 32, bg);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(__uint_as_float(g[i]) + bg[i])));
-      }
-      {
-        float bu[32];
-        load_bias32(p.bias, n_tile * BN + BN / 2 + tc, 32, bu);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= bf16_round(__uint_as_float(u[i]) + bu[i]);
-      }
-    }
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(silu(bf16_round(x1[i]))) * bf16_round(v[i]);
   } else {
     uint32_t a[32];
     tmem_ld_32x32b_x32(t_row + tc, a);
     tmem_ld_wait();
-    if (p.ln_stats_in != nullptr) {
-      ln_fold32(p, out_col, ncols_valid, ln_mean, ln_rstd, a, v);
-    } else {
-      float b[32];
-      load_bias32(p.bias, out_col, ncols_valid, b);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(a[i]) + b[i];
-    }
+    col_affine32(aux_b, aux_c, fold, tc, ln_mean, ln_rstd, a, v);
     if constexpr (EPI == MB_EPI_GELU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {  // bf16(acc + bias) as the reference's Linear output, then GELU on packed pairs
@@ -196,7 +171,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const GemmParams p) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EPI>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kTileM = Cfg::kTileM;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -205,18 +180,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // (no static shared memory in this kernel: the base is 1 KB aligned)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;  // [kNumEpiWarps][32 rows][128 B], 128B-swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiStageBytes);
+  uint8_t* smem_epi = smem + kStages * Cfg::kStageBytes;  // [kNumEpiWarps][kEpiBufs][32 rows][128 B], 128B-swizzled
+  float* aux_b = reinterpret_cast<float*>(smem_epi + Cfg::kEpiStageBytes);  // [BN] bias / folded LayerNorm bias
+  float* aux_c = aux_b + BN;                                                // [BN] column sums (LayerNorm fold)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + Cfg::kEpiStageBytes + Cfg::kAuxBytes);
   uint64_t* full_bar = bars;                    // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;         // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;     // [2]        MMA -> epilogue
   uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
-  uint64_t* epi_bar = bars + 2 * kStages + 4;   // [kNumEpiWarps] residual box landed (TMA -> epilogue warp)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + kNumEpiWarps);
+  uint64_t* epi_bar = bars + 2 * kStages + 4;   // [kNumEpiWarps][2] residual box landed (TMA -> epilogue warp)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 2 * kNumEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -241,7 +217,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kNumEpiWarps * CG);  // CG = 2: the leader's barrier collects both CTAs' epilogues
     }
-    for (int w = 0; w < kNumEpiWarps; ++w) mbar_init(&epi_bar[w], 1);
+    for (int w = 0; w < 2 * kNumEpiWarps; ++w) mbar_init(&epi_bar[w], 1);
+    if ((smem_u32(smem) & 1023u) != 0) {
+      printf("gemm_bf16_kernel: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     if (p.tma_epi) {
       tma_prefetch_desc(&tmap_out);
       if (EPI == MB_EPI_RESIDUAL) tma_prefetch_desc(&tmap_res);
@@ -351,8 +331,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int ew = warp - 2;
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;           // which half of the tile's columns
-    constexpr int kOutTileN = (EPI == MB_EPI_SWIGLU) ? BN / 2 : BN;
+    constexpr int kOutTileN = Cfg::kOutTileN;
     constexpr int kColsPerWarp = kOutTileN / 2;
+    const bool fold = p.ln_stats_in != nullptr;
     const int n_out_total = grouped ? p.grp_n_out : ((EPI == MB_EPI_SWIGLU) ? p.N / 2 : p.N);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -365,6 +346,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int n_tile = tile % num_n_tiles;
       const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 64 && tcount < 16;
       if (stamp) p.dbg[tcount * 8 + 4] = clock64();
+      // ---- before the accumulator is complete (this overlaps the tile's main loop):
+      // (1) the per-column vectors of the tile go to shared memory; (2) RESIDUAL: every residual box of the tile is
+      // requested by TMA into its own staging box
+      const int row0 = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + quad * 32;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // every epilogue warp is done with the previous tile's vectors
+      {
+        const int e = static_cast<int>(threadIdx.x) - 64;
+        if (e < BN) {
+          const int col = n_tile * BN + e;
+          float bv = 0.f, cv = 0.f;
+          if (col < p.N) {
+            if (fold) {
+              bv = __ldg(p.ln_bias + col);
+              cv = __ldg(p.ln_csum + col);
+            } else if (p.bias != nullptr) {
+              bv = __bfloat162float(p.bias[col]);
+            }
+          }
+          aux_b[e] = bv;
+          aux_c[e] = cv;
+        }
+      }
+      if constexpr (EPI == MB_EPI_RESIDUAL) {
+        if (p.tma_epi && lane == 0) {
+          tma_store_wait_read<0>();  // the stores of the previous tile have read this warp's staging boxes
+#pragma unroll
+          for (int bx = 0; bx < Cfg::kBoxesPerWarp; ++bx) {
+            const int box_col = n_tile * kOutTileN + half * kColsPerWarp + bx * 64;
+            if (box_col < n_out_total && row0 < p.M) {
+              mbar_arrive_expect_tx(&epi_bar[ew * 2 + bx], 4096);
+              tma_load_2d(&tmap_res, &epi_bar[ew * 2 + bx], smem_epi + (ew * Cfg::kEpiBufs + bx) * 4096, box_col, row0);
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // vectors visible to all epilogue warps
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       if (stamp) p.dbg[tcount * 8 + 5] = clock64();
@@ -391,31 +408,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // ---- staged path: registers -> 128B-swizzled smem box (32 rows x 64 cols) -> one TMA store per box; the
         // residual box arrives by TMA as well.  Every global access of the epilogue is a full-line bulk transfer
         // (a thread-per-row register store touches 32 different lines per instruction and was the limiter at K<=1024).
-        uint8_t* stage_buf = smem_epi + ew * 4096;
-        const int row0 = m_tile * kTileM + static_cast<int>(cta_rank) * kBM + quad * 32;
 #pragma unroll 1
         for (int bx = 0; bx < kColsPerWarp / 64; ++bx) {
+          uint8_t* stage_buf = smem_epi + (ew * Cfg::kEpiBufs + (Cfg::kEpiBufs > 1 ? bx : 0)) * 4096;
           const int box_tc = half * kColsPerWarp + bx * 64;   // first column of the box inside the output tile
           const int box_col = n_tile * kOutTileN + box_tc;    // global output column
           if (box_col >= n_out_total || row0 >= p.M) continue;  // warp-uniform
           float st_sum = 0.f, st_sq = 0.f;
-          if (lane == 0) tma_store_wait_read<0>();            // previous box fully read out of the staging buffer
-          __syncwarp();
-          if constexpr (EPI == MB_EPI_RESIDUAL) {
-            if (lane == 0) {
-              mbar_arrive_expect_tx(&epi_bar[ew], 4096);
-              tma_load_2d(&tmap_res, &epi_bar[ew], stage_buf, box_col, row0);
-            }
+          if constexpr (EPI != MB_EPI_RESIDUAL) {
+            if (lane == 0) tma_store_wait_read<0>();          // previous box fully read out of the (single) staging box
+            __syncwarp();
           }
 #pragma unroll
           for (int cc = 0; cc < 2; ++cc) {
             const int tc = box_tc + cc * 32;
             float v[32];
-            epi_math<BN, EPI>(p, t_row, tc, n_tile, n_tile * kOutTileN + tc, n_out_total - (n_tile * kOutTileN + tc),
-                              ln_mean, ln_rstd, v);
+            epi_math<BN, EPI>(t_row, tc, aux_b, aux_c, fold, ln_mean, ln_rstd, v);
             uint32_t packed[16];  // the 32 output values of this chunk as bf16 pairs
             if constexpr (EPI == MB_EPI_RESIDUAL) {
-              if (cc == 0) mbar_wait(&epi_bar[ew], epi_phase);
+              if (cc == 0) mbar_wait(&epi_bar[ew * 2 + bx], epi_phase);
               // out = bf16( bf16(acc + bias) + residual ), statistics of the stored values: all on packed fp32 pairs
               // (6 issue slots per element instead of 11 — this epilogue outlasted the K = 1024 main loop)
               const bool want_stats = p.ln_stats_out != nullptr;
@@ -464,7 +475,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if constexpr (EPI == MB_EPI_RESIDUAL) {
-            epi_phase ^= 1;
             if (p.ln_stats_out != nullptr && row_ok)
               reinterpret_cast<float2*>(p.ln_stats_out)[static_cast<int64_t>(row) * p.ln_slots_out + (box_col >> 6)] =
                   make_float2(st_sum, st_sq);
@@ -483,7 +493,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int out_col = n_tile * kOutTileN + tc;  // global output column
           const int ncols_valid = n_out_total - out_col;
           float v[32];
-          epi_math<BN, EPI>(p, t_row, tc, n_tile, out_col, ncols_valid, ln_mean, ln_rstd, v);
+          epi_math<BN, EPI>(t_row, tc, aux_b, aux_c, fold, ln_mean, ln_rstd, v);
           if constexpr (EPI == MB_EPI_RESIDUAL) {
             if (row_ok && ncols_valid > 0) {
               const __nv_bfloat16* rp = p.residual + res_row * p.ldr + out_col;
@@ -509,6 +519,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (row_ok && ncols_valid > 0) store_row_segment(p.out + out_row * p.ldo + out_col, v, ncols_valid);
         }
       }
+      if (p.tma_epi) epi_phase ^= 1;  // residual boxes: one barrier phase per tile
       // all TMEM reads of this warp are complete (tmem_ld_wait above) -> hand the accumulator back
       if (stamp) p.dbg[tcount * 8 + 6] = clock64();
       tc_fence_before();
@@ -534,7 +545,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BN, int EPI, int CG>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                        const GemmParams& p, int grid, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, CG>;
+  using Cfg = GemmCfg<BN, CG, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
