@@ -17,6 +17,10 @@ BF16 = torch.bfloat16
 # When set to a list, linear() brackets every GEMM launch with CUDA events on the launching stream and appends
 # ((M, N, K, epi), flops, start_event, end_event) — used by bench.py for the roofline of the dominant kernel.
 PROFILE: list | None = None
+# When set to a list, linear() also appends a zero-argument closure that re-issues exactly the same launch (same
+# buffers, shapes, epilogue): bench.py replays the step's GEMM launches back to back between two events, which times
+# the dominant kernel without the per-launch event pairs (those serialise the PDL chain and add ~2 us per launch).
+REPLAY: list | None = None
 
 
 def _stream() -> int:
@@ -108,6 +112,11 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
     if prof is not None:
         ev1.record()
         prof.append(((M, N, K, epi), 2.0 * M * N * K, ev0, ev1))
+    if REPLAY is not None:
+        keep = (a, weight, bias, out2, r2, ln_fold, stats_out)  # keeps the buffers alive for the replay
+        REPLAY.append((lambda: linear(x, weight, bias, epi=epi, residual=residual, res_row_mod=res_row_mod, out=ret,
+                                      out_row_group=out_row_group, out_row_pad=out_row_pad, ln_fold=ln_fold,
+                                      stats_out=stats_out), 2.0 * M * N * K, keep))
     _lib.check(rc, "mb_gemm_bf16")
     return ret
 
