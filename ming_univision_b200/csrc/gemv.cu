@@ -70,8 +70,8 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 //   * n = 8 MMA columns = up to 8 tokens (rows >= M read a shared zero row).
 // Per 1 KB of weights a warp issues 2 LDG.128 + 1 LDS.128 + 2 HMMA.  KSPLIT warps of a CTA share one row tile and split
 // its K range (narrow layers still fill the GPU); their partial sums meet in shared memory.
-template <int EPI, int KSPLIT>
-__global__ void __launch_bounds__(kGemvThreads)
+template <int EPI, int KSPLIT, bool NORM>
+__global__ void __launch_bounds__(kGemvThreads, 2)
 gemv_bf16_kernel(const GemvParams p) {
   constexpr int kTiles = (EPI == MB_EPI_SWIGLU) ? 2 : 1;  // 16-row tiles per work item
   constexpr int kUnroll = (EPI == MB_EPI_SWIGLU) ? 4 : 8;
@@ -129,7 +129,7 @@ gemv_bf16_kernel(const GemvParams p) {
   pdl_wait();
 
   // stage the activations: rows 0..M-1, then one zero row shared by the unused MMA columns
-  if (p.pro == 0) {
+  if constexpr (!NORM) {
     for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
       const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
       uint4 v = make_uint4(0, 0, 0, 0);
@@ -137,78 +137,131 @@ gemv_bf16_kernel(const GemvParams p) {
       *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = v;
     }
   } else {
-    // warp m normalises row m (M <= 8 = warps per CTA); two-pass statistics in fp32 as the row kernels do
-    if (warp <= p.M) {
-      const int m = warp;
-      uint8_t* dst = gemv_smem + m * row_bytes;
-      if (m == p.M) {
-        for (int c = lane; c < row_bytes / 16; c += 32) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0, 0, 0, 0);
-      } else {
-        const __nv_bfloat16* ar = p.A + m * p.lda;
-        float s1 = 0.f;
-        for (int c = lane; c < kchunks; c += 32) {
-          const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
-          const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-          if (p.pro == 1) s1 += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-          else s1 += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y) + (f2.x * f2.x + f2.y * f2.y) +
-                     (f3.x * f3.x + f3.y * f3.y);
+    // All 256 threads cooperate on every row: each thread keeps its 16-byte chunks of ALL rows in registers (one pass
+    // over global memory, all loads in flight together), the row statistics are block reductions (shuffle + one shared
+    // array), and the normalised rows go straight to the staging area.  ~2 us, most of it hidden behind the first
+    // weight batch that is already in flight.
+    constexpr int kMaxChunks = 2;   // per thread and row: K <= 2 * 256 * 8 = 4096
+    constexpr int kMaxRowsReg = 2;  // rows held in registers per round (register budget: two CTAs per SM)
+    __shared__ float red_s[kMaxRowsReg][kGemvThreads / 32];
+    for (int m0 = 0; m0 < p.M; m0 += kMaxRowsReg) {
+      const int nm = min(kMaxRowsReg, p.M - m0);
+      uint4 raw[kMaxRowsReg][kMaxChunks];  // the rows stay packed (bf16) in registers and are unpacked per pass
+      float part[kMaxRowsReg];
+      auto unpack8 = [](const uint4& q, float (&f)[8]) {
+        const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
+        f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
+      };
+#pragma unroll
+      for (int r = 0; r < kMaxRowsReg; ++r) {
+        part[r] = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < kMaxChunks; ++cc) {
+          const int c = tid + cc * kGemvThreads;
+          const bool ok = r < nm && c < kchunks;
+          raw[r][cc] = ok ? *reinterpret_cast<const uint4*>(p.A + (m0 + r) * p.lda + c * 8) : make_uint4(0, 0, 0, 0);
         }
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        float mean = 0.f, rstd;
-        if (p.pro == 1) {
-          mean = s1 / K;
-          float s2 = 0.f;
-          for (int c = lane; c < kchunks; c += 32) {
-            const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
-            const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-            const float d0 = f0.x - mean, d1 = f0.y - mean, d2 = f1.x - mean, d3 = f1.y - mean, d4 = f2.x - mean,
-                        d5 = f2.y - mean, d6 = f3.x - mean, d7 = f3.y - mean;
-            s2 += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3) + (d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7);
-          }
+      for (int r = 0; r < kMaxRowsReg; ++r) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          rstd = rsqrtf(s2 / K + p.pro_eps);
-        } else {
-          rstd = rsqrtf(s1 / K + p.pro_eps);
+        for (int cc = 0; cc < kMaxChunks; ++cc) {
+          float f[8];
+          unpack8(raw[r][cc], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[r] += (p.pro == 1) ? f[i] : f[i] * f[i];
         }
-        for (int c = lane; c < row_bytes / 16; c += 32) {
-          uint4 o4 = make_uint4(0, 0, 0, 0);
-          if (c < kchunks) {
-            const uint4 q = *reinterpret_cast<const uint4*>(ar + c * 8);
-            float v[8];
-            {
-              const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
-              v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y; v[4] = f2.x; v[5] = f2.y; v[6] = f3.x; v[7] = f3.y;
-            }
-            __nv_bfloat16 gm[8], bt[8], sh[8], sc[8];
-            if (p.pro_gamma) *reinterpret_cast<uint4*>(gm) = *reinterpret_cast<const uint4*>(p.pro_gamma + c * 8);
-            if (p.pro_beta) *reinterpret_cast<uint4*>(bt) = *reinterpret_cast<const uint4*>(p.pro_beta + c * 8);
-            if (p.pro == 1) {
-              *reinterpret_cast<uint4*>(sh) = *reinterpret_cast<const uint4*>(p.pro_shift + m * p.ld_shift + c * 8);
-              *reinterpret_cast<uint4*>(sc) = *reinterpret_cast<const uint4*>(p.pro_scale + m * p.ld_scale + c * 8);
-            }
+      }
+      auto block_sums = [&](float (&x)[kMaxRowsReg]) {  // x[r] <- sum over the CTA
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (p.pro == 1) {
-                float x = (v[i] - mean) * rstd;
-                if (p.pro_gamma) x = x * __bfloat162float(gm[i]) + (p.pro_beta ? __bfloat162float(bt[i]) : 0.f);
-                x = x * bf16_round(1.f + __bfloat162float(sc[i])) + __bfloat162float(sh[i]);
-                v[i] = x;
-              } else {
-                v[i] = __bfloat162float(gm[i]) * bf16_round(v[i] * rstd);
+        for (int r = 0; r < kMaxRowsReg; ++r) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) x[r] += __shfl_xor_sync(0xffffffffu, x[r], o);
+        }
+        __syncthreads();  // red_s free (previous use fully read)
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < kMaxRowsReg; ++r) red_s[r][warp] = x[r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kMaxRowsReg; ++r) {
+          float t2 = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < kGemvThreads / 32; ++w2) t2 += red_s[r][w2];
+          x[r] = t2;
+        }
+      };
+      block_sums(part);
+      float mean[kMaxRowsReg], rstd[kMaxRowsReg];
+      if (p.pro == 1) {
+        float sq[kMaxRowsReg];
+#pragma unroll
+        for (int r = 0; r < kMaxRowsReg; ++r) {
+          mean[r] = part[r] / K;
+          sq[r] = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < kMaxChunks; ++cc) {
+            if (tid + cc * kGemvThreads < kchunks) {
+              float f[8];
+              unpack8(raw[r][cc], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float d = f[i] - mean[r];
+                sq[r] += d * d;
               }
             }
-            o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
-            o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
           }
-          *reinterpret_cast<uint4*>(dst + c * 16) = o4;
+        }
+        block_sums(sq);
+#pragma unroll
+        for (int r = 0; r < kMaxRowsReg; ++r) rstd[r] = rsqrtf(sq[r] / K + p.pro_eps);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kMaxRowsReg; ++r) {
+          mean[r] = 0.f;
+          rstd[r] = rsqrtf(part[r] / K + p.pro_eps);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kMaxChunks; ++cc) {
+        const int c = tid + cc * kGemvThreads;
+        if (c >= kchunks) continue;
+        __nv_bfloat16 gm[8], bt[8];
+        if (p.pro_gamma) *reinterpret_cast<uint4*>(gm) = *reinterpret_cast<const uint4*>(p.pro_gamma + c * 8);
+        if (p.pro_beta) *reinterpret_cast<uint4*>(bt) = *reinterpret_cast<const uint4*>(p.pro_beta + c * 8);
+#pragma unroll
+        for (int r = 0; r < kMaxRowsReg; ++r) {
+          if (r >= nm) continue;
+          const int m = m0 + r;
+          __nv_bfloat16 sh[8], sc[8];
+          if (p.pro == 1) {
+            *reinterpret_cast<uint4*>(sh) = *reinterpret_cast<const uint4*>(p.pro_shift + m * p.ld_shift + c * 8);
+            *reinterpret_cast<uint4*>(sc) = *reinterpret_cast<const uint4*>(p.pro_scale + m * p.ld_scale + c * 8);
+          }
+          float o[8], f[8];
+          unpack8(raw[r][cc], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.pro == 1) {
+              float x = (f[i] - mean[r]) * rstd[r];
+              if (p.pro_gamma) x = x * __bfloat162float(gm[i]) + (p.pro_beta ? __bfloat162float(bt[i]) : 0.f);
+              o[i] = x * bf16_round(1.f + __bfloat162float(sc[i])) + __bfloat162float(sh[i]);
+            } else {
+              o[i] = __bfloat162float(gm[i]) * bf16_round(f[i] * rstd[r]);
+            }
+          }
+          uint4 o4;
+          o4.x = pack_bf16x2(o[0], o[1]); o4.y = pack_bf16x2(o[2], o[3]);
+          o4.z = pack_bf16x2(o[4], o[5]); o4.w = pack_bf16x2(o[6], o[7]);
+          *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = o4;
         }
       }
     }
-    if (p.M == 8 && warp == 0) {  // 9th (zero) row when all eight warps were busy with data rows
-      uint8_t* dst = gemv_smem + 8 * row_bytes;
-      for (int c = lane; c < row_bytes / 16; c += 32) *reinterpret_cast<uint4*>(dst + c * 16) = make_uint4(0, 0, 0, 0);
+    // padding chunks of the data rows and the shared zero row
+    for (int i = tid; i < (p.M + 1) * (row_bytes / 16); i += kGemvThreads) {
+      const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
+      if (m == p.M || c >= kchunks) *reinterpret_cast<uint4*>(gemv_smem + m * row_bytes + c * 16) = make_uint4(0, 0, 0, 0);
     }
   }
   __syncthreads();
@@ -289,17 +342,17 @@ gemv_bf16_kernel(const GemvParams p) {
   }
 }
 
-template <int KSPLIT>
+template <int KSPLIT, bool NORM>
 static int launch_gemv_ks(const GemvParams& p, int epi, int grid, size_t smem, cudaStream_t stream) {
 #define MB_GEMV_CASE(E_)                                                                                       \
   case E_: {                                                                                                   \
     static bool attr_set = false;                                                                              \
     if (!attr_set) {                                                                                           \
-      MB_CHECK_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<E_, KSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         160 * 1024));                                                         \
+      MB_CHECK_CUDA(cudaFuncSetAttribute(gemv_bf16_kernel<E_, KSPLIT, NORM>,                                   \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));            \
       attr_set = true;                                                                                         \
     }                                                                                                          \
-    MB_CHECK_CUDA(launch_pdl(gemv_bf16_kernel<E_, KSPLIT>, dim3(grid), dim3(kGemvThreads), smem, stream, p));  \
+    MB_CHECK_CUDA(launch_pdl(gemv_bf16_kernel<E_, KSPLIT, NORM>, dim3(grid), dim3(kGemvThreads), smem, stream, p)); \
     break;                                                                                                     \
   }
   switch (epi) {
@@ -372,11 +425,22 @@ static int gemv_impl(const void* A, int64_t lda, const void* W, int64_t ldw, con
   const int per_sm = smem <= 48 * 1024 ? 4 : (smem <= 100 * 1024 ? 2 : 1);
   int grid = num_sms() * per_sm;
   if (grid > units) grid = units;
+  if (pro != 0) {  // fused-normalisation instances (only the epilogues / K-splits the RF head and the LLM step use)
+    MB_CHECK_ARG(epi == MB_EPI_BIAS || epi == MB_EPI_SWIGLU, MB_ERR_SHAPE,
+                 "mb_gemv_bf16_norm: BIAS and SWIGLU epilogues only");
+
+    switch (ksplit) {
+      case 1: return launch_gemv_ks<1, true>(p, epi, grid, smem, stream);
+      case 2: return launch_gemv_ks<2, true>(p, epi, grid, smem, stream);
+      case 4: return launch_gemv_ks<4, true>(p, epi, grid, smem, stream);
+      default: return launch_gemv_ks<8, true>(p, epi, grid, smem, stream);
+    }
+  }
   switch (ksplit) {
-    case 1: return launch_gemv_ks<1>(p, epi, grid, smem, stream);
-    case 2: return launch_gemv_ks<2>(p, epi, grid, smem, stream);
-    case 4: return launch_gemv_ks<4>(p, epi, grid, smem, stream);
-    default: return launch_gemv_ks<8>(p, epi, grid, smem, stream);
+    case 1: return launch_gemv_ks<1, false>(p, epi, grid, smem, stream);
+    case 2: return launch_gemv_ks<2, false>(p, epi, grid, smem, stream);
+    case 4: return launch_gemv_ks<4, false>(p, epi, grid, smem, stream);
+    default: return launch_gemv_ks<8, false>(p, epi, grid, smem, stream);
   }
 }
 
@@ -393,6 +457,7 @@ extern "C" int mb_gemv_bf16_norm(const void* A, int64_t lda, const void* W, int6
                                  const void* beta, const void* shift, int64_t ld_shift, const void* scale,
                                  int64_t ld_scale, float eps, void* stream_) {
   MB_CHECK_ARG(norm == 1 || norm == 2, MB_ERR_SHAPE, "mb_gemv_bf16_norm: norm must be 1 (adaLN) or 2 (RMSNorm)");
+  MB_CHECK_ARG(K <= 4096, MB_ERR_SHAPE, "mb_gemv_bf16_norm: K <= 4096 (the rows are held in registers; K=%d)", K);
   if (norm == 1)
     MB_CHECK_ARG(shift != nullptr && scale != nullptr && ld_shift % 8 == 0 && ld_scale % 8 == 0 &&
                      ((reinterpret_cast<uintptr_t>(shift) | reinterpret_cast<uintptr_t>(scale) |

@@ -77,10 +77,17 @@ class SimpleMLPAdaLN(nn.Module):
         self.final_layer = FinalLayer(model_channels, out_channels)
 
 
-# The streaming kernel can normalise its input rows itself (ops.gemv_norm).  Measured on B200 the separate row kernel is
-# FASTER in this chain (8.25 vs 8.72 ms per RF sample): under PDL it overlaps the tail of the previous GEMM, while the
-# fused statistics sit at the head of every CTA of the next one.  MB_FUSED_NORM=1 selects the fused form.
-FUSED_NORM = os.environ.get("MB_FUSED_NORM", "0") == "1"
+# The streaming kernel can normalise its input rows itself (ops.gemv_norm: LN + adaLN modulation computed by all 256
+# threads of every CTA while its first weight batch is in flight).  Measured on B200 (tools/bench_rf.py): with B = 2 rows
+# the fused form wins (8.23 -> 7.89 ms per RF sample: 208 row-kernel launches and their dependency gaps disappear); with
+# B = 3 the rows no longer fit one register round and the separate row kernel, which overlaps the previous GEMM's tail
+# under PDL, is as fast (8.88 vs 9.01 ms).  MB_FUSED_NORM = 1 / 0 forces either form; default: fused for B <= 2.
+_FUSED_ENV = os.environ.get("MB_FUSED_NORM")
+FUSED_NORM = _FUSED_ENV == "1"  # (LLM decode step: fused RMSNorm only when forced)
+
+
+def _fuse_adaln(n_rows: int) -> bool:
+    return _FUSED_ENV == "1" if _FUSED_ENV in ("0", "1") else n_rows <= 2
 
 
 class _PackedRF:
@@ -163,6 +170,7 @@ class RectifiedFlowLoss(nn.Module):
     def _sample_body(self, pk: _PackedRF, z_bf16: torch.Tensor, x_f32: torch.Tensor, text_cfg: float,
                      image_cfg: float) -> None:
         B, W, depth = z_bf16.shape[0], pk.W, len(pk.blocks)
+        fuse = _fuse_adaln(B)
         c = ops.gemv(z_bf16, pk.cond_w, pk.cond_b)                       # cond_embed(z), once per token (:374)
         sy = ops.silu_add_rows(pk.temb, c)                               # SiLU(t_emb[s] + c) for every step
         mod = ops.linear(sy, pk.ada_w, pk.ada_b)                         # all adaLN modulations, [steps*B, depth*3W+2W]
@@ -173,7 +181,7 @@ class RectifiedFlowLoss(nn.Module):
             h = ops.gemv(x_bf16, pk.in_w, pk.in_b)                       # input_proj (:371)
             for i, (lnw, lnb, w12, b12, w3, b3) in enumerate(pk.blocks):  # ResBlock.forward (:268-272)
                 o = i * 3 * W
-                if FUSED_NORM:  # LN + adaLN modulation fused into the staging of the w12 streaming GEMM
+                if fuse:  # LN + adaLN modulation fused into the staging of the w12 streaming GEMM
                     hid = ops.gemv_norm(h, w12, b12, norm="adaln", gamma=lnw, beta=lnb, shift=ms[:, o:o + W],
                                         scale=ms[:, o + W:o + 2 * W], epi=ops.EPI_SWIGLU)
                 else:
@@ -181,7 +189,7 @@ class RectifiedFlowLoss(nn.Module):
                     hid = ops.gemv(a, w12, b12, epi=ops.EPI_SWIGLU)
                 ops.gemv(hid, w3, b3, epi=ops.EPI_GATED, residual=h, gate=ms[:, o + 2 * W:o + 3 * W], out=h)
             o = depth * 3 * W                                            # FinalLayer.forward (:288-292)
-            if FUSED_NORM:
+            if fuse:
                 v = ops.gemv_norm(h, pk.fin_w, pk.fin_b, norm="adaln", shift=ms[:, o:o + W], scale=ms[:, o + W:o + 2 * W])
             else:
                 a = ops.adaln_modulate(h, None, None, ms[:, o:o + W], ms[:, o + W:o + 2 * W])
