@@ -10,14 +10,15 @@
 //                           max / sum, p = exp2(c s - c m) -> bf16 -> 128B-swizzled shared memory (the A operand of the
 //                           P.V MMA); the running output O_row = alpha O_row + (P V)_row lives in registers and is
 //                           updated ONE BLOCK LATE (P V of block g is fetched from TMEM during block g + 1).
-//   warp 8      TMA       : Q tiles (double buffered) and K_0, V_0, K_1, V_1, ... through a 4-slot ring; runs ahead of
+//   warp 8      TMA       : Q tiles (double buffered) and K_0, V_0, K_1, V_1, ... through a 2-slot ring; runs ahead of
 //                           the compute across work items, so the load latency of the next item is hidden.
 //   warp 9      MMA       : S_g = Q K^T (M 128 x N keys x K head_dim, both operands K-major) into one of TWO score
 //                           buffers in TMEM, issued one block AHEAD (S_{g+1} runs on the tensor core while the softmax
 //                           warps work on S_g); O_g = P_g V (M 128 x N 64 per 64-wide head_dim box x K keys; V is the
 //                           MN-major B operand straight from its [keys][head_dim] TMA tile, no transpose).
 // So neither MMA nor its issue latency is on the softmax warps' critical path.  TMEM: 2 BN (scores) + HD (P V) columns
-// = 256 at head_dim 64, which lets two CTAs share an SM (113 KB shared memory each) and overlap their MUFU phases.
+// = 256 at head_dim 64, which lets two CTAs share an SM (105 KB shared memory each) and overlap their MUFU phases.
+// P is double-buffered in shared memory, so the softmax of block g + 1 never waits for P V of block g.
 // Key blocks are clipped to a multiple of 16 keys (MMA N / K granularity), so S = 65 costs 80 keys, not 96.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -31,7 +32,7 @@
 namespace mb {
 
 constexpr int kAttThreads = 320;  // warps 0..7 softmax (2 threads per query row), warp 8 TMA, warp 9 MMA
-constexpr int kAttRing = 4;
+constexpr int kAttRing = 2;  // K_g always lands in slot 0, V_g in slot 1
 
 struct AttnTcParams {
   __nv_bfloat16* o;
@@ -48,7 +49,12 @@ struct AttnTcCfg {
   static constexpr int kBoxes = HD / 64;                 // 64-element (128-byte) column boxes per row
   static constexpr int kQBytes = 128 * 128 * kBoxes;     // Q tile: 128 rows x HD bf16
   static constexpr int kKVBytes = kBN * 128 * kBoxes;    // K / V tile: BN rows x HD bf16
-  static constexpr int kPBytes = 128 * 128 * 2;          // P tile: 128 rows x up to 128 keys bf16 = two K-major 64-key boxes
+  // P tiles: TWO buffers (block g writes buffer g & 1 while P V of block g - 1 may still read the other one).  A tile is
+  // two K-major 64-key boxes of 128-byte rows.  With 96-key blocks the second box holds only 32 keys = the first 64
+  // bytes of every row, so both buffers SHARE one second box: buffer 0 uses 16-byte chunks 0..3 of each row, buffer 1
+  // chunks 4..7 (logical chunks; the 128-byte swizzle permutes chunks within a row, so the two never collide).
+  static constexpr bool kShareBox1 = kBN <= 96;
+  static constexpr int kPBytes = kShareBox1 ? 3 * 16384 : 4 * 16384;
   // exchange area of the two threads that share a query row: [2 halves][128] bf16 row maxima, reused as [128] fp32 for
   // the row-sum hand-over at the end of a work item.  (Every byte counts: two CTAs must fit the SM's 228 KB.)
   static constexpr int kXchBytes = 512;
@@ -143,10 +149,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       pdl_wait();
-      int g = 0;  // running key-block counter: K_g is ring load 2g, V_g is ring load 2g + 1
-      for (AttnCursor cu = cursor_at(blockIdx.x, 0); cu.valid; advance(cu), ++g) {
+      // K stream (slot 0) runs ONE BLOCK AHEAD of the V stream (slot 1), mirroring the order in which the MMA warp
+      // consumes them (S_{g+1} is issued before P V of block g): K_{g+1} is requested as soon as S_g has read its slot,
+      // V_g as soon as P V of block g - 1 has.  The Q tile of a work item travels with the K tile of its first block.
+      auto load_k = [&](const AttnCursor& cu, int g) {
         const int q0 = (cu.item % nq) * 128, h = (cu.item / nq) % p.Hq, b = cu.item / (nq * p.Hq);
-        const int hk = h / gqa;
         if (cu.j == 0) {
           const int qs = cu.qi & 1;
           mbar_wait_sleep(&q_empty[qs], ((cu.qi >> 1) & 1) ^ 1, 100);
@@ -155,16 +162,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           for (int bx = 0; bx < Cfg::kBoxes; ++bx)
             tma_load_4d(&tmap_q, &q_full[qs], q_s + qs * Cfg::kQBytes + bx * 16384, bx * 64, h, q0, b);
         }
+        mbar_wait_sleep(&kv_empty[0], (g & 1) ^ 1, 100);
+        mbar_arrive_expect_tx(&kv_full[0], Cfg::kKVBytes);
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          const int ld = 2 * g + kv, slot = ld % kAttRing;
-          mbar_wait_sleep(&kv_empty[slot], ((ld / kAttRing) & 1) ^ 1, 100);
-          mbar_arrive_expect_tx(&kv_full[slot], Cfg::kKVBytes);
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(&tmap_k, &kv_full[0], ring_s + bx * (BN * 128), bx * 64, h / gqa, cu.j * BN, b);
+      };
+      auto load_v = [&](const AttnCursor& cu, int g) {
+        const int h = (cu.item / nq) % p.Hq, b = cu.item / (nq * p.Hq);
+        mbar_wait_sleep(&kv_empty[1], (g & 1) ^ 1, 100);
+        mbar_arrive_expect_tx(&kv_full[1], Cfg::kKVBytes);
 #pragma unroll
-          for (int bx = 0; bx < Cfg::kBoxes; ++bx)
-            tma_load_4d(kv ? &tmap_v : &tmap_k, &kv_full[slot], ring_s + slot * Cfg::kKVBytes + bx * (BN * 128),
-                        bx * 64, hk, cu.j * BN, b);
-        }
+        for (int bx = 0; bx < Cfg::kBoxes; ++bx)
+          tma_load_4d(&tmap_v, &kv_full[1], ring_s + Cfg::kKVBytes + bx * (BN * 128), bx * 64, h / gqa, cu.j * BN, b);
+      };
+      AttnCursor ck = cursor_at(blockIdx.x, 0), cv = ck;
+      int gk = 0, gv = 0;
+      if (ck.valid) { load_k(ck, gk++); advance(ck); }
+      while (cv.valid) {
+        if (ck.valid) { load_k(ck, gk++); advance(ck); }
+        load_v(cv, gv++);
+        advance(cv);
       }
     }
   } else if (warp == 9) {
@@ -175,8 +193,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
       auto issue_s = [&](const AttnCursor& cu, int g) {
         const int qs = cu.qi & 1;
         if (cu.j == 0) mbar_wait(&q_full[qs], (cu.qi >> 1) & 1);
-        const int ld = 2 * g, slot = ld % kAttRing;
-        mbar_wait(&kv_full[slot], (ld / kAttRing) & 1);
+        constexpr int slot = 0;  // K tiles
+        const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && g < 64;
+        if (stamp) p.dbg[g * 16 + 8] = clock64();
+        mbar_wait(&kv_full[slot], g & 1);
         tc_fence_after();
         const int nk16 = (min(BN, cu.kv_end - cu.j * BN) + 15) & ~15;
         const uint32_t idesc = umma_idesc_bf16(128, nk16);
@@ -196,35 +216,45 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
         umma_commit(&kv_empty[slot]);
         if (cu.j == cu.nblk - 1) umma_commit(&q_empty[qs]);
         umma_commit(&s_full[g & 1]);
+        if (stamp) p.dbg[g * 16 + 9] = clock64();
       };
       // O_g = P_g V (fresh accumulator; the softmax warps keep the running O in registers)
       auto issue_pv = [&](const AttnCursor& cu, int g) {
+        const bool stamp = p.dbg != nullptr && blockIdx.x == 0 && g < 64;
+        if (stamp) p.dbg[g * 16 + 10] = clock64();
         mbar_wait_sleep(p_full, g & 1, 20);
         tc_fence_after();
-        const int ld = 2 * g + 1, slot = ld % kAttRing;
-        mbar_wait(&kv_full[slot], (ld / kAttRing) & 1);
+        if (stamp) p.dbg[g * 16 + 11] = clock64();
+        constexpr int slot = 1;  // V tiles
+        mbar_wait(&kv_full[slot], g & 1);
         tc_fence_after();
+        if (stamp) p.dbg[g * 16 + 12] = clock64();
         const int nks = (min(BN, cu.kv_end - cu.j * BN) + 15) >> 4;
         constexpr uint32_t idesc = umma_idesc_bf16(128, 64) | kUmmaBMajorMN;
-        const uint64_t da0 = umma_desc_sw128_kmajor(smem_u32(p_s));
+        const int pb = g & 1;  // P buffer of this block
+        const uint64_t da0 = umma_desc_sw128_kmajor(smem_u32(p_s + pb * 16384));                       // keys 0..63
+        const uint64_t da1 = umma_desc_sw128_kmajor(smem_u32(p_s + 32768 + (Cfg::kShareBox1 ? 0 : pb * 16384)));  // 64..
         const uint64_t db0 = umma_desc_sw128_mnmajor(smem_u32(ring_s + slot * Cfg::kKVBytes), BN * 128);
         const uint32_t hi = static_cast<uint32_t>(da0 >> 32);  // identical for both layouts (SBO, version, swizzle)
-        const uint32_t a_lo = static_cast<uint32_t>(da0), b_lo = static_cast<uint32_t>(db0);
+        const uint32_t a_lo0 = static_cast<uint32_t>(da0);
+        const uint32_t a_lo1 = static_cast<uint32_t>(da1) + (Cfg::kShareBox1 ? pb * 4 : 0);  // shared box: chunks 4..7
+        const uint32_t b_lo = static_cast<uint32_t>(db0);
 #pragma unroll
         for (int bx = 0; bx < Cfg::kBoxes; ++bx) {
 #pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks) {
             if (ks < nks) {
-              // A: 64-key boxes of P are 16 KB apart, 32 B per K step inside a box; B: 16 keys = two 8-row groups of
-              // the [keys][64] tile = 2048 B per K step, 64-column boxes BN * 128 B apart
-              const uint32_t offa = (ks >> 2) * (16384 >> 4) + 2 * (ks & 3);
+              // A: 32 B per K step inside a 64-key box; B: 16 keys = two 8-row groups of the [keys][64] tile = 2048 B
+              // per K step, 64-column boxes BN * 128 B apart
+              const uint32_t a_lo = (ks < 4 ? a_lo0 : a_lo1) + 2 * (ks & 3);
               const uint32_t offb = bx * ((BN * 128) >> 4) + ks * (2048 >> 4);
-              umma_bf16_lo(tmem_o + bx * 64, a_lo + offa, b_lo + offb, hi, idesc, ks != 0);
+              umma_bf16_lo(tmem_o + bx * 64, a_lo, b_lo + offb, hi, idesc, ks != 0);
             }
           }
         }
         umma_commit(&kv_empty[slot]);
         umma_commit(o_full);
+        if (stamp) p.dbg[g * 16 + 13] = clock64();
       };
       AttnCursor cs = cursor_at(blockIdx.x, 0), cp = cs;
       int gs = 0, gp = 0;
@@ -323,7 +353,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           uint64_t acc0 = pack_f32x2(0.f, 0.f), acc1 = acc0;
           float tail = 0.f;
           uint8_t* const prow0 = p_s + r_local * 128;
-          const int sw = r_local & 7;
+          const int sw = r_local & 7, pb = g & 1;
           for (int cc = c_beg; cc < c_end; cc += 16) {
             uint32_t sr[16];
             tmem_ld_32x32b_x16(s_addr + cc, sr);
@@ -350,8 +380,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
                 pk[i] = pack_bf16x2(p0, p1);
               }
             }
-            uint8_t* prow = prow0 + (cc >> 6) * 16384;
-            const int ch = (cc & 63) >> 3;
+            // P buffer g & 1: keys 0..63 in its own box, keys 64.. in the second box (shared: chunk offset 4 for buffer 1)
+            uint8_t* prow = prow0 + ((cc < 64) ? pb * 16384 : 32768 + (Cfg::kShareBox1 ? 0 : pb * 16384));
+            const int ch = ((cc & 63) >> 3) + ((cc >= 64 && Cfg::kShareBox1) ? pb * 4 : 0);
             *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
@@ -378,11 +409,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (stamp) p.dbg[g * 16 + 4] = clock64();
         } else {
           if (stamp) p.dbg[g * 16 + 2] = clock64();
-          // P V of the previous block complete: the P tile is free and O_{g-1} is in TMEM
-          mbar_wait(o_full, (g - 1) & 1);
-          tc_fence_after();
           if (stamp) p.dbg[g * 16 + 3] = clock64();
-          exp_pass(m * c);
+          exp_pass(m * c);  // (P buffer g & 1 is free: its last reader, P V of block g - 2, was waited for one block ago)
           if (stamp) p.dbg[g * 16 + 4] = clock64();
           const float flag = exchange(!(sum <= kSumLimit) ? 1.f : 0.f);  // NaN / inf count as "over the limit"
           // rare: some row's scores outgrew the stale reference.  The two warps that share these rows see the same flags,
@@ -390,8 +418,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant
           if (__any_sync(0xffffffffu, flag != 0.f)) exact_block(flag != 0.f);
         }
         if (stamp) p.dbg[g * 16 + 5] = clock64();
-        // fold in P V of the PREVIOUS block before handing the O columns back to the tensor core
-        if (j > 0) accumulate_prev();
+        // fold in P V of the PREVIOUS block (it had the whole exponent pass to complete) before handing the O columns
+        // back to the tensor core
+        if (j > 0) {
+          mbar_wait(o_full, (g - 1) & 1);
+          tc_fence_after();
+          accumulate_prev();
+        }
         fence_proxy_async_smem();  // P stores -> visible to the tensor core's (async proxy) reads
         tc_fence_before();         // the TMEM reads of S_g and O_{g-1} are complete before the MMA warp reuses them
         __syncwarp();

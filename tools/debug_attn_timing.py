@@ -16,7 +16,7 @@ torch.cuda.synchronize()
 _lib.load().mb_attn_set_debug(None)
 t = buf.cpu().view(64, 16)
 base = int(t[0, 0])
-names = ["sm:wait_s", "sm:got_s", "sm:pass1", "sm:xchg", "sm:p_free", "sm:pass2", "sm:arrive", "sm:acc", "mma:k_wait", "mma:k_ok", "mma:S_iss", "mma:p_ok", "mma:v_ok", "mma:PV_iss"]
+names = ["sm:wait_s", "sm:got_s", "sm:-", "sm:exp0", "sm:exp1", "sm:xchg", "sm:arrive", "-", "mma:k_wait", "mma:S_iss", "mma:p_wait", "mma:p_ok", "mma:v_ok", "mma:PV_iss"]
 print(" g " + " ".join(f"{n:>10s}" for n in names))
 for g in range(24):
     print(f"{g:2d} " + " ".join(f"{int(t[g, i]) - base:10d}" for i in range(14)))
