@@ -404,12 +404,9 @@ def main():
         return
     world, rank, local = _dist_setup(args)
     try:
-        if False:
-            pass
-        else:
-            if not torch.cuda.is_available():
-                raise SystemExit("bench.py: no CUDA device (the ming_univision_b200 path has no CPU fallback)")
-            run_ours(args, world, rank, local)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the ming_univision_b200 path has no CPU fallback)")
+        run_ours(args, world, rank, local)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -1,8 +1,9 @@
 // Fused softmax(QK^T * scale)V forward for head_dim 64 / 128 (bf16 in, fp32 softmax + accumulate, bf16 out).
 // One CTA = 64 query rows of one (batch, head); 4 warps x 16 rows; K/V streamed through a double-buffered,
 // XOR-swizzled shared-memory ring with cp.async; online softmax in registers.
-// (Round-1 kernel uses warp-level mma.sync tiles; attention is ~3 % of the MingTok FLOPs — the GEMMs carry the
-// tcgen05 path.  A tcgen05/TMEM variant is listed in DESIGN.md "next".)
+// Warp-level mma.sync kernel: backend 2 of mb_attn_hd64 / mb_attn_fwd (A/B tests, shapes the tcgen05 kernel declines);
+// the default backend is the tcgen05 / TMEM / TMA kernel in attention_tc.cu.  This file also holds the cached q_len = 1
+// decode step of the semantic decoder.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>

@@ -5,8 +5,16 @@
 //   warp 1        MMA issuer     : one lane issues tcgen05.mma (M=128, N=BN, K=16) with both operands read from
 //                                  shared memory through UMMA descriptors; accumulators live in TMEM, double
 //                                  buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of i+1.
-//   warps 2..9    epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> bias / GELU / SwiGLU / residual
-//                                  -> bf16 -> 16-byte global stores (each thread owns one output row segment).
+//   warps 2..9    epilogue       : BEFORE the accumulator is complete: the tile's per-column vectors (bias, or the
+//                                  folded LayerNorm bias and column sums) go to shared memory and every residual box
+//                                  of the tile is requested by TMA into its own staging box; then tcgen05.ld 32 lanes
+//                                  x 32 columns -> registers -> bias / GELU / SwiGLU / residual (packed FFMA2 math) ->
+//                                  bf16 -> 128B-swizzled staging box -> TMA store.  (Direct 16-byte stores remain for
+//                                  the remapped outputs of the patch embedding.)
+//
+// Grouped mode (mb_moe_grouped_gemm): the same kernel walks expert-sorted rows whose tile -> expert map and tile COUNT
+// live in device memory (routing plan), offsets the B tile by expert, and can assemble it from two half-height TMA
+// boxes (gate rows, up rows) for the SwiGLU epilogue.
 //
 // CG = 2 runs the same roles on a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each CTA
 // stages its own 128 rows of A and HALF of the W tile (BN/2 rows), the leader CTA issues M = 256 MMAs that read both
