@@ -280,6 +280,19 @@ int mb_moe_grouped_gemm(const void* A, const void* W, void* out, const int32_t* 
  * weighted sum (non-local pairs contribute zeros), the ranks all-reduce the [T, D] fp32 partials over NCCL, and
  * mb_moe_finalize applies the reference's rounding chain: bf16(bf16(bf16(sum) + shared) + residual). */
 int mb_moe_finalize(const float* y_sum, const void* shared, const void* residual, void* y, int T, int D, void* stream);
+/* The same combine FUSED with its exchange over NVLink peer memory (decode-sized inputs; no NCCL, no host sync).
+ * Every rank owns an exchange area of mb_moe_peer_area_bytes(G, Tmax, D) bytes, zero-initialised, in memory that all
+ * ranks have mapped (torch symmetric memory / CUDA IPC); `peers` is a DEVICE array of the G base pointers as seen from
+ * this process.  mb_moe_combine_push stores this rank's fp32 partial sums straight into every peer's area (st.global
+ * on peer pointers) and raises a system-scope flag there; mb_moe_reduce_finalize waits for the G flags of the local
+ * area, adds the G partials in rank order (bit-identical on every rank), applies the rounding chain of mb_moe_finalize
+ * and advances the epoch.  `fin_done` is a zero-initialised local device word.  Both calls must be made by every rank,
+ * in the same order, on its stream. */
+int mb_moe_peer_area_bytes(int G, int Tmax, int D, int64_t* bytes);
+int mb_moe_combine_push(const void* out_pairs, const float* weights, const int32_t* pair_row, float* const* peers,
+                        int my_rank, int G, int T, int Tmax, int k, int D, void* stream);
+int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int Tmax, int D, const void* shared,
+                           const void* residual, void* y, uint32_t* fin_done, void* stream);
 
 #ifdef __cplusplus
 }

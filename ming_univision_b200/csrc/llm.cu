@@ -605,6 +605,111 @@ __global__ void moe_finalize_kernel(const float* __restrict__ y_sum, const __nv_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Expert-parallel combine FUSED with its exchange over NVLink peer memory (decode-sized inputs, tokens replicated on
+// every rank): no NCCL call, no host involvement.  Every rank owns an exchange area in symmetric (peer-mapped) memory:
+//     slots [2 parities][G source ranks][Tmax * D] fp32,   flags [G] u32,   then local-only: epoch u32, done u32
+// and knows the base pointer of every peer's area (`peers`, a device array of G pointers).
+//   mb_moe_combine_push   : this rank's fp32 partial sums  sum_j w[t,j] * out_pairs[row(t,j)]  are STORED DIRECTLY INTO
+//                           EVERY PEER'S slot [parity][my_rank] (plain st.global on the peer pointers: the stores
+//                           travel over NVLink while the kernel is still computing); the last CTA to finish issues a
+//                           system-scope fence and raises flag[my_rank] = epoch in every peer's area.
+//   mb_moe_reduce_finalize: waits (bounded spin, ld.acquire.sys) until all G flags of the LOCAL area show the epoch,
+//                           adds the G slots in rank order (so every rank computes bit-identical sums), applies the
+//                           reference's rounding chain  bf16(bf16(bf16(sum) + shared) + residual)  and bumps the epoch.
+// Two parities suffice: a rank can be at most one call ahead of its slowest peer (it cannot pass its own reduce of call
+// n + 1 before every peer has pushed call n + 1, i.e. finished its reduce of call n).
+// ------------------------------------------------------------------------------------------------------------
+struct PeerArea {
+  static __host__ __device__ size_t slot_floats(int G, int Tmax, int D) { return static_cast<size_t>(2) * G * Tmax * D; }
+};
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+moe_combine_push_kernel(const __nv_bfloat16* __restrict__ out_pairs, const float* __restrict__ w,
+                        const int32_t* __restrict__ pair_row, float* const* __restrict__ peers, int my_rank, int G,
+                        int T, int Tmax, int k, int D) {
+  float* local = peers[my_rank];
+  uint32_t* ctrl = reinterpret_cast<uint32_t*>(local + PeerArea::slot_floats(G, Tmax, D));  // flags[G], epoch, done
+  const uint32_t epoch = ctrl[G] + 1;
+  const size_t slot_off = (static_cast<size_t>(epoch & 1) * G + my_rank) * Tmax * D;
+  const int64_t total = static_cast<int64_t>(T) * D;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t t = i / D;
+    const int d = static_cast<int>(i % D);
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int r = pair_row ? pair_row[t * k + j] : static_cast<int>(t * k + j);
+      if (r >= 0) acc += w[t * k + j] * __bfloat162float(out_pairs[static_cast<int64_t>(r) * D + d]);
+    }
+    for (int pr = 0; pr < G; ++pr) peers[pr][slot_off + i] = acc;  // NVLink peer stores (local store for pr == my_rank)
+  }
+  // last CTA: everything this rank pushed is ordered before the flags it raises
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) is_last = atomicAdd(&ctrl[G + 1], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last) {
+    __threadfence_system();
+    for (int pr = threadIdx.x; pr < G; pr += blockDim.x) {
+      uint32_t* pctrl = reinterpret_cast<uint32_t*>(peers[pr] + PeerArea::slot_floats(G, Tmax, D));
+      st_release_sys_u32(pctrl + my_rank, epoch);
+    }
+    if (threadIdx.x == 0) ctrl[G + 1] = 0;  // done counter ready for the next call
+  }
+}
+
+__global__ void __launch_bounds__(256)
+moe_reduce_finalize_kernel(float* const* __restrict__ peers, int my_rank, int G, int T, int Tmax, int D,
+                           const __nv_bfloat16* __restrict__ shared, const __nv_bfloat16* __restrict__ residual,
+                           __nv_bfloat16* __restrict__ y, uint32_t* __restrict__ fin_done) {
+  const float* local = peers[my_rank];
+  uint32_t* ctrl = reinterpret_cast<uint32_t*>(peers[my_rank] + PeerArea::slot_floats(G, Tmax, D));
+  const uint32_t epoch = ctrl[G] + 1;
+  if (threadIdx.x < G) {  // bounded wait for every source rank's flag (a diverged peer must trap, not hang the GPU)
+    uint32_t spins = 0;
+    // flags only grow; a fast peer may already have raised the NEXT epoch (it writes the other parity)
+    while (static_cast<int32_t>(ld_acquire_sys_u32(ctrl + threadIdx.x) - epoch) < 0) {
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        printf("moe_reduce_finalize: rank %d never saw epoch %u from rank %d\n", my_rank, epoch, (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const float* slots = local + static_cast<size_t>(epoch & 1) * G * Tmax * D;
+  const int64_t total = static_cast<int64_t>(T) * D;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < G; ++r) sum += __ldcg(slots + static_cast<size_t>(r) * Tmax * D + i);  // rank order: deterministic
+    float v = bf16_round(sum);
+    if (shared) v = bf16_round(v + __bfloat162float(shared[i]));
+    if (residual) v = v + __bfloat162float(residual[i]);
+    y[i] = __float2bfloat16_rn(v);
+  }
+  // the last CTA to finish advances the epoch (all CTAs have read `epoch` and the slots by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(fin_done, 1u) == gridDim.x - 1) {
+      *fin_done = 0;
+      ctrl[G] = epoch;
+    }
+  }
+}
+
 // greedy sampling: first index of the row maximum (torch.argmax tie rule)   one CTA per row
 __global__ void __launch_bounds__(256)
 argmax_f32_kernel(const float* __restrict__ x, int32_t* __restrict__ out, int V) {
@@ -795,6 +900,48 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
                           T * k < E ? T * k : E, static_cast<cudaStream_t>(stream_));
 }
 
+
+
+extern "C" int mb_moe_peer_area_bytes(int G, int Tmax, int D, int64_t* bytes) {
+  MB_CHECK_ARG(G >= 1 && Tmax >= 1 && D >= 1 && bytes != nullptr, MB_ERR_SHAPE, "mb_moe_peer_area_bytes: bad shape");
+  *bytes = static_cast<int64_t>(PeerArea::slot_floats(G, Tmax, D) * 4 + (static_cast<size_t>(G) + 3) * 4);
+  return MB_OK;
+}
+
+extern "C" int mb_moe_combine_push(const void* out_pairs, const float* weights, const int32_t* pair_row,
+                                   float* const* peers, int my_rank, int G, int T, int Tmax, int k, int D,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_combine_push: no sm_100 device");
+  MB_CHECK_ARG(G >= 1 && my_rank >= 0 && my_rank < G && T >= 1 && T <= Tmax && peers != nullptr, MB_ERR_SHAPE,
+               "mb_moe_combine_push: bad ranks / rows (T=%d Tmax=%d G=%d)", T, Tmax, G);
+  const int64_t total = static_cast<int64_t>(T) * D;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms()) grid = num_sms();
+  moe_combine_push_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out_pairs), weights, pair_row,
+                                                    peers, my_rank, G, T, Tmax, k, D);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int Tmax, int D,
+                                      const void* shared, const void* residual, void* y, uint32_t* fin_done,
+                                      void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_reduce_finalize: no sm_100 device");
+  MB_CHECK_ARG(G >= 1 && G <= 256 && my_rank >= 0 && my_rank < G && T >= 1 && T <= Tmax && peers != nullptr &&
+                   fin_done != nullptr,
+               MB_ERR_SHAPE, "mb_moe_reduce_finalize: bad ranks / rows");
+  const int64_t total = static_cast<int64_t>(T) * D;
+  int grid = static_cast<int>((total + 255) / 256);
+  if (grid > num_sms()) grid = num_sms();
+  moe_reduce_finalize_kernel<<<grid, 256, 0, stream>>>(peers, my_rank, G, T, Tmax, D,
+                                                       static_cast<const __nv_bfloat16*>(shared),
+                                                       static_cast<const __nv_bfloat16*>(residual),
+                                                       static_cast<__nv_bfloat16*>(y), fin_done);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
 
 extern "C" int mb_moe_plan(const int32_t* idx, int32_t* pair_row, int32_t* row_token, int32_t* tile_expert,
                            int32_t* meta, int32_t* counts, int T, int k, int E, int e_begin, int div, int granule,

@@ -67,3 +67,36 @@ def token_slice(T: int, size: int, rank: int) -> tuple[int, int, int]:
     """Contiguous token slice of `rank`: chunk = ceil(T / size); returns (begin, end, chunk) with end <= T."""
     chunk = (T + size - 1) // size
     return min(rank * chunk, T), min((rank + 1) * chunk, T), chunk
+
+
+class PeerExchange:
+    """Exchange area of the FUSED expert-parallel combine (mb_moe_combine_push / mb_moe_reduce_finalize): one buffer
+    per rank in torch symmetric memory (cuMem allocation mapped into every process of the group over NVLink), plus the
+    device array of the peers' base pointers that the kernels store through.  One instance serves every MoE layer of a
+    model: the calls are stream-ordered and the kernels' epoch / parity protocol keeps consecutive calls apart."""
+
+    T_MAX = 8  # rows per call (decode regime: CFG rows)
+
+    def __init__(self, group, hidden_size: int, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.size, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.hidden_size = hidden_size
+        import ctypes
+
+        nbytes = ctypes.c_int64(0)
+        _lib.check(_lib.load().mb_moe_peer_area_bytes(self.size, self.T_MAX, hidden_size, ctypes.byref(nbytes)),
+                   "mb_moe_peer_area_bytes")
+        n = (nbytes.value + 3) // 4
+        self.buf = symm_mem.empty((n,), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)  # collective: exchanges the memory handles
+        if len(self.handle.buffer_ptrs) != self.size:
+            raise RuntimeError("symmetric-memory rendezvous did not return one buffer per rank")
+        self.peers_dev = int(self.handle.buffer_ptrs_dev)  # device array of G base pointers (as mapped in this process)
+        self.fin_done = torch.zeros((1,), dtype=torch.int32, device=device)
+        dist.barrier(self.group)  # every area is zeroed before anyone pushes

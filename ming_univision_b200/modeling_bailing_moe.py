@@ -123,22 +123,26 @@ class BailingMoeSparseMoeBlock(nn.Module):
         self._pk = None
         # expert parallelism: this rank keeps experts [ep_rank * E / ep_size, (ep_rank + 1) * E / ep_size)
         self.ep_group, self.ep_rank, self.ep_size = None, 0, 1
-        self.ep_mode, self._a2a = "allreduce", None
+        self.ep_mode, self._a2a, self.ep_peer = "allreduce", None, None
 
     # below this many tokens per rank the all-to-all exchange costs more than it saves (decode: B <= 3 rows)
     A2A_MIN_TOKENS_PER_RANK = 4
 
-    def set_expert_parallel(self, group, rank: int, size: int, mode: str = "allreduce") -> None:
-        """mode "allreduce": tokens replicated, every rank runs its experts on all tokens and the fp32 partial sums are
+    def set_expert_parallel(self, group, rank: int, size: int, mode: str = "allreduce", peer=None) -> None:
+        """mode "peer": like "allreduce", but decode-sized inputs exchange their fp32 partial sums through NVLink peer
+        memory inside the combine kernels (ep.PeerExchange; no NCCL call).  mode "allreduce": tokens replicated, every rank runs its experts on all tokens and the fp32 partial sums are
         all-reduced (decode-sized inputs).  mode "alltoall": prefill-sized inputs additionally shard the TOKENS of the
         MoE block over the ranks with an all-to-all dispatch / combine (ming_univision_b200/ep.py); small inputs still
         take the all-reduce path."""
         if self.config.num_experts % size != 0:
             raise ValueError("num_experts must be divisible by the expert-parallel world size")
-        if mode not in ("allreduce", "alltoall"):
-            raise ValueError("mode must be 'allreduce' or 'alltoall'")
+        if mode not in ("allreduce", "alltoall", "peer"):
+            raise ValueError("mode must be 'allreduce', 'alltoall' or 'peer'")
         self.ep_group, self.ep_rank, self.ep_size = (group if size > 1 else None), rank, size
         self.ep_mode = mode
+        self.ep_peer = peer if (mode == "peer" and size > 1) else None
+        if mode == "peer" and size > 1 and peer is None:
+            raise ValueError("mode 'peer' needs a PeerExchange (ming_univision_b200.ep)")
         self._a2a = None
         self._pk = None
 
@@ -190,7 +194,8 @@ class BailingMoeSparseMoeBlock(nn.Module):
                 shared = ops.gemv(ops.gemv(x2d, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
             else:
                 shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
-        y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual, pk["e_begin"], self.ep_group)
+        y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual, pk["e_begin"], self.ep_group,
+                            self.ep_peer)
         return y, logits, idx
 
     @torch.no_grad()
@@ -358,9 +363,14 @@ class BailingMoeModel(nn.Module):
 
         size = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
+        peer = None
+        if mode == "peer" and size > 1:  # one exchange area for all layers (stream-ordered calls, epoch protocol)
+            from .ep import PeerExchange
+
+            peer = PeerExchange(group, self.config.hidden_size, self.norm.weight.device)
         for lyr in self.layers:
             lyr.mlp.set_expert_parallel(group if group is not None else (dist.group.WORLD if size > 1 else None),
-                                        rank, size, mode)
+                                        rank, size, mode, peer)
         self.ep_size = size
 
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:

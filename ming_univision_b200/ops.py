@@ -572,7 +572,7 @@ def moe_grouped_ffn(xg: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor, tile_
 
 def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor,
                 shared: torch.Tensor | None, residual: torch.Tensor | None, e_begin: int = 0,
-                ep_group=None) -> torch.Tensor:
+                ep_group=None, ep_peer=None) -> torch.Tensor:
     """moe_infer + shared-expert add + residual: x [T, D]; Wgu [E_local, 2I, D]; Wd [E_local, D, I]; idx int32 [T, k]
     (GLOBAL expert ids); w fp32.  Small token counts stream each hit expert's weights once per 8 rows
     (mb_moe_gate_up / mb_moe_down); prefill-sized inputs run as grouped tcgen05 GEMMs (mb_moe_plan /
@@ -611,6 +611,17 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
     if not ep:
         _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(),
                                       None, pr, T, k, D, s), "mb_moe_combine")
+        return y
+    if ep_peer is not None and T <= ep_peer.T_MAX:
+        # fused exchange over NVLink peer memory: partial sums are stored straight into every peer's area, then every
+        # rank adds the G partials in rank order (no NCCL call, no host sync)
+        if D != ep_peer.hidden_size:
+            raise ValueError("peer exchange area was sized for another hidden size")
+        _lib.check(lib.mb_moe_combine_push(out_pairs.data_ptr(), w.data_ptr(), pr, ep_peer.peers_dev, ep_peer.rank,
+                                           ep_peer.size, T, ep_peer.T_MAX, k, D, s), "mb_moe_combine_push")
+        _lib.check(lib.mb_moe_reduce_finalize(ep_peer.peers_dev, ep_peer.rank, ep_peer.size, T, ep_peer.T_MAX, D,
+                                              _ptr(shared), _ptr(residual), y.data_ptr(), ep_peer.fin_done.data_ptr(),
+                                              s), "mb_moe_reduce_finalize")
         return y
     import torch.distributed as dist
 

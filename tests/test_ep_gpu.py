@@ -50,6 +50,23 @@ WORKER = textwrap.dedent("""
         dist.all_gather(gathered, y2)
         assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree"
         print("rank", rank, "T", T, "rel err vs single GPU", err, flush=True)
+    # fused exchange over NVLink peer memory (no NCCL in the combine): decode-sized inputs, several calls in a row so
+    # that both parities and the epoch protocol are exercised; larger inputs fall back to the all-reduce
+    from ming_univision_b200.ep import PeerExchange
+    peer_blk = build()
+    px = PeerExchange(dist.group.WORLD, cfg["hidden_size"], dev)
+    peer_blk.set_expert_parallel(dist.group.WORLD, rank, world, mode="peer", peer=px)
+    for it, T in enumerate((1, 3, 2, 8, 3, 40)):
+        x = torch.randn((1, T, cfg["hidden_size"]), generator=g).to(dev).to(torch.bfloat16)
+        res = torch.randn((T, cfg["hidden_size"]), generator=g).to(dev).to(torch.bfloat16)
+        y1, _, _ = single._run(x.view(T, -1), res, None)
+        y2, _, _ = peer_blk._run(x.view(T, -1), res, None)
+        err = ((y1.float() - y2.float()).norm() / y1.float().norm()).item()
+        assert err < 5e-3, err
+        gathered = [torch.empty_like(y2) for _ in range(world)]
+        dist.all_gather(gathered, y2)
+        assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree (peer mode)"
+        print("rank", rank, "T", T, "peer-memory rel err vs single GPU", err, flush=True)
     # token- AND expert-sharded block: all-to-all dispatch / combine + all-gather (prefill-sized inputs; T = 7 stays
     # on the all-reduce path, T = 41 gives uneven token slices 21 + 20)
     a2a = build()

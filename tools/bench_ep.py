@@ -60,6 +60,12 @@ if world > 1:
     y_ep, _, _ = blk._run(x, res, None)
     out["rel_err_vs_unsharded"] = float(((y_ep.float() - y_single.float()).norm() / y_single.float().norm()).item())
     out["ms_layer_ep"] = round(timeit(lambda: blk._run(x, res, None)), 4)
+    from ming_univision_b200.ep import PeerExchange  # noqa: E402
+    px = PeerExchange(dist.group.WORLD, 2048, dev)
+    blk.set_expert_parallel(dist.group.WORLD, rank, world, mode="peer", peer=px)
+    y_px, _, _ = blk._run(x, res, None)
+    out["rel_err_peer_vs_unsharded"] = float(((y_px.float() - y_single.float()).norm() / y_single.float().norm()).item())
+    out["ms_layer_ep_peer"] = round(timeit(lambda: blk._run(x, res, None)), 4)
 # ---- prefill-sized input (BASELINE configs[2] shape: 1552 tokens): unsharded grouped tcgen05 GEMMs vs expert-parallel
 # all-reduce (tokens replicated) vs token-sharded all-to-all dispatch / combine + all-gather
 T = int(os.environ.get("EP_PREFILL_TOKENS", "1552"))
