@@ -1,0 +1,124 @@
+"""Host-side logic of the multi-round `generate` (modeling_bailingmm.py:206-301) on CPU: the CUDA-backed pieces
+(embedding lookup, LLM forward, greedy decoder, generate_image) are replaced by shape-faithful stand-ins, so what is
+checked here is the bookkeeping the reference does in Python — mask concatenation across rounds, the PAST_MODE KEEP / DROP
+padding rules, the cache-length contract ("the last emitted token is not part of the cached context"), the `<image>`
+hand-off to generate_image and the returned sequences."""
+import os
+
+import pytest
+import torch
+
+from ming_univision_b200 import synthetic
+from ming_univision_b200.mingtok import MingTokConfig
+from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig
+from ming_univision_b200.modeling_bailingmm import MingUniVisionForConditionalGeneration
+
+
+@pytest.fixture()
+def stubbed():
+    cfg, vh, tok = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG, synthetic.MINGTOK_TINY_CONFIG
+    m = MingUniVisionForConditionalGeneration(BailingMoeConfig(**cfg), MingTokConfig(**tok), vh)
+    llm = m.model
+    D, n_tok = cfg["hidden_size"], llm.config.num_image_tokens_for_gen
+    log = {"prefill": [], "image": []}
+    script = {"tokens": []}
+
+    llm.model.embed = lambda ids: torch.zeros(tuple(ids.shape) + (D,))
+
+    def forward_tokens(emb, pos, cache, key_mask=None, image_mask=None, t_dev=None):
+        B, S, _ = emb.shape
+        assert int(pos[0, 0]) == cache.seq_len, "the round's prompt must be appended right behind the cached context"
+        log["prefill"].append((cache.seq_len, S))
+        cache.seq_len += S
+        return torch.zeros((B, S, D))
+
+    def greedy_decode(last, cache, max_new_tokens, stop_ids=()):
+        out = []
+        while script["tokens"] and len(out) < max_new_tokens:
+            t = script["tokens"].pop(0)
+            out.append(t)
+            cache.seq_len += 1
+            if t in stop_ids:
+                break
+        if out:
+            cache.seq_len -= 1
+        return out
+
+    def generate_image(input_embeds, past_key_values, attention_mask, uncond_attention_mask,
+                       text_uncond_attention_mask, **kw):
+        assert attention_mask.shape[1] == past_key_values.seq_len + 1
+        log["image"].append((past_key_values.seq_len, uncond_attention_mask.clone(), text_uncond_attention_mask.clone()))
+        past_key_values.seq_len += n_tok + 1
+        return torch.zeros((1, 3, 8, 8)), torch.zeros((2, 1, D)), None
+
+    llm.model.forward_tokens = forward_tokens
+    llm.greedy_decode = greedy_decode
+    llm.generate_image = generate_image
+    return m, llm, log, script, n_tok
+
+
+def _ref_masks(mode, am, un, tun, cache_len):
+    """modeling_bailingmm.py:272-299 restated."""
+    pad1 = torch.ones((1, cache_len - am.shape[1]), dtype=am.dtype)
+    pad0 = torch.zeros_like(pad1)
+    if mode == "KEEP":
+        return torch.cat((am, pad1), 1), torch.cat((tun, pad1), 1), torch.cat((un, pad0), 1)
+    return torch.cat((am, pad1), 1), torch.cat((am, pad1), 1), torch.cat((am, pad0), 1)
+
+
+@pytest.mark.parametrize("mode", ["DROP", "KEEP"])
+def test_multi_round_mask_bookkeeping(stubbed, mode, monkeypatch):
+    m, llm, log, script, n_tok = stubbed
+    monkeypatch.setenv("PAST_MODE", mode)
+    eos, img_tok = 7, llm.config.image_start_token
+    # round 1: 6 prompt tokens, the model answers 3 text tokens, asks for an image, then 2 more tokens and EOS
+    ids1 = torch.arange(10, 16).view(1, -1)
+    un1 = torch.tensor([[1, 1, 0, 0, 0, 0]], dtype=torch.int32)
+    tun1 = torch.tensor([[1, 1, 1, 0, 0, 1]], dtype=torch.int32)
+    script["tokens"] = [21, 22, 23, img_tok, 31, 32, eos]
+    seq1 = m.generate(ids1, uncond_attention_mask=un1, text_uncond_attention_mask=tun1, max_new_tokens=32,
+                      eos_token_id=eos)
+    assert seq1[0].tolist() == list(range(10, 16)) + [21, 22, 23, img_tok, 31, 32, eos]
+    assert log["prefill"] == [(0, 6)]
+    # the image step starts right behind prompt + 3 fed tokens; it sees the round's uncond masks unchanged
+    assert log["image"][0][0] == 6 + 3 and torch.equal(log["image"][0][1], un1) and torch.equal(log["image"][0][2], tun1)
+    L1 = 6 + 3 + (n_tok + 1) + 3 - 1  # prompt, 3 tokens, <image> + visual tokens, 31 32 eos minus the unfed last one
+    assert m.past_key_values.seq_len == L1 and len(m.generated_images) == 1
+    am1 = torch.ones((1, 6), dtype=torch.int32)
+    exp = _ref_masks(mode, am1, un1, tun1, L1)
+    assert torch.equal(m.past_attention_mask, exp[0])
+    assert torch.equal(m.past_text_uncond_attention_mask, exp[1])
+    assert torch.equal(m.past_uncond_attention_mask, exp[2])
+    # round 2: 4 new prompt tokens appended behind the cached context; masks concatenate with the stored ones
+    ids2 = torch.arange(40, 44).view(1, -1)
+    un2 = torch.zeros((1, 4), dtype=torch.int32)
+    tun2 = torch.tensor([[0, 1, 1, 0]], dtype=torch.int32)
+    script["tokens"] = [img_tok, eos]
+    seq2 = m.generate(ids2, uncond_attention_mask=un2, text_uncond_attention_mask=tun2, max_new_tokens=8, eos_token_id=eos)
+    assert seq2[0].tolist() == [40, 41, 42, 43, img_tok, eos]
+    assert log["prefill"][1] == (L1, 4)
+    assert torch.equal(log["image"][1][1], torch.cat((exp[2], un2), 1))      # accumulated uncond mask reaches generate_image
+    assert torch.equal(log["image"][1][2], torch.cat((exp[1], tun2), 1))
+    L2 = L1 + 4 + (n_tok + 1) + 1 - 1
+    assert m.past_key_values.seq_len == L2
+    exp2 = _ref_masks(mode, torch.cat((exp[0], torch.ones((1, 4), dtype=torch.int32)), 1), torch.cat((exp[2], un2), 1),
+                      torch.cat((exp[1], tun2), 1), L2)
+    assert torch.equal(m.past_attention_mask, exp2[0])
+    assert torch.equal(m.past_text_uncond_attention_mask, exp2[1])
+    assert torch.equal(m.past_uncond_attention_mask, exp2[2])
+    m.reset_inner_state()
+    assert m.past_key_values is None and m.past_uncond_attention_mask is None
+
+
+def test_generate_rejects_misuse(stubbed):
+    m, llm, log, script, n_tok = stubbed
+    with pytest.raises(ValueError):
+        m.generate(torch.zeros((2, 4), dtype=torch.long))                       # batch 1 only (:1865)
+    with pytest.raises(NotImplementedError):
+        m.generate(torch.zeros((1, 4), dtype=torch.long), attention_mask=torch.tensor([[0, 1, 1, 1]]))  # left padding
+    m.reset_inner_state()
+    script["tokens"] = [5]
+    m.generate(torch.zeros((1, 4), dtype=torch.long), max_new_tokens=1, eos_token_id=99)
+    with pytest.raises(ValueError):  # a later round whose masks do not line up with the cached context
+        m.past_attention_mask = m.past_attention_mask[:, :-1]
+        m.generate(torch.zeros((1, 3), dtype=torch.long), max_new_tokens=1)
