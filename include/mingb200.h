@@ -294,6 +294,29 @@ int mb_moe_combine_push(const void* out_pairs, const float* weights, const int32
 int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int Tmax, int D, const void* shared,
                            const void* residual, void* y, uint32_t* fin_done, void* stream);
 
+/* ---- Image pre- / post-processing either side of MingTok -------------------------------------------
+ * Replaces, on the device, the PIL / torchvision CPU transforms of `CenterCropProcessor` (mingtok/utils/processor.py:17-27),
+ * `MingTokUndProcessor` / `MingTokCenterCropProcessor` (mingunivision/processing_bailingmm.py:80-123):
+ *   Resize(bicubic; PIL image => Pillow's ANTIALIASED resample in 8-bit fixed point, horizontal pass, u8 rounding,
+ *   vertical pass) -> CenterCrop -> ToTensor (u8 / 255) -> Normalize ((x - mean) / std),
+ * bit-exact with Pillow 12 + torchvision (u8 image identical, fp32 tensor identical; bf16 = its RN rounding).
+ * src: [n, in_h, in_w, 3] u8 (RGB, HWC) in device memory.  res_h x res_w is the size after Resize (the caller applies
+ * torchvision's rule: short edge -> size, long edge = int(size * long / short)); (crop_top, crop_left, out_h, out_w) the
+ * kept window of the resized image (the whole image when there is no crop).  Only the kept columns / rows are computed.
+ * out: [n, 3, out_h, out_w] bf16 (out_is_fp32 = 0) or fp32.  workspace: >= mb_image_preprocess_workspace_bytes(...)
+ * bytes, 16-byte aligned (coefficient tables + the u8 intermediate); no allocation, no host synchronisation. */
+int mb_image_preprocess_workspace_bytes(int n, int in_h, int in_w, int res_h, int res_w, int crop_top, int crop_left,
+                                        int out_h, int out_w, int64_t* bytes);
+int mb_image_preprocess_u8(const void* src, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,
+                           int crop_left, int out_h, int out_w, float mean0, float mean1, float mean2, float std0,
+                           float std1, float std2, void* out, int out_is_fp32, void* workspace,
+                           int64_t workspace_bytes, void* stream);
+/* `tensor_to_pil` (mingunivision/modeling_bailing_moe.py:84-90, test_infer_recon_image.py:24-28): img [n, 3, h, w]
+ * (bf16, or fp32 with img_is_fp32) -> out [n, h, w, 3] u8 = trunc((x * std + mean) * 255), fp32 steps rounded
+ * separately, ToPILImage's truncation toward zero (saturating outside [0, 255]). */
+int mb_image_postprocess_u8(const void* img, int img_is_fp32, int n, int h, int w, float mean0, float mean1,
+                            float mean2, float std0, float std1, float std2, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,10 +197,11 @@ class MingUniVisionForConditionalGeneration(nn.Module):
 
     @staticmethod
     def _save_image(img: torch.Tensor, prefix: str, index: int) -> None:
-        """[-1, 1] CHW tensor -> `{prefix}.png` / `{prefix}_{i}.png` (modeling_bailing_moe.py:1788-1796)."""
+        """[-1, 1] CHW tensor -> `{prefix}.png` / `{prefix}_{i}.png` (modeling_bailing_moe.py:84-90, :1788-1796)."""
         from PIL import Image
 
-        arr = ((img.float().clamp(-1, 1) + 1) * 127.5).round().to(torch.uint8).permute(1, 2, 0).cpu().numpy()
+        # tensor_to_pil (:84-90): x*std + mean in fp32, then ToPILImage = mul(255).byte(), i.e. TRUNCATION
+        arr = ((img.float().clamp(-1, 1) * 0.5 + 0.5) * 255).to(torch.uint8).permute(1, 2, 0).cpu().numpy()
         Image.fromarray(arr).save(f"{prefix}.png" if index == 0 else f"{prefix}_{index}.png")
 
     @torch.no_grad()

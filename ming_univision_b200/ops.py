@@ -661,3 +661,85 @@ def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     _lib.check(lib.mb_argmax_f32(logits.data_ptr(), out.data_ptr(), rows, V, _ptr(wv), _ptr(wi), n_chunks, _stream()),
                "mb_argmax_f32")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# image pre- / post-processing
+# ---------------------------------------------------------------------------------------------------------------
+def resized_output_size(h: int, w: int, size) -> tuple[int, int]:
+    """torchvision's Resize rule (`_compute_resized_output_size`, no max_size): an int (or 1-tuple) sets the SHORT edge
+    and the long edge becomes int(size * long / short); a pair is (h, w) verbatim."""
+    if isinstance(size, (tuple, list)):
+        if len(size) == 2:
+            return int(size[0]), int(size[1])
+        if len(size) != 1:
+            raise ValueError(f"size must be an int or a 1- or 2-element sequence, not {size!r}")
+        size = size[0]
+    size = int(size)
+    short, long = (w, h) if w <= h else (h, w)
+    new_short, new_long = size, int(size * long / short)
+    new_w, new_h = (new_short, new_long) if w <= h else (new_long, new_short)
+    return new_h, new_w
+
+
+def center_crop_window(h: int, w: int, crop_h: int, crop_w: int) -> tuple[int, int]:
+    """torchvision `center_crop` offsets (top, left) = int(round((full - crop) / 2.0)) — Python's round, half to even.
+    Crops larger than the image (torchvision zero-pads) do not occur after Resize(short edge) and are refused."""
+    if crop_h > h or crop_w > w:
+        raise ValueError(f"centre crop {crop_h}x{crop_w} larger than the resized image {h}x{w}")
+    return int(round((h - crop_h) / 2.0)), int(round((w - crop_w) / 2.0))
+
+
+def image_preprocess(images: torch.Tensor, size, crop: int | tuple[int, int] | None = None,
+                     mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Resize(size, bicubic, Pillow's antialiased 8-bit resample) [-> CenterCrop(crop)] -> ToTensor -> Normalize on the
+    device: images uint8 [N, H, W, 3] (or [H, W, 3]) RGB on CUDA -> [N, 3, h, w] `out_dtype` (fp32: identical to the
+    torchvision pipeline on PIL images; bf16: its round-to-nearest)."""
+    if images.dtype != torch.uint8 or not images.is_cuda:
+        raise TypeError(f"expected a CUDA uint8 tensor, got {images.dtype} on {images.device}")
+    if images.dim() == 3:
+        images = images.unsqueeze(0)
+    if images.dim() != 4 or images.shape[-1] != 3:
+        raise ValueError(f"expected [N, H, W, 3] RGB images, got {tuple(images.shape)}")
+    if out_dtype not in (torch.float32, BF16):
+        raise TypeError("out_dtype must be float32 or bfloat16")
+    images = images.contiguous()
+    n, h, w, _ = images.shape
+    rh, rw = resized_output_size(h, w, size)
+    if crop is None:
+        top, left, oh, ow = 0, 0, rh, rw
+    else:
+        oh, ow = (int(crop), int(crop)) if isinstance(crop, int) else (int(crop[0]), int(crop[1]))
+        top, left = center_crop_window(rh, rw, oh, ow)
+    import ctypes
+
+    lib = _lib.load()
+    nbytes = ctypes.c_int64(0)
+    _lib.check(lib.mb_image_preprocess_workspace_bytes(n, h, w, rh, rw, top, left, oh, ow, ctypes.byref(nbytes)),
+               "mb_image_preprocess_workspace_bytes")
+    ws = torch.empty((max(16, nbytes.value),), dtype=torch.uint8, device=images.device)
+    out = torch.empty((n, 3, oh, ow), dtype=out_dtype, device=images.device)
+    _lib.check(lib.mb_image_preprocess_u8(images.data_ptr(), n, h, w, rh, rw, top, left, oh, ow, float(mean[0]),
+                                          float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]),
+                                          out.data_ptr(), int(out_dtype == torch.float32), ws.data_ptr(), ws.numel(),
+                                          _stream()), "mb_image_preprocess_u8")
+    return out
+
+
+def image_postprocess(img: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> torch.Tensor:
+    """`tensor_to_pil` on the device: [N, 3, H, W] (or [3, H, W]) fp32 / bf16 in [-1, 1] -> uint8 [N, H, W, 3] =
+    trunc((x * std + mean) * 255)."""
+    if img.dtype not in (torch.float32, BF16) or not img.is_cuda:
+        raise TypeError(f"expected a CUDA float32 / bfloat16 tensor, got {img.dtype} on {img.device}")
+    if img.dim() == 3:
+        img = img.unsqueeze(0)
+    if img.dim() != 4 or img.shape[1] != 3:
+        raise ValueError(f"expected [N, 3, H, W], got {tuple(img.shape)}")
+    img = img.contiguous()
+    n, _, h, w = img.shape
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=img.device)
+    lib = _lib.load()
+    _lib.check(lib.mb_image_postprocess_u8(img.data_ptr(), int(img.dtype == torch.float32), n, h, w, float(mean[0]),
+                                           float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]),
+                                           out.data_ptr(), _stream()), "mb_image_postprocess_u8")
+    return out
