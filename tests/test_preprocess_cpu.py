@@ -290,3 +290,33 @@ def test_processors_refuse_to_run_without_a_gpu():
         proc(np.zeros((8, 8, 3), dtype=np.uint8))
     lib = __import__("ming_univision_b200._lib", fromlist=["load"]).load()
     assert lib.mb_image_postprocess_u8(None, 1, 1, 8, 8, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, None, None) == -3  # MB_ERR_ARCH
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 4. the reference's own fixture for this path (read in the build container only; absent on the GPU box)
+# ---------------------------------------------------------------------------------------------------------------------
+REF_ASSET = "/root/reference/mingtok/asset/mingtok.png"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_ASSET), reason="reference checkout not present")
+def test_reference_asset_through_all_three_processors(emu):
+    """mingtok/asset/mingtok.png (a real 512 x 512 photograph, the input of test_infer_recon_image.py:14) through the
+    demo's CenterCropProcessor(512) (nothing to resample: the crop-only path), the generation processor at 256 and the
+    understanding processor's Resize((1024, 1024)): oracle and emulated device code == torchvision, bit for bit."""
+    from PIL import Image
+
+    img = np.array(Image.open(REF_ASSET).convert("RGB"))
+    assert img.shape == (512, 512, 3)
+    for size, crop in ((512, 512), (256, 256), ((1024, 1024), None), (200, 200)):
+        ref = torchvision_pipeline(img, size, crop, HALF, HALF)
+        assert np.array_equal(po.preprocess(img, size, crop), ref), (size, crop)
+        got, _ = emu_preprocess(emu, img[None], size, crop)
+        assert np.array_equal(got[0], ref), (size, crop)
+    # and the way back (test_infer_recon_image.py:24-28): normalised tensor -> PIL bytes
+    import torchvision.transforms as T
+
+    x = torch.from_numpy(torchvision_pipeline(img, 512, 512, HALF, HALF))
+    half = torch.tensor(HALF).view(1, -1, 1, 1)
+    back = np.asarray(T.ToPILImage()((x[None] * half + half)[0]))
+    assert np.array_equal(po.postprocess(x.numpy()), back)
+    assert np.abs(back.astype(int) - img.astype(int)).max() <= 1  # truncation may lose one level, never more
