@@ -24,5 +24,5 @@ def test_preprocess_on_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "preprocess_gpu_worker.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "preprocess worker ok" in r.stdout, (r.stdout[-2000:] + "\n" + r.stderr[-3000:])
