@@ -32,8 +32,11 @@ extern "C" int emu_image_preprocess(const uint8_t* src, int n, int in_h, int in_
     memcpy(plan_out, v, sizeof(v));
   }
   // the workspace is filled with garbage first: nothing may depend on its initial contents
-  std::vector<uint8_t> ws(static_cast<size_t>(p.total_bytes) + 16, 0xA5);
-  uint8_t* base = ws.data() + ((16 - (reinterpret_cast<uintptr_t>(ws.data()) & 15)) & 15);
+  // (exact size, 16-byte aligned like a device allocation: an access past the end is visible to ASAN)
+  uint8_t* base = static_cast<uint8_t*>(aligned_alloc(16, static_cast<size_t>(p.total_bytes) + (p.total_bytes == 0 ? 16 : 0)));
+  if (!base) return -101;
+  memset(base, 0xA5, static_cast<size_t>(p.total_bytes));
+  struct Free { uint8_t* p; ~Free() { free(p); } } free_ws{base};
   int32_t* bounds_h = reinterpret_cast<int32_t*>(base + p.off_bounds_h);
   int32_t* kk_h = reinterpret_cast<int32_t*>(base + p.off_kk_h);
   int32_t* bounds_v = reinterpret_cast<int32_t*>(base + p.off_bounds_v);
@@ -47,8 +50,9 @@ extern "C" int emu_image_preprocess(const uint8_t* src, int n, int in_h, int in_
   }
   if (p.do_h) {  // resample_h_kernel<<<grid, kHThreads, smem_row_bytes * tile_rows>>>
     const int gx = (out_w + p.tile_w - 1) / p.tile_w, gy = (p.rows + p.tile_rows - 1) / p.tile_rows;
-    std::vector<uint8_t> smem_store(static_cast<size_t>(p.smem_row_bytes) * p.tile_rows + 16);
-    uint8_t* smem = smem_store.data() + ((16 - (reinterpret_cast<uintptr_t>(smem_store.data()) & 15)) & 15);
+    uint8_t* smem = static_cast<uint8_t*>(aligned_alloc(16, static_cast<size_t>(p.smem_row_bytes) * p.tile_rows));
+    if (!smem) return -101;
+    struct FreeS { uint8_t* p; ~FreeS() { free(p); } } free_smem{smem};
     for (int bz = 0; bz < n; ++bz)
       for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {

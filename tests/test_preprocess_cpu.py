@@ -320,3 +320,18 @@ def test_reference_asset_through_all_three_processors(emu):
     back = np.asarray(T.ToPILImage()((x[None] * half + half)[0]))
     assert np.array_equal(po.postprocess(x.numpy()), back)
     assert np.abs(back.astype(int) - img.astype(int)).max() <= 1  # truncation may lose one level, never more
+
+
+def test_device_code_is_memory_safe(tmp_path):
+    """The same device code under AddressSanitizer + UBSan with exact-size buffers (tests/native/preprocess_asan.cpp)."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "preprocess_asan"
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+                            "-ffp-contract=off", "-std=c++17", "-Wall", "-o", str(exe),
+                            os.path.join(ROOT, "tests", "native", "preprocess_asan.cpp")], capture_output=True, text=True)
+    if build.returncode != 0 and "asan" in (build.stderr or "").lower():
+        pytest.skip("sanitizer runtime not installed")
+    assert build.returncode == 0, build.stderr[-2000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "asan ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
