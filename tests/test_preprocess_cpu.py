@@ -335,3 +335,21 @@ def test_device_code_is_memory_safe(tmp_path):
     assert build.returncode == 0, build.stderr[-2000:]
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "asan ok" in r.stdout, r.stdout[-1000:] + r.stderr[-3000:]
+
+
+def test_reference_processor_names_and_defaults():
+    """processing_bailingmm.py:80-123: class names, constructor defaults (CLIP statistics, 224) and the 0.5 / 0.5
+    instances BailingMMProcessor creates (:175-176)."""
+    from ming_univision_b200.processing_bailingmm import (MingTokCenterCropProcessor, MingTokUndProcessor,
+                                                          install_gpu_image_processors)
+
+    und, gen = MingTokUndProcessor(), MingTokCenterCropProcessor()
+    for p in (und, gen):
+        assert p.image_size == 224 and p.mean == CLIP_MEAN and p.std == CLIP_STD
+
+    class Holder:
+        vis_processor = gen_processor = None
+
+    h = install_gpu_image_processors(Holder())
+    assert (h.vis_processor.image_size, h.gen_processor.image_size) == (1024, 512)
+    assert h.vis_processor.mean == HALF and h.gen_processor.std == HALF
