@@ -316,6 +316,12 @@ int mb_image_preprocess_u8(const void* src, int n, int in_h, int in_w, int res_h
  * separately, ToPILImage's truncation toward zero (saturating outside [0, 255]). */
 int mb_image_postprocess_u8(const void* img, int img_is_fp32, int n, int h, int w, float mean0, float mean1,
                             float mean2, float std0, float std1, float std2, void* out, void* stream);
+/* The tail of forward_pixel_decoder (modeling_mingtok.py:190-196: unpatchify, clamp_(-1, 1)) fused with tensor_to_pil:
+ * x [B, g*g, p*p*3] bf16 (rows of the head GEMM, channel-last inside the patch) -> out [B, g*p, g*p, 3] u8, identical
+ * to mb_unpatchify_clamp followed by mb_image_postprocess_u8; the image never exists as a float tensor and 3 bytes per
+ * pixel leave the device. */
+int mb_unpatchify_to_u8(const void* x, void* out, int B, int g, int p, float mean0, float mean1, float mean2,
+                        float std0, float std1, float std2, void* stream);
 
 #ifdef __cplusplus
 }

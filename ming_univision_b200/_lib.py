@@ -54,6 +54,7 @@ SIGNATURES = {
     "mb_image_preprocess_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _i, _vp, _i64,
                                _vp],
     "mb_image_postprocess_u8": [_vp, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _vp],
+    "mb_unpatchify_to_u8": [_vp, _vp, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp],
     "mb_pack_swiglu_rows": [_vp, _vp, _i, _i, _i, _vp],
     "mb_layernorm": [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _f, _i, _i, _i64, _vp],
     "mb_attn_hd64": [_vp, _vp, _i, _i, _i, _f, _i, _vp],

@@ -8,6 +8,7 @@
 //                               thread, only the columns and rows the crop keeps) -> u8 scratch [n, rows, out_w, 3]
 //                            -> vertical pass fused with crop + /255 + (x - mean) / std + NCHW store (bf16 or fp32)
 //   mb_image_postprocess_u8: [n, 3, h, w] in [-1, 1] -> [n, h, w, 3] u8
+//   mb_unpatchify_to_u8    : the pixel decoder's head rows -> unpatchify + clamp + the same u8 conversion in ONE pass
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -67,6 +68,16 @@ __global__ void __launch_bounds__(256) image_to_u8_kernel(const void* __restrict
                          : __bfloat162float(static_cast<const __nv_bfloat16*>(img_)[src]);
     out[i * 3 + c] = mbpre::denormalize_to_u8(x, mean[c], stdv[c]);
   }
+}
+
+__global__ void __launch_bounds__(256) unpatchify_to_u8_kernel(const uint16_t* __restrict__ x,
+                                                               uint8_t* __restrict__ out, int g, int p,
+                                                               int64_t total_pix, float m0, float m1, float m2,
+                                                               float s0, float s1, float s2) {
+  const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total_pix;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    mbpre::unpatchify_u8_pixel(x, g, p, idx, mean, stdv, out);
 }
 
 }  // namespace
@@ -147,6 +158,21 @@ extern "C" int mb_image_postprocess_u8(const void* img, int img_is_fp32, int n, 
   else
     image_to_u8_kernel<false><<<blocks, 256, 0, stream>>>(img, static_cast<uint8_t*>(out), n_px, plane, mean0, mean1,
                                                           mean2, std0, std1, std2);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_unpatchify_to_u8(const void* x, void* out, int B, int g, int p, float mean0, float mean1,
+                                   float mean2, float std0, float std1, float std2, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_unpatchify_to_u8: no sm_100 device");
+  MB_CHECK_ARG(B >= 0 && g >= 1 && p >= 1, MB_ERR_SHAPE, "mb_unpatchify_to_u8: invalid shape B=%d g=%d p=%d", B, g, p);
+  const int64_t total = static_cast<int64_t>(B) * g * p * g * p;  // pixels; each thread writes 3 adjacent bytes
+  if (total == 0) return MB_OK;
+  const int64_t want = (total + 255) / 256;
+  const int cap = num_sms() * 16;
+  unpatchify_to_u8_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0, stream>>>(
+      static_cast<const uint16_t*>(x), static_cast<uint8_t*>(out), g, p, total, mean0, mean1, mean2, std0, std1, std2);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

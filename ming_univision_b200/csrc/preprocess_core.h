@@ -362,4 +362,32 @@ MBP_HD void v_pixel(const Plan& p, const uint8_t* src, const uint8_t* temp, cons
   out3[2] = normalize_u8(u2, mean[2], stdv[2]);
 }
 
+// ---- pixel-decoder tail fused with the u8 conversion (unpatchify -> clamp(-1, 1) -> tensor_to_pil)
+
+MBP_HD float bf16_bits_to_float(uint16_t bits) {
+  union {
+    uint32_t u;
+    float f;
+  } cvt;
+  cvt.u = static_cast<uint32_t>(bits) << 16;
+  return cvt.f;
+}
+
+// Output pixel idx over [B, HW, HW] of the head GEMM's rows x [B, g*g, p*p*3] (bf16 bit patterns; channel-last inside a
+// patch, vision_transformer.py:515-527): clamp as modeling_mingtok.py:194, then trunc((v*std + mean) * 255).
+MBP_HD void unpatchify_u8_pixel(const uint16_t* x, int g, int p, int64_t idx, const float mean[3], const float stdv[3],
+                                uint8_t* out) {
+  const int HW = g * p;
+  const int xw = static_cast<int>(idx % HW);
+  const int yh = static_cast<int>((idx / HW) % HW);
+  const int64_t b = idx / (static_cast<int64_t>(HW) * HW);
+  const int h = yh / p, pp = yh % p, w = xw / p, q = xw % p;
+  const int64_t src = ((b * g * g + static_cast<int64_t>(h) * g + w) * (p * p) + pp * p + q) * 3;
+  for (int c = 0; c < 3; ++c) {
+    float v = bf16_bits_to_float(x[src + c]);
+    v = v < -1.f ? -1.f : (v > 1.f ? 1.f : v);  // NaN passes through, as torch.clamp does; the cast below gives 0
+    out[idx * 3 + c] = denormalize_to_u8(v, mean[c], stdv[c]);
+  }
+}
+
 }  // namespace mbpre

@@ -456,7 +456,8 @@ class MingTok(PreTrainedModel):
     @torch.no_grad()
     def forward_pixel_decoder(self, x, out_dtype: torch.dtype = BF16):
         """modeling_mingtok.py:179-196: sem_to_pix + pixel shuffle, 24 full-attention blocks, LN, head, unpatchify,
-        clamp(-1, 1).  x: [B, n, 1024] -> [B, 3, H, W]."""
+        clamp(-1, 1).  x: [B, n, 1024] -> [B, 3, H, W] (bf16 / fp32), or with out_dtype=torch.uint8 the finished
+        [B, H, W, 3] pixels of `tensor_to_pil` (modeling_bailing_moe.py:84-90) straight from the head GEMM's rows."""
         pk = self._pack()
         pix, sem = self.pixel_decoder, self.semantic_decoder
         if x.dtype != BF16:
@@ -472,4 +473,6 @@ class MingTok(PreTrainedModel):
         _run_blocks(pk.pix_blocks, t, B, S, pix.num_heads, False)
         hn = ops.layernorm(t, pk.pix_nw, pk.pix_nb)
         y = ops.linear(hn, pk.head_w, pk.head_b)
+        if out_dtype == torch.uint8:  # [B, H, W, 3] pixels as tensor_to_pil would produce them (0.5 / 0.5 statistics)
+            return ops.unpatchify_to_u8(y, g * f, pix.patch_size)
         return ops.unpatchify_clamp(y, g * f, pix.patch_size, out_dtype)

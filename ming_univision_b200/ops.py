@@ -743,3 +743,19 @@ def image_postprocess(img: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.
                                            float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]),
                                            out.data_ptr(), _stream()), "mb_image_postprocess_u8")
     return out
+
+
+def unpatchify_to_u8(x: torch.Tensor, g: int, p: int, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> torch.Tensor:
+    """Head rows [B, g*g, p*p*3] bf16 -> uint8 [B, g*p, g*p, 3]: unpatchify + clamp(-1, 1) + `tensor_to_pil`'s
+    conversion in one pass (== image_postprocess(unpatchify_clamp(x)))."""
+    _check_bf16(x)
+    lib = _lib.load()
+    x = x.contiguous()
+    B = x.shape[0]
+    if x.shape[1] != g * g or x.shape[2] != p * p * 3:
+        raise ValueError(f"expected [B, {g * g}, {p * p * 3}], got {tuple(x.shape)}")
+    out = torch.empty((B, g * p, g * p, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.mb_unpatchify_to_u8(x.data_ptr(), out.data_ptr(), B, g, p, float(mean[0]), float(mean[1]),
+                                       float(mean[2]), float(std[0]), float(std[1]), float(std[2]), _stream()),
+               "mb_unpatchify_to_u8")
+    return out

@@ -96,3 +96,12 @@ extern "C" int emu_axis_coeffs(int in_size, int out_size, int32_t* bounds, int32
   for (int xx = 0; xx < out_size; ++xx) mbpre::axis_coeffs(g, in_size, xx, bounds + 2 * xx, kk + static_cast<long long>(xx) * g.ksize);
   return g.ksize;
 }
+
+// unpatchify_to_u8_kernel: grid-stride loop over the pixels of [B, g*p, g*p]
+extern "C" void emu_unpatchify_to_u8(const uint16_t* x, int B, int g, int p, const float* mean, const float* stdv,
+                                     uint8_t* out) {
+  const long long total = static_cast<long long>(B) * g * p * g * p;
+  const long long threads = 7 * 256;  // a grid smaller than the problem, so the stride loop is exercised
+  for (long long t = 0; t < threads; ++t)
+    for (long long idx = t; idx < total; idx += threads) mbpre::unpatchify_u8_pixel(x, g, p, idx, mean, stdv, out);
+}

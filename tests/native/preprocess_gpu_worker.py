@@ -131,6 +131,12 @@ def main():
     recon = model.forward_enc_dec(image)
     pil = tensor_to_pil(recon)
     assert pil.size == (128, 128) and pil.mode == "RGB"
+    # the fused tail: head rows -> u8 pixels in one pass == unpatchify_clamp followed by the u8 conversion
+    feats = model.forward(image)["x_norm_patchtokens"]
+    fused = model.forward_pixel_decoder(feats, out_dtype=torch.uint8)
+    for dt in (torch.bfloat16, torch.float32):
+        assert torch.equal(fused, ops.image_postprocess(model.forward_pixel_decoder(feats, out_dtype=dt))), dt
+    assert fused.shape == (1, 128, 128, 3) and np.array_equal(fused[0].cpu().numpy(), np.asarray(pil))
     torch.cuda.synchronize()
     print("demo flow ok", flush=True)
     print("preprocess worker ok", flush=True)

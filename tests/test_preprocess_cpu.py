@@ -353,3 +353,20 @@ def test_reference_processor_names_and_defaults():
     h = install_gpu_image_processors(Holder())
     assert (h.vis_processor.image_size, h.gen_processor.image_size) == (1024, 512)
     assert h.vis_processor.mean == HALF and h.gen_processor.std == HALF
+
+
+def test_emulated_unpatchify_to_u8_equals_unpatchify_clamp_then_tensor_to_pil(emu):
+    """mb_unpatchify_to_u8 == the reference's tail composed: unpatchify (vision_transformer.py:515-527: rows
+    [B, g*g, p*p*3], channel-last inside the patch) -> clamp_(-1, 1) (modeling_mingtok.py:194) -> tensor_to_pil."""
+    B, g, p = 2, 5, 4
+    gen = torch.Generator().manual_seed(4)
+    x = (torch.randn((B, g * g, p * p * 3), generator=gen) * 0.8).to(torch.bfloat16)
+    x[0, 0, :4] = torch.tensor([-1.5, 1.5, 1.0, -1.0], dtype=torch.bfloat16)
+    # the oracle's restatement of :515-527 (oracle/mingtok_oracle.py, pixel_decoder_forward)
+    img = torch.einsum("nhwpqc->nchpwq", x.float().reshape(B, g, g, p, p, 3)).reshape(B, 3, g * p, g * p).clamp(-1, 1)
+    want = np.stack([po.postprocess(img[i].numpy()) for i in range(B)])
+    bits = np.ascontiguousarray(x.view(torch.int16).numpy().view(np.uint16))
+    out = np.full((B, g * p, g * p, 3), 7, dtype=np.uint8)
+    emu.emu_unpatchify_to_u8(bits.ctypes.data_as(C.c_void_p), B, g, p, (C.c_float * 3)(*HALF), (C.c_float * 3)(*HALF),
+                             out.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, want)
