@@ -227,6 +227,15 @@ int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, 
 int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, void* q_out, void* kcache, void* vcache, int B,
                       int S, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev, int t_host, float rope_theta,
                       void* stream);
+/* The config-gated 3-D multimodal variant (`rope_scaling.type == "3D"`): BailingMoe3DRotaryEmbedding.forward (:413-425)
+ * + apply_multimodal_rotary_pos_emb (:463-469).  position_ids3: int32 [3, B, S] (temporal, height, width); frequency i
+ * of a head takes its angle from component 0 / 1 / 2 for i < sec0 / < sec0 + sec1 / else (the reference's sections
+ * [16, 24, 24] doubled over both halves).  cos / sin stay fp32 here, so q and k are rounded to bf16 once, after
+ * q*cos + rotate_half(q)*sin in fp32 (the 1-D legacy path above rounds the tables and every product to bf16).
+ * Layouts, cache slots and t_dev / t_host as mb_rope_kv_append. */
+int mb_rope3d_kv_append(const void* qkv, const int32_t* position_ids3, void* q_out, void* kcache, void* vcache, int B,
+                        int S, int H, int Hkv, int hd, int Tmax, const int32_t* t_dev, int t_host, float rope_theta,
+                        int sec0, int sec1, int sec2, void* stream);
 /* GQA attention for q_len == 1 (head_dim 128) over cache slots 0 .. T-1, skipping keys whose key_mask[b, j] == 0
  * (the 2-D padding mask of the CFG rows; _upad_input / flash_attn_varlen_func :1009-1045, eager :795-812).
  * key_mask may be NULL; mask_stride = elements between rows of key_mask.  n_splits > 1 spreads the keys of every head

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],
     "mb_rmsnorm": [_vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp],
     "mb_rope_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
+    "mb_rope3d_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _i, _i, _i, _vp],
     "mb_attn_decode_gqa": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _vp, _i, _vp],
     "mb_argmax_f32": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "mb_router_topk": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

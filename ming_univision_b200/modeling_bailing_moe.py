@@ -9,7 +9,8 @@ reference's ``mingunivision/modeling_bailing_moe.py`` for the rows of SURVEY.md 
 Every operator runs in libmingb200.so (ops.py); the nn.Modules only own parameters.  Token counts on this path are
 tiny (CFG rows B <= 3 per step, prompts of tens of tokens), so all linears go through the HBM-streaming kernel for
 <= 8 rows and through the tcgen05 GEMM otherwise; routed experts are grouped by expert on the device (no host sync —
-the reference's `tokens_per_expert.cpu()` at :616 is gone).  1-D legacy RoPE (rope_scaling=None).
+the reference's `tokens_per_expert.cpu()` at :616 is gone).  1-D legacy RoPE (rope_scaling=None); the
+3-D M-RoPE variant is config-gated (forward_tokens with position_ids [3, B, S]).
 KV caches are static [Bmax, Hkv, Tmax, hd] tensors written in place.  Inference only, bf16.
 """
 from __future__ import annotations
@@ -402,7 +403,17 @@ class BailingMoeModel(nn.Module):
             raise NotImplementedError("multi-token forward needs an all-ones key mask (causal prefill; a later round's "
                                       "prompt appended behind the cached context)")
         h = inputs_embeds.to(BF16).reshape(B * S, D).contiguous().clone()
-        pos = position_ids.reshape(-1).to(torch.int32).contiguous()
+        # 3-D multimodal RoPE (rope_scaling.type == "3D", :413-425 / :463-469) is config-gated: position_ids [3, B, S]
+        mrope = position_ids.dim() == 3
+        if mrope:
+            rs = cfg.rope_scaling
+            # (transformers 5 normalises rope_scaling into a dict with a `rope_type` key; the reference reads `type`)
+            is3d = isinstance(rs, dict) and "3D" in (rs.get("type"), rs.get("rope_type"))
+            if not is3d or tuple(position_ids.shape) != (3, B, S):
+                raise ValueError("3-D position_ids [3, B, S] need config.rope_scaling = {'type': '3D', ...}")
+            pos = position_ids.reshape(3, B * S).to(torch.int32).contiguous()
+        else:
+            pos = position_ids.reshape(-1).to(torch.int32).contiguous()
         eps = cfg.rms_norm_eps
         im = None if image_mask is None else image_mask.reshape(-1)
         for li, (lp, lyr) in enumerate(zip(pk["layers"], self.layers)):
@@ -411,7 +422,11 @@ class BailingMoeModel(nn.Module):
             else:
                 qkv = _dense(ops.rmsnorm(h, lp["ln1"], eps), lp["qkv_w"], lp["qkv_b"])
             # rows 0..B-1 of the [Bmax, Hkv, Tmax, hd] cache are a contiguous prefix the kernels index directly
-            q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta, t_dev)
+            if mrope:
+                q = ops.rope3d_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta,
+                                         (16, 24, 24), t_dev)  # the reference's hard-wired sections (:463)
+            else:
+                q = ops.rope_kv_append(qkv, pos, cache.k[li], cache.v[li], B, S, H, t0, cfg.rope_theta, t_dev)
             if S == 1:
                 a = ops.attn_decode_gqa(q, cache.k[li], cache.v[li], key_mask, H, t0 + 1, t_dev)
             else:

@@ -457,6 +457,24 @@ def rope_kv_append(qkv: torch.Tensor, position_ids: torch.Tensor, kcache: torch.
     return q
 
 
+def rope3d_kv_append(qkv: torch.Tensor, position_ids3: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor,
+                     B: int, S: int, H: int, t: int, rope_theta: float, mrope_section=(16, 24, 24),
+                     t_dev: torch.Tensor | None = None) -> torch.Tensor:
+    """The 3-D M-RoPE variant of rope_kv_append: position_ids3 int32 [3, B*S] (temporal, height, width)."""
+    _check_bf16(qkv, kcache, vcache)
+    if position_ids3.dtype != torch.int32 or position_ids3.shape != (3, B * S) or not position_ids3.is_contiguous():
+        raise ValueError(f"position_ids3 must be a contiguous int32 [3, {B * S}] tensor")
+    lib = _lib.load()
+    _, Hkv, Tmax, hd = kcache.shape
+    s0, s1, s2 = (int(v) for v in mrope_section)
+    q = torch.empty((B * S, H * hd), dtype=BF16, device=qkv.device)
+    rc = lib.mb_rope3d_kv_append(qkv.data_ptr(), _iptr(position_ids3), q.data_ptr(), kcache.data_ptr(),
+                                 vcache.data_ptr(), B, S, H, Hkv, hd, Tmax, _iptr(t_dev), int(t), float(rope_theta),
+                                 s0, s1, s2, _stream())
+    _lib.check(rc, "mb_rope3d_kv_append")
+    return q
+
+
 def attn_decode_gqa(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, key_mask: torch.Tensor | None,
                     H: int, T: int, t_dev: torch.Tensor | None = None) -> torch.Tensor:
     """q [B, H*128] against cache slots 0..T-1 (key_mask int32 [B, >=T], 0 = skip).  Contexts longer than a few

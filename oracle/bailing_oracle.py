@@ -7,7 +7,8 @@ forward_for_image_generation_inner :1622-1673, generate_image :1844-1965).
 TEST INFRASTRUCTURE — NOT PRODUCT CODE (rules in oracle/mingtok_oracle.py).  Pinned against the unmodified reference
 by tests/golden/make_golden_llm.py -> tests/golden/llm_tiny.npz.  `sd` uses the reference's state_dict keys of
 BailingMoeForCausalLM (model.layers.{l}.attention.query_key_value.weight, ...); `cfg` is a dict with the
-BailingMoeConfig field names.  RoPE is the 1-D legacy variant (rope_scaling=None).
+BailingMoeConfig field names.  RoPE is the 1-D legacy variant (rope_scaling=None); the 3-D M-RoPE
+variant is restated separately (mrope_tables / apply_mrope) for the config-gated kernel.
 """
 from __future__ import annotations
 
@@ -38,6 +39,26 @@ def rope_tables(head_dim, base, seq_len):
 def rotate_half(x):
     x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
     return torch.cat((-x2, x1), dim=-1)
+
+
+def mrope_tables(head_dim, base, position_ids3):
+    """BailingMoe3DRotaryEmbedding.forward — :413-425 (the config-gated `rope_scaling.type == "3D"` variant, SURVEY.md
+    §0.4): position_ids3 [3, B, S] (temporal, height, width) -> fp32 cos / sin [3, B, S, head_dim], never cast down."""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2).float() / head_dim))
+    freqs = position_ids3[..., None].float() * inv_freq  # the reference's [dim/2, 1] @ [1, S] matmul: one product each
+    emb = torch.cat((freqs, freqs), dim=-1)
+    return emb.cos(), emb.sin()
+
+
+def apply_mrope(q, k, cos, sin, mrope_section=(16, 24, 24)):
+    """apply_multimodal_rotary_pos_emb — :463-469: the head dimension is cut into sections [16, 24, 24, 16, 24, 24] and
+    section i takes its angles from position component i % 3.  q [B, H, S, hd], k [B, Hkv, S, hd] (bf16 or fp32);
+    cos / sin fp32 [3, B, S, hd].  The products promote to fp32 and the results STAY fp32 (the attention casts them to
+    the compute dtype afterwards, :946-975), i.e. one rounding at the very end."""
+    sec = list(mrope_section) * 2
+    cos = torch.cat([m[i % 3] for i, m in enumerate(cos.split(sec, dim=-1))], dim=-1).unsqueeze(1)
+    sin = torch.cat([m[i % 3] for i, m in enumerate(sin.split(sec, dim=-1))], dim=-1).unsqueeze(1)
+    return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
 
 
 def causal_4d_mask(attention_mask, bsz, q_len, past_len, dtype=torch.float32):
