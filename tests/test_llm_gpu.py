@@ -2,7 +2,7 @@
 modules (BailingMoeForCausalLM.generate_image through MingUniVisionForConditionalGeneration) against the fp32 oracle and
 the golden outputs of the UNMODIFIED reference's own `generate_image` (tests/golden/llm_tiny.npz).
 
-Stated tolerances: hidden states / z / logits of one step: relative L2 <= 2e-2; latents, features and image after the
+Stated tolerances: hidden states / z / logits of one step: relative L2 <= 2e-2, logit max-abs-diff <= 0.1 (unit-scale logits); latents, features and image after the
 4-token AR loop with the RF sampler in the loop: relative L2 <= 5e-2 (bf16 everywhere vs an all-fp32 reference)."""
 import math
 import os
@@ -254,6 +254,9 @@ def test_prefill_and_cfg_step_vs_reference(tiny_model, cuda_device):
     logits = llm.compute_logit(h[:, -1])
     assert logits.dtype == torch.float32
     assert rel_l2(logits, torch.from_numpy(g["prefill_logits_last"])) < 2e-2
+    # logit max-abs-diff (the north-star's AR-step metric): the golden logits have unit scale (std 1.01, max 2.9), bf16
+    # weight rounding alone moves them by up to 0.02 (fp32 oracle with bf16-rounded weights); stated tolerance 0.1
+    assert float((logits.float().cpu() - torch.from_numpy(g["prefill_logits_last"])).abs().max()) < 0.1
     assert rel_l2(cache.k[0][0:1, :, :S], torch.from_numpy(g["prefill_k0"])) < 1e-2
     assert rel_l2(cache.v[1][0:1, :, :S], torch.from_numpy(g["prefill_v1"])) < 1e-2
     # one cached step, 2 CFG rows with a 2-D mask and per-row positions
