@@ -15,3 +15,7 @@ ls -la gpurun_out/ | tail -8
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_tc -s 40 -c 1 \
     -o gpurun_out/prof_attn_${TAG} -f python bench.py --steps 1 --warmup 3 > gpurun_out/ncu_attn_${TAG}.log 2>&1
 ls -la gpurun_out/ | tail -4
+# image pre-processing kernels: --set full of the horizontal and vertical passes on the 64-image batch
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:resample_ -c 6 \
+    -o gpurun_out/prof_preprocess_${TAG} -f python tools/bench_preprocess.py --iters 1 > gpurun_out/ncu_preprocess_${TAG}.log 2>&1
+ls -la gpurun_out/ | tail -3
