@@ -313,7 +313,9 @@ int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int T
  * torchvision's rule: short edge -> size, long edge = int(size * long / short)); (crop_top, crop_left, out_h, out_w) the
  * kept window of the resized image (the whole image when there is no crop).  Only the kept columns / rows are computed.
  * out: [n, 3, out_h, out_w] bf16 (out_is_fp32 = 0) or fp32.  workspace: >= mb_image_preprocess_workspace_bytes(...)
- * bytes, 16-byte aligned (coefficient tables + the u8 intermediate); no allocation, no host synchronisation. */
+ * bytes, 16-byte aligned (coefficient tables + the u8 intermediate); no allocation, no host synchronisation.
+ * MB_ERR_SHAPE for a crop window outside the resized image and for images more than 100 times taller than wide whose
+ * height shrinks (Pillow >= 11 resizes those height-first; the pass order shows in the u8 result). */
 int mb_image_preprocess_workspace_bytes(int n, int in_h, int in_w, int res_h, int res_w, int crop_top, int crop_left,
                                         int out_h, int out_w, int64_t* bytes);
 int mb_image_preprocess_u8(const void* src, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,

@@ -88,6 +88,9 @@ extern "C" int mb_image_preprocess_workspace_bytes(int n, int in_h, int in_w, in
                                                    int crop_left, int out_h, int out_w, int64_t* bytes) {
   Plan p;
   const int bad = mbpre::make_plan(n, in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w, &p);
+  MB_CHECK_ARG(bad != 5, MB_ERR_SHAPE,
+               "mb_image_preprocess_workspace_bytes: %dx%d is more than 100 times taller than wide and shrinks "
+               "vertically; Pillow resizes such images height-first, which this path does not reproduce", in_h, in_w);
   MB_CHECK_ARG(bad == 0 && bytes != nullptr, MB_ERR_SHAPE,
                "mb_image_preprocess_workspace_bytes: invalid geometry (check %d): in %dx%d resized %dx%d crop (%d,%d) "
                "%dx%d", bad, in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w);
@@ -103,6 +106,9 @@ extern "C" int mb_image_preprocess_u8(const void* src_, int n, int in_h, int in_
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_image_preprocess_u8: no sm_100 device");
   Plan p;
   const int bad = mbpre::make_plan(n, in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w, &p);
+  MB_CHECK_ARG(bad != 5, MB_ERR_SHAPE,
+               "mb_image_preprocess_u8: %dx%d is more than 100 times taller than wide and shrinks vertically; Pillow "
+               "resizes such images height-first, which this path does not reproduce", in_h, in_w);
   MB_CHECK_ARG(bad == 0, MB_ERR_SHAPE,
                "mb_image_preprocess_u8: invalid geometry (check %d): in %dx%d resized %dx%d crop (%d,%d) %dx%d", bad,
                in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w);

@@ -188,6 +188,10 @@ static inline int make_plan(int n, int in_h, int in_w, int res_h, int res_w, int
   if (n < 0 || in_h < 1 || in_w < 1 || res_h < 1 || res_w < 1 || out_h < 1 || out_w < 1) return 1;
   if (crop_top < 0 || crop_left < 0 || crop_top + out_h > res_h || crop_left + out_w > res_w) return 2;
   if (in_h > (1 << 24) || in_w > (1 << 24)) return 3;  // Pillow's box is float
+  // Pillow >= 11 runs the VERTICAL pass first for images more than 100 times taller than wide whose height shrinks
+  // (PIL/Image.py, Image.resize); the u8 rounding between the passes makes the order visible.  Not a photograph's
+  // geometry: refused rather than answered differently from the library.
+  if (static_cast<int64_t>(in_h) > static_cast<int64_t>(in_w) * 100 && res_h < in_h) return 5;
   p->n = n, p->in_h = in_h, p->in_w = in_w, p->res_h = res_h, p->res_w = res_w;
   p->crop_top = crop_top, p->crop_left = crop_left, p->out_h = out_h, p->out_w = out_w;
   p->do_h = res_w != in_w, p->do_v = res_h != in_h;

@@ -13,7 +13,8 @@ The arithmetic lives in third-party code that is NOT under /root/reference:
     src/libImaging/Resample.c — `precompute_coeffs` (antialiased: filter support scaled by the down-scale factor, Keys
     cubic a = -0.5, weights normalised in double), `normalize_coeffs_8bpc` (fixed point, 22 fractional bits, round half
     away from zero), `ImagingResampleHorizontal_8bpc` then `ImagingResampleVertical_8bpc` (int32 accumulation from
-    1 << 21, arithmetic shift, clip to u8 BETWEEN the two passes).  Restated below in numpy from its published algorithm.
+    1 << 21, arithmetic shift, clip to u8 BETWEEN the two passes); PIL/Image.py `Image.resize` (the pass order flips for
+    images more than 100 times taller than wide).  Restated below in numpy from its published algorithm.
   * torchvision 0.26 (`torchvision==0.22.0` in requirements.txt:2): `_compute_resized_output_size` (short edge -> size,
     long edge = int(size * long / short)), `center_crop` (offset = int(round((full - crop) / 2.0)), Python's half-to-even),
     `to_tensor` (u8 -> fp32, true division by 255), `normalize` ((x - mean) / std in fp32).
@@ -97,13 +98,32 @@ def resize_bicubic_u8(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
     if img.dtype != np.uint8 or img.ndim != 3:
         raise ValueError("expected a [H, W, C] uint8 image")
     h, w, _ = img.shape
-    if w != out_w:
-        bh, kh, _ = precompute_coeffs(w, out_w)
-        img = _resample_axis1(img, bh, kh)
-    if h != out_h:
-        bv, kv, _ = precompute_coeffs(h, out_h)
-        img = _resample_axis1(img.transpose(1, 0, 2), bv, kv).transpose(1, 0, 2)
+
+    def horizontal(a):
+        if a.shape[1] == out_w:
+            return a
+        bh, kh, _ = precompute_coeffs(a.shape[1], out_w)
+        return _resample_axis1(a, bh, kh)
+
+    def vertical(a):
+        if a.shape[0] == out_h:
+            return a
+        bv, kv, _ = precompute_coeffs(a.shape[0], out_h)
+        return _resample_axis1(a.transpose(1, 0, 2), bv, kv).transpose(1, 0, 2)
+
+    if vertical_pass_first(h, w, out_h):
+        img = horizontal(np.ascontiguousarray(vertical(img)))
+    else:
+        img = vertical(horizontal(img))
     return np.ascontiguousarray(img)
+
+
+def vertical_pass_first(h: int, w: int, out_h: int) -> bool:
+    """Pillow >= 11 (`Image.resize`, PIL/Image.py: `if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]`)
+    resizes images more than 100 times taller than wide in two calls, height first, when the height shrinks; the u8
+    rounding between the passes makes the order visible in the result.  Found by fuzzing the oracle against Pillow 12.2;
+    photographs never get there, and the device path refuses the geometry (MB_ERR_SHAPE) instead of guessing."""
+    return h > w * 100 and out_h < h
 
 
 def resized_output_size(h: int, w: int, size) -> tuple[int, int]:

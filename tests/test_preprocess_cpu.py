@@ -57,7 +57,11 @@ def golden():
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("h,w,oh,ow", [(64, 64, 32, 32), (100, 75, 37, 51), (33, 47, 80, 90), (300, 200, 512, 341),
                                        (517, 389, 256, 256), (64, 64, 64, 32), (64, 64, 128, 64), (7, 9, 3, 4),
-                                       (1, 1, 5, 5), (5, 5, 1, 1), (1000, 60, 17, 60), (640, 480, 20, 15)])
+                                       (1, 1, 5, 5), (5, 5, 1, 1), (1000, 60, 17, 60), (640, 480, 20, 15),
+                                       # more than 100 times taller than wide: Pillow >= 11 goes height-first when the
+                                       # height shrinks (PIL/Image.py, Image.resize) — and only then
+                                       (306, 3, 95, 203), (221, 2, 153, 278), (301, 3, 300, 7), (300, 3, 95, 203),
+                                       (306, 3, 400, 203), (3, 306, 203, 95)])
 def test_oracle_resize_matches_pillow(h, w, oh, ow):
     from PIL import Image
 
@@ -207,6 +211,21 @@ def test_emulated_device_path_is_bit_exact(emu, h, w, size, crop, mean, std):
     assert np.array_equal(got[0], torchvision_pipeline(imgs[0], size, crop, mean, std)), plan
     rh, rw = po.resized_output_size(h, w, size)
     assert plan["do_h"] == int(rw != w) and plan["do_v"] == int(rh != h)
+
+
+def test_height_first_geometry_is_refused(emu):
+    """Images more than 100 times taller than wide whose height shrinks: Pillow resizes them height-first (the oracle
+    follows, test_oracle_resize_matches_pillow); the device path refuses instead of answering differently."""
+    assert po.vertical_pass_first(306, 3, 95) and not po.vertical_pass_first(300, 3, 95)
+    assert not po.vertical_pass_first(306, 3, 400) and not po.vertical_pass_first(3, 306, 1)
+    assert emu.emu_workspace_bytes(1, 306, 3, 95, 203, 0, 0, 95, 203) == -1
+    assert emu.emu_workspace_bytes(1, 300, 3, 95, 203, 0, 0, 95, 203) > 0
+    assert emu.emu_workspace_bytes(1, 306, 3, 400, 203, 0, 0, 400, 203) > 0
+    from ming_univision_b200 import _lib
+
+    lib, nbytes = _lib.load(), C.c_int64(-1)
+    assert lib.mb_image_preprocess_workspace_bytes(1, 306, 3, 95, 203, 0, 0, 95, 203, C.byref(nbytes)) == -1
+    assert b"height-first" in lib.mb_last_error() and nbytes.value == -1
 
 
 def test_emulated_plan_narrows_the_tile(emu):
