@@ -312,7 +312,8 @@ int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int T
  * src: [n, in_h, in_w, 3] u8 (RGB, HWC) in device memory.  res_h x res_w is the size after Resize (the caller applies
  * torchvision's rule: short edge -> size, long edge = int(size * long / short)); (crop_top, crop_left, out_h, out_w) the
  * kept window of the resized image (the whole image when there is no crop).  Only the kept columns / rows are computed.
- * out: [n, 3, out_h, out_w] bf16 (out_is_fp32 = 0) or fp32.  workspace: >= mb_image_preprocess_workspace_bytes(...)
+ * out: [n, 3, out_h, out_w] bf16 (out_kind 0) or fp32 (out_kind 1), or — out_kind 2 — the resized + cropped image
+ * itself, [n, out_h, out_w, 3] u8 (Pillow's `Image.resize` + crop on the device; mean / std unused).  workspace: >= mb_image_preprocess_workspace_bytes(...)
  * bytes, 16-byte aligned (coefficient tables + the u8 intermediate); no allocation, no host synchronisation.
  * MB_ERR_SHAPE for a crop window outside the resized image and for images more than 100 times taller than wide whose
  * height shrinks (Pillow >= 11 resizes those height-first; the pass order shows in the u8 result). */
@@ -320,7 +321,7 @@ int mb_image_preprocess_workspace_bytes(int n, int in_h, int in_w, int res_h, in
                                         int out_h, int out_w, int64_t* bytes);
 int mb_image_preprocess_u8(const void* src, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,
                            int crop_left, int out_h, int out_w, float mean0, float mean1, float mean2, float std0,
-                           float std1, float std2, void* out, int out_is_fp32, void* workspace,
+                           float std1, float std2, void* out, int out_kind, void* workspace,
                            int64_t workspace_bytes, void* stream);
 /* `tensor_to_pil` (mingunivision/modeling_bailing_moe.py:84-90, test_infer_recon_image.py:24-28): img [n, 3, h, w]
  * (bf16, or fp32 with img_is_fp32) -> out [n, h, w, 3] u8 = trunc((x * std + mean) * 255), fp32 steps rounded

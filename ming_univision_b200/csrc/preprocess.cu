@@ -6,7 +6,8 @@
 //   mb_image_preprocess_u8 : coefficient tables (one thread per output column / row, IEEE double, no FMA contraction)
 //                            -> horizontal pass (input row segments staged in shared memory, one output pixel per
 //                               thread, only the columns and rows the crop keeps) -> u8 scratch [n, rows, out_w, 3]
-//                            -> vertical pass fused with crop + /255 + (x - mean) / std + NCHW store (bf16 or fp32)
+//                            -> vertical pass fused with crop + /255 + (x - mean) / std + NCHW store (bf16 or fp32),
+//                               or with a plain u8 HWC store (out_kind 2: PIL's Image.resize + crop on the device)
 //   mb_image_postprocess_u8: [n, 3, h, w] in [-1, 1] -> [n, h, w, 3] u8
 //   mb_unpatchify_to_u8    : the pixel decoder's head rows -> unpatchify + clamp + the same u8 conversion in ONE pass
 #include <cuda_bf16.h>
@@ -35,12 +36,20 @@ __global__ void __launch_bounds__(mbpre::kHThreads) resample_h_kernel(Plan p, co
   mbpre::h_phase_compute(p, src, bounds_h, kk_h, bx, by, bz, threadIdx.x, blockDim.x, smem, temp);
 }
 
-template <bool kF32>
+// kOut: 0 = bf16 NCHW, 1 = fp32 NCHW (both normalised), 2 = u8 HWC (the resized + cropped image itself)
+template <int kOut>
 __global__ void __launch_bounds__(mbpre::kVThreads) resample_v_normalize_kernel(
     Plan p, const uint8_t* __restrict__ src, const uint8_t* __restrict__ temp, const int32_t* __restrict__ bounds_v,
     const int32_t* __restrict__ kk_v, float m0, float m1, float m2, float s0, float s1, float s2, void* out_) {
   const int xl = blockIdx.x * blockDim.x + threadIdx.x, yy = blockIdx.y, img = blockIdx.z;
   if (xl >= p.out_w) return;
+  if (kOut == 2) {
+    uint8_t u[3];
+    mbpre::v_pixel_u8(p, src, temp, bounds_v, kk_v, img, yy, xl, u);
+    uint8_t* o = static_cast<uint8_t*>(out_) + ((static_cast<int64_t>(img) * p.out_h + yy) * p.out_w + xl) * 3;
+    o[0] = u[0], o[1] = u[1], o[2] = u[2];
+    return;
+  }
   const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
   float v[3];
   mbpre::v_pixel(p, src, temp, bounds_v, kk_v, img, yy, xl, mean, stdv, v);
@@ -48,7 +57,7 @@ __global__ void __launch_bounds__(mbpre::kVThreads) resample_v_normalize_kernel(
   const int64_t o = static_cast<int64_t>(img) * 3 * plane + static_cast<int64_t>(yy) * p.out_w + xl;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    if (kF32) static_cast<float*>(out_)[o + c * plane] = v[c];
+    if (kOut == 1) static_cast<float*>(out_)[o + c * plane] = v[c];
     else static_cast<__nv_bfloat16*>(out_)[o + c * plane] = __float2bfloat16_rn(v[c]);
   }
 }
@@ -100,7 +109,7 @@ extern "C" int mb_image_preprocess_workspace_bytes(int n, int in_h, int in_w, in
 
 extern "C" int mb_image_preprocess_u8(const void* src_, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,
                                       int crop_left, int out_h, int out_w, float mean0, float mean1, float mean2,
-                                      float std0, float std1, float std2, void* out, int out_is_fp32, void* workspace,
+                                      float std0, float std1, float std2, void* out, int out_kind, void* workspace,
                                       int64_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_image_preprocess_u8: no sm_100 device");
@@ -112,7 +121,9 @@ extern "C" int mb_image_preprocess_u8(const void* src_, int n, int in_h, int in_
   MB_CHECK_ARG(bad == 0, MB_ERR_SHAPE,
                "mb_image_preprocess_u8: invalid geometry (check %d): in %dx%d resized %dx%d crop (%d,%d) %dx%d", bad,
                in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w);
-  MB_CHECK_ARG(std0 != 0.f && std1 != 0.f && std2 != 0.f, MB_ERR_SHAPE, "mb_image_preprocess_u8: std must be non-zero");
+  MB_CHECK_ARG(out_kind >= 0 && out_kind <= 2, MB_ERR_SHAPE, "mb_image_preprocess_u8: out_kind must be 0, 1 or 2");
+  MB_CHECK_ARG(out_kind == 2 || (std0 != 0.f && std1 != 0.f && std2 != 0.f), MB_ERR_SHAPE,
+               "mb_image_preprocess_u8: std must be non-zero");
   MB_CHECK_ARG(workspace_bytes >= p.total_bytes, MB_ERR_SHAPE,
                "mb_image_preprocess_u8: workspace of %lld bytes, %lld needed", (long long)workspace_bytes,
                (long long)p.total_bytes);
@@ -140,11 +151,14 @@ extern "C" int mb_image_preprocess_u8(const void* src_, int n, int in_h, int in_
     MB_CHECK_CUDA(cudaGetLastError());
   }
   const dim3 vgrid((out_w + mbpre::kVThreads - 1) / mbpre::kVThreads, out_h, n);
-  if (out_is_fp32)
-    resample_v_normalize_kernel<true><<<vgrid, mbpre::kVThreads, 0, stream>>>(
+  if (out_kind == 1)
+    resample_v_normalize_kernel<1><<<vgrid, mbpre::kVThreads, 0, stream>>>(
+        p, src, temp, bounds_v, kk_v, mean0, mean1, mean2, std0, std1, std2, out);
+  else if (out_kind == 2)
+    resample_v_normalize_kernel<2><<<vgrid, mbpre::kVThreads, 0, stream>>>(
         p, src, temp, bounds_v, kk_v, mean0, mean1, mean2, std0, std1, std2, out);
   else
-    resample_v_normalize_kernel<false><<<vgrid, mbpre::kVThreads, 0, stream>>>(
+    resample_v_normalize_kernel<0><<<vgrid, mbpre::kVThreads, 0, stream>>>(
         p, src, temp, bounds_v, kk_v, mean0, mean1, mean2, std0, std1, std2, out);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;

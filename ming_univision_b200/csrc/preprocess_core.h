@@ -326,12 +326,12 @@ MBP_HD void h_phase_compute(const Plan& p, const uint8_t* src, const int32_t* bo
   }
 }
 
-// Vertical pass + crop + ToTensor + Normalize for output pixel (img, yy, xl); returns the three channel values.
+// Vertical pass + crop for output pixel (img, yy, xl): the u8 channel values (v_pixel_u8: what Pillow's resize + the
+// crop hold) and their ToTensor + Normalize (v_pixel).
 // `in` is the horizontal pass's output (row pitch out_w, rows [row0, row0 + rows)) or, when Pillow skips that pass,
 // the source itself (row pitch in_w, column offset crop_left).
-MBP_HD void v_pixel(const Plan& p, const uint8_t* src, const uint8_t* temp, const int32_t* bounds_v,
-                    const int32_t* kk_v, int img, int yy, int xl, const float mean[3], const float stdv[3],
-                    float out3[3]) {
+MBP_HD void v_pixel_u8(const Plan& p, const uint8_t* src, const uint8_t* temp, const int32_t* bounds_v,
+                       const int32_t* kk_v, int img, int yy, int xl, uint8_t u[3]) {
   const uint8_t* base;
   int64_t pitch;  // bytes per row
   int row_origin;
@@ -361,9 +361,17 @@ MBP_HD void v_pixel(const Plan& p, const uint8_t* src, const uint8_t* temp, cons
     const uint8_t* px = base + (p.crop_top + yy - row_origin) * pitch;
     u0 = px[0], u1 = px[1], u2 = px[2];
   }
-  out3[0] = normalize_u8(u0, mean[0], stdv[0]);
-  out3[1] = normalize_u8(u1, mean[1], stdv[1]);
-  out3[2] = normalize_u8(u2, mean[2], stdv[2]);
+  u[0] = u0, u[1] = u1, u[2] = u2;
+}
+
+MBP_HD void v_pixel(const Plan& p, const uint8_t* src, const uint8_t* temp, const int32_t* bounds_v,
+                    const int32_t* kk_v, int img, int yy, int xl, const float mean[3], const float stdv[3],
+                    float out3[3]) {
+  uint8_t u[3];
+  v_pixel_u8(p, src, temp, bounds_v, kk_v, img, yy, xl, u);
+  out3[0] = normalize_u8(u[0], mean[0], stdv[0]);
+  out3[1] = normalize_u8(u[1], mean[1], stdv[1]);
+  out3[2] = normalize_u8(u[2], mean[2], stdv[2]);
 }
 
 // ---- pixel-decoder tail fused with the u8 conversion (unpatchify -> clamp(-1, 1) -> tensor_to_pil)

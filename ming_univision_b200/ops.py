@@ -712,15 +712,16 @@ def image_preprocess(images: torch.Tensor, size, crop: int | tuple[int, int] | N
                      mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5), out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
     """Resize(size, bicubic, Pillow's antialiased 8-bit resample) [-> CenterCrop(crop)] -> ToTensor -> Normalize on the
     device: images uint8 [N, H, W, 3] (or [H, W, 3]) RGB on CUDA -> [N, 3, h, w] `out_dtype` (fp32: identical to the
-    torchvision pipeline on PIL images; bf16: its round-to-nearest)."""
+    torchvision pipeline on PIL images; bf16: its round-to-nearest; uint8: the resized + cropped image itself,
+    [N, h, w, 3], without ToTensor / Normalize)."""
     if images.dtype != torch.uint8 or not images.is_cuda:
         raise TypeError(f"expected a CUDA uint8 tensor, got {images.dtype} on {images.device}")
     if images.dim() == 3:
         images = images.unsqueeze(0)
     if images.dim() != 4 or images.shape[-1] != 3:
         raise ValueError(f"expected [N, H, W, 3] RGB images, got {tuple(images.shape)}")
-    if out_dtype not in (torch.float32, BF16):
-        raise TypeError("out_dtype must be float32 or bfloat16")
+    if out_dtype not in (torch.float32, BF16, torch.uint8):
+        raise TypeError("out_dtype must be float32, bfloat16 or uint8")
     images = images.contiguous()
     n, h, w, _ = images.shape
     rh, rw = resized_output_size(h, w, size)
@@ -736,12 +737,21 @@ def image_preprocess(images: torch.Tensor, size, crop: int | tuple[int, int] | N
     _lib.check(lib.mb_image_preprocess_workspace_bytes(n, h, w, rh, rw, top, left, oh, ow, ctypes.byref(nbytes)),
                "mb_image_preprocess_workspace_bytes")
     ws = torch.empty((max(16, nbytes.value),), dtype=torch.uint8, device=images.device)
-    out = torch.empty((n, 3, oh, ow), dtype=out_dtype, device=images.device)
+    kind = {BF16: 0, torch.float32: 1, torch.uint8: 2}[out_dtype]
+    shape = (n, oh, ow, 3) if kind == 2 else (n, 3, oh, ow)
+    out = torch.empty(shape, dtype=out_dtype, device=images.device)
     _lib.check(lib.mb_image_preprocess_u8(images.data_ptr(), n, h, w, rh, rw, top, left, oh, ow, float(mean[0]),
                                           float(mean[1]), float(mean[2]), float(std[0]), float(std[1]), float(std[2]),
-                                          out.data_ptr(), int(out_dtype == torch.float32), ws.data_ptr(), ws.numel(),
-                                          _stream()), "mb_image_preprocess_u8")
+                                          out.data_ptr(), kind, ws.data_ptr(), ws.numel(), _stream()),
+               "mb_image_preprocess_u8")
     return out
+
+
+def image_resize_u8(images: torch.Tensor, size, crop: int | tuple[int, int] | None = None) -> torch.Tensor:
+    """Pillow's `Image.resize(BICUBIC)` (+ torchvision's centre crop) on the device, u8 in / u8 out: uint8 [N, H, W, 3]
+    -> uint8 [N, h, w, 3], bit-identical with the library (the resize `fetch_image` applies before the processors,
+    mingunivision/bailingmm_utils.py:162, is this call with size = (resized_height, resized_width))."""
+    return image_preprocess(images, size, crop, out_dtype=torch.uint8)
 
 
 def image_postprocess(img: torch.Tensor, mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5)) -> torch.Tensor:

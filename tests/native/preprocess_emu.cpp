@@ -18,12 +18,12 @@ extern "C" long long emu_workspace_bytes(int n, int in_h, int in_w, int res_h, i
   return p.total_bytes;
 }
 
-// out: fp32 [n, 3, out_h, out_w]; u8_out (optional): the resized + cropped u8 image [n, out_h, out_w, 3] is not
-// produced by the device path (it normalises in the same kernel), so the test inverts the normalisation instead.
+// out: fp32 [n, 3, out_h, out_w] (out_kind 1); u8_out (optional): the resized + cropped u8 image [n, out_h, out_w, 3]
+// (out_kind 2).
 // plan_out (optional, 8 ints): do_h, do_v, ksize_h, ksize_v, row0, rows, tile_w, tile_rows.
-extern "C" int emu_image_preprocess(const uint8_t* src, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,
-                                    int crop_left, int out_h, int out_w, const float* mean, const float* stdv,
-                                    float* out, int* plan_out) {
+extern "C" int emu_image_preprocess_ex(const uint8_t* src, int n, int in_h, int in_w, int res_h, int res_w,
+                                       int crop_top, int crop_left, int out_h, int out_w, const float* mean,
+                                       const float* stdv, float* out, uint8_t* u8_out, int* plan_out) {
   Plan p;
   const int bad = mbpre::make_plan(n, in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w, &p);
   if (bad) return -bad;
@@ -76,8 +76,20 @@ extern "C" int emu_image_preprocess(const uint8_t* src, int n, int in_h, int in_
           float v[3];
           mbpre::v_pixel(p, src, temp, bounds_v, kk_v, img, yy, xl, mean, stdv, v);
           for (int c = 0; c < 3; ++c) out[(img * 3LL + c) * plane + static_cast<long long>(yy) * out_w + xl] = v[c];
+          if (u8_out) {  // resample_v_normalize_kernel<2>: the u8 image itself, HWC
+            uint8_t u[3];
+            mbpre::v_pixel_u8(p, src, temp, bounds_v, kk_v, img, yy, xl, u);
+            for (int c = 0; c < 3; ++c) u8_out[((static_cast<long long>(img) * out_h + yy) * out_w + xl) * 3 + c] = u[c];
+          }
         }
   return 0;
+}
+
+extern "C" int emu_image_preprocess(const uint8_t* src, int n, int in_h, int in_w, int res_h, int res_w, int crop_top,
+                                    int crop_left, int out_h, int out_w, const float* mean, const float* stdv,
+                                    float* out, int* plan_out) {
+  return emu_image_preprocess_ex(src, n, in_h, in_w, res_h, res_w, crop_top, crop_left, out_h, out_w, mean, stdv, out,
+                                 nullptr, plan_out);
 }
 
 // image_to_u8_kernel<true>

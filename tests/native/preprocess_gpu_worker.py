@@ -50,6 +50,13 @@ def main():
             ref = torch.from_numpy(po.preprocess(imgs[i], size, crop, mean, std))
             assert torch.equal(got[i].cpu(), ref), ("fp32 mismatch", h, w, size, crop, i)
             assert torch.equal(got16[i].cpu(), ref.to(torch.bfloat16)), ("bf16 mismatch", h, w, size, crop, i)
+        u8 = ops.image_resize_u8(d, size, crop)  # the resized + cropped image itself (out_kind 2)
+        rh, rw = po.resized_output_size(h, w, size)
+        want = po.resize_bicubic_u8(imgs[0], rh, rw)
+        if crop is not None:
+            t, l = po.center_crop_offsets(rh, rw, crop, crop)
+            want = want[t:t + crop, l:l + crop]
+        assert u8.dtype == torch.uint8 and np.array_equal(u8[0].cpu().numpy(), want), ("u8 mismatch", h, w, size, crop)
         print("preprocess ok", (h, w, size, crop), flush=True)
 
     # 2. golden vectors produced by Pillow / torchvision

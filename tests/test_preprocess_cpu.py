@@ -228,6 +228,24 @@ def test_height_first_geometry_is_refused(emu):
     assert b"height-first" in lib.mb_last_error() and nbytes.value == -1
 
 
+def test_emulated_u8_output_is_pillows_resize(emu):
+    """out_kind 2: the resized + cropped u8 image itself == PIL's Image.resize (+ crop), e.g. fetch_image's resize
+    (bailingmm_utils.py:162) on the device."""
+    from PIL import Image
+
+    rng = np.random.default_rng(8)
+    for h, w, oh, ow, top, left, ch, cw in [(300, 400, 224, 308, 0, 0, 224, 308), (97, 131, 64, 86, 0, 11, 64, 64),
+                                            (50, 60, 120, 150, 7, 9, 100, 100), (64, 64, 64, 32, 0, 0, 64, 32)]:
+        img = synthetic_photo(rng, h, w)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BICUBIC))[top:top + ch, left:left + cw]
+        f32 = np.empty((1, 3, ch, cw), dtype=np.float32)
+        u8 = np.full((1, ch, cw, 3), 9, dtype=np.uint8)
+        rc = emu.emu_image_preprocess_ex(np.ascontiguousarray(img[None]).ctypes.data_as(C.c_void_p), 1, h, w, oh, ow, top,
+                                         left, ch, cw, (C.c_float * 3)(*HALF), (C.c_float * 3)(*HALF),
+                                         f32.ctypes.data_as(C.c_void_p), u8.ctypes.data_as(C.c_void_p), None)
+        assert rc == 0 and np.array_equal(u8[0], ref)
+
+
 def test_emulated_plan_narrows_the_tile(emu):
     imgs = np.zeros((1, 40, 2600, 3), dtype=np.uint8)
     _, plan = emu_preprocess(emu, imgs, (40, 3), None)
