@@ -122,3 +122,45 @@ def test_generate_rejects_misuse(stubbed):
     with pytest.raises(ValueError):  # a later round whose masks do not line up with the cached context
         m.past_attention_mask = m.past_attention_mask[:, :-1]
         m.generate(torch.zeros((1, 3), dtype=torch.long), max_new_tokens=1)
+
+
+def test_committed_bench_line_keeps_the_contract():
+    """profiles/r01e_bench.json is a line bench.py printed on a B200: it must carry every key of the measurement contract
+    (metric / value / e2e / roofline / cpu_baseline / clocks / gpu_launches) with consistent numbers, and the reference
+    arm must print the same metric with its own keys — a guard against editing bench.py out of the contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "profiles", "r01e_bench.json")) as f:
+        d = json.load(f)
+    with open(os.path.join(root, "BASELINE.json")) as f:
+        base = json.load(f)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"].split(" (")[0] in base["metric"] and d["unit"] == "tokens/s" and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and base["published"] == {}          # no published number for this metric
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+    tokens = d["config"]["tokens_per_step"]
+    assert abs(d["value"] - tokens / d["ms_per_step"] * 1e3) / d["value"] < 1e-6      # value == units / time
+    e2e = d["e2e"]
+    assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] <= d["value"] * 1.02
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
+    # the reference arm of the live bench.py (CPU, one tiny step)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == d["metric"] and line["unit"] == d["unit"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["value"] == line["value"] and line["config"]["workload"] == d["config"]["workload"]
