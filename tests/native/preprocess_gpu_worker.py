@@ -59,6 +59,11 @@ def main():
         assert u8.dtype == torch.uint8 and np.array_equal(u8[0].cpu().numpy(), want), ("u8 mismatch", h, w, size, crop)
         print("preprocess ok", (h, w, size, crop), flush=True)
 
+    # empty batch: no launch, empty result
+    empty = ops.image_preprocess(torch.zeros((0, 50, 60, 3), dtype=torch.uint8, device=dev), 32, 32)
+    assert empty.shape == (0, 3, 32, 32)
+    assert ops.image_postprocess(torch.zeros((0, 3, 8, 8), device=dev)).shape == (0, 8, 8, 3)
+
     # 2. golden vectors produced by Pillow / torchvision
     g = np.load(os.path.join(ROOT, "tests", "golden", "preprocess.npz"))
     for c in json.loads(str(g["cases"])):

@@ -246,6 +246,11 @@ def test_emulated_u8_output_is_pillows_resize(emu):
         assert rc == 0 and np.array_equal(u8[0], ref)
 
 
+def test_emulated_empty_batch(emu):
+    out, plan = emu_preprocess(emu, np.zeros((0, 50, 60, 3), dtype=np.uint8), 32, 32)
+    assert out.shape == (0, 3, 32, 32) and plan["do_h"] == 1 and plan["do_v"] == 1
+
+
 def test_emulated_plan_narrows_the_tile(emu):
     imgs = np.zeros((1, 40, 2600, 3), dtype=np.uint8)
     _, plan = emu_preprocess(emu, imgs, (40, 3), None)
