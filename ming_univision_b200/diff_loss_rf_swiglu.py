@@ -20,7 +20,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _packs, ops
 
 BF16 = torch.bfloat16
 
@@ -143,19 +143,20 @@ class RectifiedFlowLoss(nn.Module):
         self.use_cuda_graph = True
         self._packed: _PackedRF | None = None
         self._graphs: dict = {}
+        _packs.watch(self, self._reset_packs)
         for p in self.parameters():
             p.requires_grad_(False)
+
+    def _reset_packs(self) -> None:
+        self._packed, self._graphs = None, {}
 
     def set_t_sample_strategy(self, strategy="uniform"):
         self.t_sample_strategy = strategy
 
     def _apply(self, fn, *args, **kwargs):
-        self._packed, self._graphs = None, {}
+        self._reset_packs()
+        _packs.bump()
         return super()._apply(fn, *args, **kwargs)
-
-    def load_state_dict(self, *args, **kwargs):
-        self._packed, self._graphs = None, {}
-        return super().load_state_dict(*args, **kwargs)
 
     def _pack(self) -> _PackedRF:
         dev = next(self.parameters()).device
@@ -211,7 +212,7 @@ class RectifiedFlowLoss(nn.Module):
         if noise is None:
             noise = torch.randn(1 if text_cfg != 1.0 else B, self.in_channels, device=device)
         x0 = (torch.cat([noise] * B, dim=0) if text_cfg != 1.0 else noise) * temperature
-        key = (B, float(text_cfg), float(image_cfg))
+        key = (B, float(text_cfg), float(image_cfg), _packs.epoch())
         if not self.use_cuda_graph:
             x = x0.float().contiguous().clone()
             self._sample_body(pk, ops.affine(z.reshape(B, -1), 1.0, 0.0), x, text_cfg, image_cfg)

@@ -20,7 +20,7 @@ import torch
 import torch.nn as nn
 from transformers import PretrainedConfig, PreTrainedModel
 
-from .. import ops
+from .. import _packs, ops
 
 BF16 = torch.bfloat16
 
@@ -333,6 +333,7 @@ class MingTok(PreTrainedModel):
         self.scaling_factor = config.scaling_factor
         self.mean = config.mean
         self._packed: Optional[_Packed] = None
+        _packs.watch(self, self._reset_packs)  # a state-dict load through ANY ancestor drops the packed copy
         for p in self.parameters():
             p.requires_grad_(False)
         self.post_init()  # modeling_mingtok.py:126 (HF bookkeeping; _init_weights is a no-op here)
@@ -341,13 +342,13 @@ class MingTok(PreTrainedModel):
     def _init_weights(self, module):  # weights always come from a checkpoint / state_dict
         return
 
-    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .bfloat16() invalidate the packed copy
+    def _reset_packs(self) -> None:
         self._packed = None
-        return super()._apply(fn, *args, **kwargs)
 
-    def load_state_dict(self, *args, **kwargs):
-        self._packed = None
-        return super().load_state_dict(*args, **kwargs)
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .bfloat16() invalidate the packed copy
+        self._reset_packs()
+        _packs.bump()
+        return super()._apply(fn, *args, **kwargs)
 
     @property
     def device(self):

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 from transformers import PretrainedConfig
 
-from . import ops
+from . import _packs, ops
 from .diff_loss_rf_swiglu import FUSED_NORM, RectifiedFlowLoss
 
 BF16 = torch.bfloat16
@@ -125,6 +125,10 @@ class BailingMoeSparseMoeBlock(nn.Module):
         # expert parallelism: this rank keeps experts [ep_rank * E / ep_size, (ep_rank + 1) * E / ep_size)
         self.ep_group, self.ep_rank, self.ep_size = None, 0, 1
         self.ep_mode, self._a2a, self.ep_peer = "allreduce", None, None
+        _packs.watch(self, self._reset_packs)
+
+    def _reset_packs(self) -> None:
+        self._pk, self._a2a = None, None
 
     # below this many tokens per rank the all-to-all exchange costs more than it saves (decode: B <= 3 rows)
     A2A_MIN_TOKENS_PER_RANK = 4
@@ -171,7 +175,8 @@ class BailingMoeSparseMoeBlock(nn.Module):
         return self._pk
 
     def _apply(self, fn, *a, **k):
-        self._pk = None
+        self._reset_packs()
+        _packs.bump()
         return super()._apply(fn, *a, **k)
 
     @torch.no_grad()
@@ -336,9 +341,14 @@ class BailingMoeModel(nn.Module):
         self.layers = nn.ModuleList([BailingMoeDecoderLayer(config, i) for i in range(config.num_hidden_layers)])
         self.norm = BailingMoeRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self._pk = None
+        _packs.watch(self, self._reset_packs)
+
+    def _reset_packs(self) -> None:
+        self._pk = None
 
     def _apply(self, fn, *a, **k):
-        self._pk = None
+        self._reset_packs()
+        _packs.bump()
         return super()._apply(fn, *a, **k)
 
     def _pack(self):
@@ -455,15 +465,25 @@ class BailingMoeForCausalLM(nn.Module):
         self.num_generated_images = 0
         self._pk = None
         self.use_cuda_graph = True
+        # The CFG rows of a generation carry IDENTICAL latents (shared noise, one combined velocity: diff_loss_rf_swiglu.py
+        # :118-122, :149-171), so the reference's semantic-decoder step, linear_proj and pixel decoder compute the same
+        # row B times (:1939-1964).  With this package's own callbacks those three stages run on ONE row and the result is
+        # broadcast — bit-identical (every kernel on that path is row-independent), (B-1)/B of their traffic saved.
+        self.dedupe_cfg_rows = True
         self._gen_ws = {}
         self._txt_ws = {}
+        _packs.watch(self, self._reset_packs)
         for p in self.parameters():
             p.requires_grad_(False)
 
-    def _apply(self, fn, *a, **k):
+    def _reset_packs(self) -> None:
         self._pk = None
         self._gen_ws = {}
         self._txt_ws = {}
+
+    def _apply(self, fn, *a, **k):
+        self._reset_packs()
+        _packs.bump()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -581,22 +601,39 @@ class BailingMoeForCausalLM(nn.Module):
         mask[:, :t_now] = attention_mask.to(dev)
         pos0 = (attention_mask.long().cumsum(-1) - 1)[:, -1:].to(dev)  # position of the current token per row
         output_tokens, sem_cache, hidden = [], None, None
+        one_row = self.dedupe_cfg_rows and B > 1 and self._graphable(latent_to_sem_func, linear_proj)
         for token_idx in range(n_tok + 1):
             position_ids = (pos0 + token_idx).to(torch.int32)
             latent, hidden = self.forward_for_image_generation_inner(
                 inputs_embeds=input_embeds, attention_mask=mask, position_ids=position_ids, past_key_values=cache,
                 image_gen_temperature=image_gen_temperature,
-                noise=None if noises is None else noises[token_idx].to(dev))
+                noise=self._draw_noise(dev) if noises is None else noises[token_idx].to(dev))
             if token_idx < n_tok:
-                feat = latent_to_sem_func(latent, past_key_values=sem_cache)
+                feat = latent_to_sem_func(latent[0:1] if one_row else latent, past_key_values=sem_cache)
                 sem_cache = feat["past_key_values"]
                 output_token = feat["x_norm_patchtokens"]
                 output_tokens.append(output_token)
                 input_embeds = linear_proj(output_token)
+                if one_row:
+                    input_embeds = input_embeds.expand(B, -1, -1)
         cache.trim_rows()
         final_mask = mask[:, :t_now + n_tok]
         image_tensor = sem_to_pix_func(torch.cat(output_tokens, dim=1))
+        if one_row:
+            image_tensor = image_tensor.expand(B, *image_tensor.shape[1:])
         return image_tensor, hidden, final_mask
+
+    def _draw_noise(self, dev) -> torch.Tensor:
+        """The per-token torch.randn(1, C) of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:118).  Expert-parallel
+        modes that REPLICATE the tokens on every rank need the same draw everywhere (the ranks' partial expert sums are
+        added): rank 0 draws, the others receive it, so differently seeded processes cannot diverge silently."""
+        noise = torch.randn(1, self.diffloss.in_channels, device=dev)
+        if getattr(self.model, "ep_size", 1) > 1 and getattr(self.model, "ep_tokens_replicated", True):
+            import torch.distributed as dist
+
+            dist.broadcast(noise, src=dist.get_global_rank(self.model.ep_group, 0) if self.model.ep_group is not None
+                           else 0, group=self.model.ep_group)
+        return noise
 
     # ---------------------------------------------------------------------------------------------------------------
     # Greedy text decoding (HF GenerationMixin.generate with do_sample = false, mingunivision/config.json:30, as driven by
@@ -626,7 +663,7 @@ class BailingMoeForCausalLM(nn.Module):
         if cache.seq_len + max_new_tokens > cache.max_len:
             raise ValueError("KV cache too small for max_new_tokens")
         use_graph = self.use_cuda_graph and getattr(self.model, "ep_size", 1) == 1
-        key = (id(cache), cache.max_len)
+        key = (id(cache), cache.max_len, _packs.epoch())
         ws = self._txt_ws.get(key) if use_graph else None
         if ws is None:
             D = self.config.hidden_size
@@ -694,9 +731,10 @@ class BailingMoeForCausalLM(nn.Module):
         z = self.compute_vis_z(hidden[:, -1])
         ws["x"].copy_(ws["noise"].expand(ws["B"], -1) * ws["temperature"])
         self.diffloss._sample_body(self.diffloss._pack(), z, ws["x"], 3.0, 1.1)
-        feat = ws["vision"]._decode_step(ws["x"], ws["sem_cache"], 0, ws["sem_cache"].t_dev)
+        R = ws["sem_rows"]  # 1 when the CFG rows are de-duplicated (identical latents), else B
+        feat = ws["vision"]._decode_step(ws["x"][0:R], ws["sem_cache"], 0, ws["sem_cache"].t_dev)
         ws["feats"].index_copy_(1, ws["t_idx"], feat.unsqueeze(1))
-        ws["embeds"].copy_(ws["linear_proj"](feat.unsqueeze(1)))
+        ws["embeds"].copy_(ws["linear_proj"](feat.unsqueeze(1)).expand(ws["B"], -1, -1))
         ws["t_llm"].add_(1)
         ws["sem_cache"].t_dev.add_(1)
         ws["t_idx"].add_(1)
@@ -709,21 +747,23 @@ class BailingMoeForCausalLM(nn.Module):
         t_now = attention_mask.shape[1]
         if cache.seq_len != t_now - 1 or cache.seq_len + n_tok + 1 > cache.max_len:
             raise ValueError("KV cache / attention mask length mismatch or cache too small for the generation")
-        key = (B, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len)
+        R = 1 if self.dedupe_cfg_rows else B
+        key = (B, R, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len, _packs.epoch())
         ws = self._gen_ws.get(key)
         if ws is None:
             C, D, F = self.diffloss.in_channels, self.config.hidden_size, vision.feature_dim
-            ws = dict(B=B, temperature=float(temperature), cache=cache, vision=vision, linear_proj=linear_proj,
+            ws = dict(B=B, sem_rows=R, temperature=float(temperature), cache=cache, vision=vision,
+                      linear_proj=linear_proj,
                       embeds=torch.zeros((B, 1, D), dtype=BF16, device=dev),
                       hidden=torch.zeros((B, 1, D), dtype=BF16, device=dev),
                       noise=torch.zeros((1, C), dtype=torch.float32, device=dev),
                       x=torch.zeros((B, C), dtype=torch.float32, device=dev),
-                      feats=torch.zeros((B, n_tok + 1, F), dtype=BF16, device=dev),
+                      feats=torch.zeros((R, n_tok + 1, F), dtype=BF16, device=dev),
                       pos=torch.zeros((B, 1), dtype=torch.int32, device=dev),
                       mask=torch.ones((B, cache.max_len), dtype=torch.int32, device=dev),
                       t_llm=torch.zeros((1,), dtype=torch.int32, device=dev),
                       t_idx=torch.zeros((1,), dtype=torch.int64, device=dev),
-                      sem_cache=vision.new_decode_cache(B, n_tok + 8), graph=None)
+                      sem_cache=vision.new_decode_cache(R, n_tok + 8), graph=None)
             self._gen_ws = {key: ws}  # one workspace at a time (a new cache / batch size re-captures)
 
         def reset_state():
@@ -750,12 +790,13 @@ class BailingMoeForCausalLM(nn.Module):
             reset_state()
         for token_idx in range(n_tok + 1):
             # RNG stays on the host side as in the reference (torch.randn(1, C) per token, diff_loss_rf_swiglu.py:118)
-            ws["noise"].copy_(torch.randn(1, ws["noise"].shape[1], device=dev) if noises is None
-                              else noises[token_idx].to(dev))
+            ws["noise"].copy_(self._draw_noise(dev) if noises is None else noises[token_idx].to(dev))
             ws["graph"].replay()
         cache.seq_len += n_tok + 1
         cache.trim_rows()
         final_mask = ws["mask"][:, :t_now + n_tok].clone()
         image_tensor = sem_to_pix_func(ws["feats"][:, :n_tok])
+        if R != B:
+            image_tensor = image_tensor.expand(B, *image_tensor.shape[1:])
         self._last_gen_latent_hidden = ws["hidden"]
         return image_tensor, ws["hidden"].clone(), final_mask

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _packs, ops
 from .mingtok.modeling_mingtok import MingTok, MingTokConfig
 from .modeling_bailing_moe import BailingMoeConfig, BailingMoeForCausalLM
 
@@ -28,9 +28,14 @@ class LinearProj(nn.Sequential):
     def __init__(self, feature_dim: int, hidden: int):
         super().__init__(nn.Linear(feature_dim, hidden), nn.GELU(), nn.Linear(hidden, hidden))
         self._pk = None
+        _packs.watch(self, self._reset_packs)
+
+    def _reset_packs(self) -> None:
+        self._pk = None
 
     def _apply(self, fn, *a, **k):
-        self._pk = None
+        self._reset_packs()
+        _packs.bump()
         return super()._apply(fn, *a, **k)
 
     @torch.no_grad()
@@ -127,11 +132,17 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         S = input_ids.shape[1]
         ones = lambda n: torch.ones((1, n), dtype=torch.int32, device=dev)  # noqa: E731
         attention_mask = ones(S) if attention_mask is None else attention_mask.to(dev, torch.int32)
-        uncond_attention_mask = torch.zeros_like(attention_mask) if uncond_attention_mask is None \
-            else uncond_attention_mask.to(dev, torch.int32)
-        text_uncond_attention_mask = torch.zeros_like(attention_mask) if text_uncond_attention_mask is None \
-            else text_uncond_attention_mask.to(dev, torch.int32)
+        # None masks stay None on the first round, exactly as in the reference: generate_image then runs B = 1 without
+        # guidance (modeling_bailing_moe.py:1867-1891).  Later rounds concatenate them behind the saved ones (:229-234),
+        # where the reference's torch.cat raises on None — so they are required there.
+        if uncond_attention_mask is not None:
+            uncond_attention_mask = uncond_attention_mask.to(dev, torch.int32)
+        if text_uncond_attention_mask is not None:
+            text_uncond_attention_mask = text_uncond_attention_mask.to(dev, torch.int32)
         if self.past_attention_mask is not None:  # :229-234
+            if uncond_attention_mask is None or text_uncond_attention_mask is None:
+                raise ValueError("rounds after the first need uncond_attention_mask and text_uncond_attention_mask "
+                                 "(they are concatenated behind the saved masks, modeling_bailingmm.py:229-234)")
             attention_mask = torch.cat((self.past_attention_mask, attention_mask), dim=1)
             uncond_attention_mask = torch.cat((self.past_uncond_attention_mask, uncond_attention_mask), dim=1)
             text_uncond_attention_mask = torch.cat((self.past_text_uncond_attention_mask, text_uncond_attention_mask), dim=1)
@@ -183,6 +194,8 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         pad0 = torch.zeros((1, pad_n), dtype=torch.int32, device=dev)
         past_mode = os.environ.get("PAST_MODE", "DROP")
         if past_mode == "KEEP":
+            if uncond_attention_mask is None or text_uncond_attention_mask is None:
+                raise ValueError("PAST_MODE=KEEP carries the two uncond masks to the next round; they cannot be None")
             self.past_attention_mask = torch.cat((attention_mask, pad1), dim=1)
             self.past_text_uncond_attention_mask = torch.cat((text_uncond_attention_mask, pad1), dim=1)
             self.past_uncond_attention_mask = torch.cat((uncond_attention_mask, pad0), dim=1)

@@ -209,6 +209,10 @@ LLM_CONFIG = dict(vocab_size=126464, hidden_size=2048, intermediate_size=5632, n
 VISHEAD_CONFIG = dict(diffloss_w=3072, diffloss_d=12, num_sampling_steps="16", gen_method="flow_matching_swiglu-4",
                       hidden_size=2048, vis_head_arch="linear2-norm", image_emb_dim_for_gen=32)
 
+# the true 16B-A3B widths with 2 layers instead of 28 (SURVEY.md §8c "layer-exact, depth-reduced"): golden fixture
+# tests/golden/llm_wide.npz and the CPU baseline of bench.py (per-layer time x 28, flagged as extrapolated)
+LLM_WIDE_CONFIG = dict(LLM_CONFIG, num_hidden_layers=2, num_image_tokens_for_gen=4)
+
 LLM_TINY_CONFIG = dict(vocab_size=512, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
                        num_attention_heads=4, num_key_value_heads=2, head_dim=128, hidden_act="silu",
                        use_qkv_bias=False, use_bias=False, rms_norm_eps=1e-5, max_position_embeddings=4096,
@@ -286,11 +290,16 @@ def llm_tensor(key: str, shape: tuple, seed: int = 0, dtype=torch.float32, devic
 
 def llm_state_dict(cfg: dict, vh: dict | None = None, feature_dim: int | None = None, seed: int = 0,
                    dtype=torch.float32) -> dict[str, torch.Tensor]:
-    sd = {}
-    for key, shape in llm_param_shapes(cfg, vh, feature_dim).items():
-        if key.startswith("diffloss."):
-            continue
-        sd[key] = llm_tensor(key, shape, seed, dtype)
+    shapes = {k: v for k, v in llm_param_shapes(cfg, vh, feature_dim).items() if not k.startswith("diffloss.")}
+    if sum(math.prod(v) for v in shapes.values()) > 50_000_000:
+        # every tensor has its own generator (seeded by its key), so the keys can be drawn concurrently — torch.randn
+        # releases the GIL; the true-width fixtures (3 B parameters) take ~10 s instead of a minute
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as ex:
+            sd = dict(zip(shapes, ex.map(lambda kv: llm_tensor(kv[0], kv[1], seed, dtype), shapes.items())))
+    else:
+        sd = {key: llm_tensor(key, shape, seed, dtype) for key, shape in shapes.items()}
     if vh is not None:
         for k, v in rf_state_dict(rf_config_from_vishead(vh), seed, dtype).items():
             sd["diffloss." + k] = v

@@ -164,3 +164,42 @@ def test_committed_bench_line_keeps_the_contract():
     assert line["impl"] == "reference" and line["metric"] == d["metric"] and line["unit"] == d["unit"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["cpu_baseline"]["value"] == line["value"] and line["config"]["workload"] == d["config"]["workload"]
+
+
+def test_state_dict_load_through_the_parent_drops_every_pack():
+    """nn.Module.load_state_dict recurses through `_load_from_state_dict`, so a sub-module's own
+    `load_state_dict` override is never reached when the PARENT wrapper loads a checkpoint.  Every pack owner therefore
+    registers a load-state-dict post hook (ming_univision_b200/_packs.py); captured-graph workspaces are keyed on the
+    pack epoch the hooks bump."""
+    from ming_univision_b200 import _packs, synthetic
+    from ming_univision_b200.mingtok import MingTokConfig
+    from ming_univision_b200.modeling_bailing_moe import BailingMoeConfig
+    from ming_univision_b200.modeling_bailingmm import MingUniVisionForConditionalGeneration
+
+    m = MingUniVisionForConditionalGeneration(BailingMoeConfig(**synthetic.LLM_TINY_CONFIG),
+                                              MingTokConfig(**synthetic.MINGTOK_TINY_CONFIG),
+                                              synthetic.VISHEAD_TINY_CONFIG)
+    llm = m.model
+    moe = llm.model.layers[1].mlp
+
+    def poison():
+        llm._pk = llm.model._pk = moe._pk = m.linear_proj._pk = "stale"
+        llm.diffloss._packed = m.vision._packed = "stale"
+        llm._gen_ws, llm._txt_ws, llm.diffloss._graphs = {"k": 1}, {"k": 1}, {"k": 1}
+
+    def clean():
+        return (llm._pk is None and llm.model._pk is None and moe._pk is None and m.linear_proj._pk is None
+                and llm.diffloss._packed is None and m.vision._packed is None
+                and llm._gen_ws == {} and llm._txt_ws == {} and llm.diffloss._graphs == {})
+
+    poison()
+    e0 = _packs.epoch()
+    m.load_state_dict(m.state_dict(), strict=True)          # through the top-level wrapper
+    assert clean() and _packs.epoch() > e0
+    poison()
+    e1 = _packs.epoch()
+    llm.diffloss.load_state_dict(llm.diffloss.state_dict())  # a child on its own: its packs go, the epoch moves
+    assert llm.diffloss._packed is None and llm.diffloss._graphs == {} and _packs.epoch() > e1
+    poison()
+    m.float()                                                # _apply path (.to / .float / .bfloat16)
+    assert clean()

@@ -2,10 +2,9 @@
 vectors of Pillow / torchvision and the libraries themselves, through the C ABI (`mb_image_preprocess_u8`,
 `mb_image_postprocess_u8`) and the drop-in classes (`mingtok.utils.CenterCropProcessor`).
 
-The checks run in tests/native/preprocess_gpu_worker.py, a process of their own.  These kernels were written after the
-round's GPU minutes were spent: their arithmetic and indexing are verified bit-exactly on the CPU through the header
-they share with the emulation (tests/test_preprocess_cpu.py), but the launches have not run on hardware yet — hence the
-non-strict xfail, which keeps a first-run defect from masking the validated suite and reports XPASS when all is well.
+The checks run in tests/native/preprocess_gpu_worker.py, a process of their own (first hardware run: the driver's
+round-1 GPU suite, green); the same device code is also walked on the CPU through the header it shares with the emulation
+(tests/test_preprocess_cpu.py).
 """
 import os
 import subprocess
@@ -18,8 +17,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent); "
-                                        "CPU emulation of the same device code is bit-exact")
 def test_preprocess_on_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

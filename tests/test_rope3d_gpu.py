@@ -1,8 +1,8 @@
 """3-D multimodal RoPE kernel on the device (the config-gated `rope_scaling.type == "3D"` variant):
 `mb_rope3d_kv_append` against the oracle / the reference's golden vectors, and the gated path through
-`BailingMoeModel.forward_tokens`.  Runs in tests/native/rope3d_gpu_worker.py, a process of its own.  Written after the
-round's GPU minutes were spent — the arithmetic, cache layout and section selection are verified on the CPU through the
-header shared with the emulation (tests/test_rope3d_cpu.py), the launch has not run on hardware yet: non-strict xfail."""
+`BailingMoeModel.forward_tokens`.  Runs in tests/native/rope3d_gpu_worker.py, a process of its own (first hardware run:
+the driver's round-1 GPU suite, green); the arithmetic, cache layout and section selection are also verified on the CPU
+through the header shared with the emulation (tests/test_rope3d_cpu.py)."""
 import os
 import subprocess
 import sys
@@ -14,8 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (written after the round's GPU budget was spent); "
-                                        "CPU emulation of the same device code matches the reference")
 def test_rope3d_on_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
