@@ -302,6 +302,30 @@ int mb_moe_combine_push(const void* out_pairs, const float* weights, const int32
                         int my_rank, int G, int T, int Tmax, int k, int D, void* stream);
 int mb_moe_reduce_finalize(float* const* peers, int my_rank, int G, int T, int Tmax, int D, const void* shared,
                            const void* residual, void* y, uint32_t* fin_done, void* stream);
+/* Expert parallelism with the DISPATCH on peer memory too ("data parallel x expert parallel"; csrc/ep.cu): every rank
+ * works on its OWN T rows and owns experts [e_begin, e_begin + e_local).  One zero-initialised, peer-mapped exchange
+ * area per rank (byte offsets of its x / idx / w / partial-sum / control regions and its size: mb_ep_area_layout ->
+ * offsets6).  Per MoE layer, every rank, same order, same T, on its stream:
+ *   mb_ep_dispatch_push   stores x [T, D] bf16, idx [T, k] i32 (GLOBAL expert ids), w [T, k] f32 into every peer's area
+ *                         (row block my_rank of the packed [G*T, .] arrays), raises the dispatch flags;
+ *   mb_ep_dispatch_wait   bounded wait for the G dispatch flags of the local area; afterwards the local area holds the
+ *                         gathered rows of all ranks — run mb_moe_sort / gate_up / down (or mb_moe_plan / grouped GEMM)
+ *                         on them with (e_begin, e_local);
+ *   mb_ep_combine_push    fp32 partial sums of the local experts for all G*T rows (pair_row = grouped layout or NULL for
+ *                         (token, slot) order), rows of source rank q stored into q's area, raises the combine flags;
+ *   mb_ep_reduce_finalize bounded wait for the G combine flags, sum in rank order, bf16(bf16(bf16(sum) + shared) +
+ *                         residual) -> y [T, D], advances the device-side epoch.
+ * No NCCL, no host synchronisation, capturable in a CUDA graph.  A wait that exceeds MB_EP_TIMEOUT_MS (default 20000)
+ * records a code in the control block (u32 words 2G+4: 1 = dispatch, 2 = combine; 2G+5: the missing rank) and returns;
+ * the host checks it after synchronising. */
+int mb_ep_area_layout(int G, int Tmax, int D, int k, int64_t* offsets6);
+int mb_ep_dispatch_push(const void* x, const int32_t* idx, const float* w, void* const* peers, int my_rank, int G, int T,
+                        int Tmax, int D, int k, void* stream);
+int mb_ep_dispatch_wait(void* const* peers, int my_rank, int G, int Tmax, int D, int k, void* stream);
+int mb_ep_combine_push(const void* out_pairs, const int32_t* pair_row, void* const* peers, int my_rank, int G, int T,
+                       int Tmax, int D, int k, int e_begin, int e_local, void* stream);
+int mb_ep_reduce_finalize(void* const* peers, int my_rank, int G, int T, int Tmax, int D, int k, const void* shared,
+                          const void* residual, void* y, void* stream);
 
 /* ---- Image pre- / post-processing either side of MingTok -------------------------------------------
  * Replaces, on the device, the PIL / torchvision CPU transforms of `CenterCropProcessor` (mingtok/utils/processor.py:17-27),

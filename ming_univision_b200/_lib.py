@@ -51,6 +51,11 @@ SIGNATURES = {
     "mb_moe_peer_area_bytes": [_i, _i, _i, _vp],
     "mb_moe_combine_push": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_reduce_finalize": [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "mb_ep_area_layout": [_i, _i, _i, _i, _vp],
+    "mb_ep_dispatch_push": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mb_ep_dispatch_wait": [_vp, _i, _i, _i, _i, _i, _vp],
+    "mb_ep_combine_push": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "mb_ep_reduce_finalize": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mb_image_preprocess_workspace_bytes": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mb_image_preprocess_u8": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _f, _f, _f, _vp, _i, _vp, _i64,
                                _vp],
@@ -77,6 +82,14 @@ _launches = 0  # successful C-ABI calls == kernel launches issued by this proces
 
 def launch_count() -> int:
     return _launches
+
+
+def count_replay(n_kernels: int) -> None:
+    """A CUDA-graph replay launches the kernels that were captured into it: the owners of the graphs record how many
+    C-ABI calls the capture made and add them here on every replay, so launch_count() keeps meaning "kernels of this
+    library launched by this process"."""
+    global _launches
+    _launches += int(n_kernels)
 
 
 def header_symbols() -> list[str]:

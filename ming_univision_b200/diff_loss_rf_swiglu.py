@@ -20,7 +20,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import _packs, ops
+from . import _lib, _packs, ops
 
 BF16 = torch.bfloat16
 
@@ -226,11 +226,13 @@ class RectifiedFlowLoss(nn.Module):
                 self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg)
-            self._graphs[key] = (g, z_buf, x_buf)
-        g, z_buf, x_buf = self._graphs[key]
+            self._graphs[key] = (g, z_buf, x_buf, _lib.launch_count() - l0)
+        g, z_buf, x_buf, n_kernels = self._graphs[key]
         z_buf.copy_(z.reshape(B, -1))
         x_buf.copy_(x0)
         g.replay()
+        _lib.count_replay(n_kernels)
         return x_buf.clone()

@@ -100,3 +100,71 @@ class PeerExchange:
         self.peers_dev = int(self.handle.buffer_ptrs_dev)  # device array of G base pointers (as mapped in this process)
         self.fin_done = torch.zeros((1,), dtype=torch.int32, device=device)
         dist.barrier(self.group)  # every area is zeroed before anyone pushes
+
+
+class PeerDispatch:
+    """Exchange areas of the peer-memory DISPATCH + COMBINE (csrc/ep.cu: mb_ep_dispatch_push / _wait / mb_ep_combine_push /
+    mb_ep_reduce_finalize) — "data parallel x expert parallel": every rank runs its OWN token rows (its own image or
+    request) through replicated attention / gates / shared experts and owns E / G routed experts; per MoE layer the rows
+    are all-gathered through NVLink peer stores, each rank runs its experts on the rows of all ranks, and the fp32
+    partial sums travel back to their owners the same way.  No NCCL call and no host synchronisation per layer, so a
+    whole token step (28 layers) stays ONE CUDA graph.
+
+    One instance serves every MoE layer of a model (calls are stream-ordered; the device-side epoch keeps them apart).
+    `t_max` = most rows per rank and call (CFG rows at decode, prompt length at prefill); every rank must make the same
+    calls with the same T.  Built either over torch symmetric memory (one process per GPU, `group`) or — `local_ranks=G`
+    — as G virtual ranks on ONE device, which is how the protocol is tested on a single-GPU box."""
+
+    def __init__(self, group, hidden_size: int, top_k: int, t_max: int, device, local_ranks: int = 0):
+        import ctypes
+
+        from . import _lib
+
+        lib = _lib.load()
+        self.hidden_size, self.top_k, self.t_max = hidden_size, top_k, t_max
+        self.local = local_ranks > 0
+        if self.local:
+            self.group, self.size, self.rank = None, local_ranks, 0
+        else:
+            self.group = group if group is not None else dist.group.WORLD
+            self.size, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        offs = (ctypes.c_int64 * 6)()
+        _lib.check(lib.mb_ep_area_layout(self.size, t_max, hidden_size, top_k, offs), "mb_ep_area_layout")
+        self.off_x, self.off_idx, self.off_w, self.off_part, self.off_ctrl, self.nbytes = (int(v) for v in offs)
+        if self.local:
+            self.bufs = [torch.zeros((self.nbytes,), dtype=torch.uint8, device=device) for _ in range(self.size)]
+            self._ptrs = torch.tensor([b.data_ptr() for b in self.bufs], dtype=torch.int64, device=device)
+            self.peers_dev = self._ptrs.data_ptr()
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            buf = symm_mem.empty((self.nbytes,), dtype=torch.uint8, device=device)
+            buf.zero_()
+            torch.cuda.synchronize(device)
+            self.handle = symm_mem.rendezvous(buf, self.group)  # collective: exchanges the memory handles
+            if len(self.handle.buffer_ptrs) != self.size:
+                raise RuntimeError("symmetric-memory rendezvous did not return one buffer per rank")
+            self.bufs = [None] * self.size
+            self.bufs[self.rank] = buf
+            self.peers_dev = int(self.handle.buffer_ptrs_dev)
+            dist.barrier(self.group)  # every area is zeroed before anyone pushes
+
+    def area(self, rank: int | None = None) -> torch.Tensor:
+        return self.bufs[self.rank if rank is None else rank]
+
+    def gathered(self, T: int, rank: int | None = None):
+        """Views of the local area after mb_ep_dispatch_wait: (x [G*T, D] bf16, idx [G*T, k] i32, w [G*T, k] f32)."""
+        a, G, D, k = self.area(rank), self.size, self.hidden_size, self.top_k
+        x = a[self.off_x:self.off_x + G * T * D * 2].view(torch.bfloat16).view(G * T, D)
+        idx = a[self.off_idx:self.off_idx + G * T * k * 4].view(torch.int32).view(G * T, k)
+        w = a[self.off_w:self.off_w + G * T * k * 4].view(torch.float32).view(G * T, k)
+        return x, idx, w
+
+    def check(self, rank: int | None = None) -> None:
+        """Raises if a bounded wait of this rank's kernels expired (call after a synchronisation point)."""
+        G = self.size
+        ctl = self.area(rank)[self.off_ctrl:self.off_ctrl + (2 * G + 8) * 4].view(torch.int32)
+        code, peer = int(ctl[2 * G + 4]), int(ctl[2 * G + 5])
+        if code != 0:
+            raise RuntimeError(f"expert-parallel exchange timed out waiting for rank {peer} "
+                               f"({'dispatch' if code == 1 else 'combine'} flag); the step's output is invalid")

@@ -43,24 +43,43 @@ def load_checkpoint(model_dir: str, device="cuda") -> MingUniVisionForConditiona
             tok_cfg = json.load(f)
     llm_cfg = {k: v for k, v in cfg["llm_config"].items() if k not in ("architectures", "model_type", "torch_dtype",
                                                                        "transformers_version", "auto_map")}
-    llm_cfg["rope_scaling"] = None  # the path uses the 1-D legacy rotary
-    with torch.device(device):
-        model = MingUniVisionForConditionalGeneration(BailingMoeConfig(**llm_cfg), MingTokConfig(**tok_cfg),
-                                                      cfg["vishead_diffloss_config"])
-    sd = {}
-    for shard in sorted(glob.glob(os.path.join(model_dir, "*.safetensors"))):
-        sd.update(load_file(shard, device=str(device)))
+    # The reference's own callers build 2-D position ids, so its rotary embedding is the 1-D legacy one whatever the
+    # checkpoint's `rope_scaling` says about "3D"  — mapped to None, loudly.  Any OTHER scaling (yarn,
+    # linear, dynamic NTK) changes the arithmetic and is not implemented: refuse rather than mis-execute.
+    rs = llm_cfg.get("rope_scaling")
+    if rs is not None:
+        kind = rs.get("type", rs.get("rope_type")) if isinstance(rs, dict) else rs
+        if kind not in ("3D", "default"):
+            raise NotImplementedError(f"rope_scaling {rs!r}: only None or the reference's '3D' entry are supported")
+        import warnings
+
+        warnings.warn("config rope_scaling '3D' -> None: the generation path uses 2-D position ids and the 1-D legacy "
+                      "rotary embedding (pass 3-D position ids to forward_tokens for the M-RoPE variant)")
+    llm_cfg["rope_scaling"] = None
+    # meta-device construction + bf16 storage (routed experts straight in their kernel slabs): never an fp32 copy of the
+    # 16.8 B parameters, never per-expert tensors next to a stacked copy
+    model = MingUniVisionForConditionalGeneration.on_device(BailingMoeConfig(**llm_cfg), MingTokConfig(**tok_cfg),
+                                                            cfg["vishead_diffloss_config"], device)
+    expected = {k for k, v in model.state_dict().items() if not v.is_meta}
+    loaded = set()
+    shards = [(s, "") for s in sorted(glob.glob(os.path.join(model_dir, "*.safetensors")))]
     tok_dir = os.path.join(model_dir, "models", "MingTok-Vision")
-    for shard in sorted(glob.glob(os.path.join(tok_dir, "*.safetensors"))):
-        sd.update({"vision." + k: v for k, v in load_file(shard, device=str(device)).items()})
-    # only the three sub-trees of the continuous-visual-token path (audio encoder / talker weights of an omni checkpoint
-    # are ignored); the reference-only rotary buffers are derived from rope_theta here
-    sd = {k: v for k, v in sd.items()
-          if k.split(".")[0] in ("model", "vision", "linear_proj") and not k.endswith("rotary_emb.inv_freq")}
-    missing, unexpected = model.load_state_dict(sd, strict=False)
+    shards += [(s, "vision.") for s in sorted(glob.glob(os.path.join(tok_dir, "*.safetensors")))]
+    unexpected = []
+    for shard, prefix in shards:  # shard by shard: the host / device never holds more than one shard beside the model
+        part = {prefix + k: v for k, v in load_file(shard, device=str(device)).items()}
+        # only the three sub-trees of the continuous-visual-token path (audio encoder / talker weights of an omni
+        # checkpoint are ignored); the reference-only rotary buffers are derived from rope_theta here
+        part = {k: v for k, v in part.items()
+                if k.split(".")[0] in ("model", "vision", "linear_proj") and not k.endswith("rotary_emb.inv_freq")}
+        unexpected += [k for k in part if k not in expected]
+        model.load_state_dict({k: v for k, v in part.items() if k in expected}, strict=False)
+        loaded.update(k for k in part if k in expected)
+        del part
+    missing = sorted(expected - loaded)
     if missing or unexpected:
         raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")
-    return model.to(torch.bfloat16)
+    return model
 
 
 class MingUniVisionInfer:

@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 from transformers import PretrainedConfig
 
-from . import _packs, ops
+from . import _lib, _packs, ops
 from .diff_loss_rf_swiglu import FUSED_NORM, RectifiedFlowLoss
 
 BF16 = torch.bfloat16
@@ -125,6 +125,7 @@ class BailingMoeSparseMoeBlock(nn.Module):
         # expert parallelism: this rank keeps experts [ep_rank * E / ep_size, (ep_rank + 1) * E / ep_size)
         self.ep_group, self.ep_rank, self.ep_size = None, 0, 1
         self.ep_mode, self._a2a, self.ep_peer = "allreduce", None, None
+        self._slab = None
         _packs.watch(self, self._reset_packs)
 
     def _reset_packs(self) -> None:
@@ -134,21 +135,49 @@ class BailingMoeSparseMoeBlock(nn.Module):
     A2A_MIN_TOKENS_PER_RANK = 4
 
     def set_expert_parallel(self, group, rank: int, size: int, mode: str = "allreduce", peer=None) -> None:
-        """mode "peer": like "allreduce", but decode-sized inputs exchange their fp32 partial sums through NVLink peer
-        memory inside the combine kernels (ep.PeerExchange; no NCCL call).  mode "allreduce": tokens replicated, every rank runs its experts on all tokens and the fp32 partial sums are
-        all-reduced (decode-sized inputs).  mode "alltoall": prefill-sized inputs additionally shard the TOKENS of the
-        MoE block over the ranks with an all-to-all dispatch / combine (ming_univision_b200/ep.py); small inputs still
-        take the all-reduce path."""
+        """Rank `rank` of `size` keeps experts [rank E / size, (rank + 1) E / size).  Exchange modes:
+        "dispatch"  (the one that scales) every rank runs its OWN rows; dispatch and combine both go through NVLink peer
+                    memory inside the kernels of csrc/ep.cu (ep.PeerDispatch) — no NCCL, graph-capturable;
+        "peer"      tokens replicated on every rank, combine through peer memory (ep.PeerExchange, <= 8 rows);
+        "allreduce" tokens replicated, NCCL all-reduce of the fp32 partial sums;
+        "alltoall"  prefill-sized inputs also shard the TOKENS of the block with NCCL all-to-alls (ep.py)."""
         if self.config.num_experts % size != 0:
             raise ValueError("num_experts must be divisible by the expert-parallel world size")
-        if mode not in ("allreduce", "alltoall", "peer"):
-            raise ValueError("mode must be 'allreduce', 'alltoall' or 'peer'")
+        if mode not in ("allreduce", "alltoall", "peer", "dispatch"):
+            raise ValueError("mode must be 'allreduce', 'alltoall', 'peer' or 'dispatch'")
         self.ep_group, self.ep_rank, self.ep_size = (group if size > 1 else None), rank, size
         self.ep_mode = mode
-        self.ep_peer = peer if (mode == "peer" and size > 1) else None
-        if mode == "peer" and size > 1 and peer is None:
-            raise ValueError("mode 'peer' needs a PeerExchange (ming_univision_b200.ep)")
+        self.ep_peer = peer if (mode in ("peer", "dispatch") and size > 1) else None
+        if mode in ("peer", "dispatch") and size > 1 and peer is None:
+            raise ValueError(f"mode '{mode}' needs its exchange area (ming_univision_b200.ep)")
         self._a2a = None
+        self._pk = None
+
+    def materialize_experts(self, device, ep_rank: int = 0, ep_size: int = 1, dtype=BF16) -> None:
+        """Gives the LOCAL routed experts their storage as views into two contiguous slabs — Wgu [E_local, 2I, D]
+        (gate rows then up rows) and Wd [E_local, D, I], the layout the expert kernels stream — and leaves the experts of
+        other ranks without storage (meta tensors).  `load_state_dict` / in-place initialisation then write straight into
+        the slabs: no per-expert tensors next to a stacked copy, and an expert-parallel rank holds only its
+        E / G experts.  Call on a module whose expert parameters are still on the meta device (or to be discarded)."""
+        cfg = self.config
+        E, I, D = cfg.num_experts, cfg.moe_intermediate_size, cfg.hidden_size
+        if E % ep_size != 0:
+            raise ValueError("num_experts must be divisible by the expert-parallel world size")
+        n_local = E // ep_size
+        e0 = ep_rank * n_local
+        Wgu = torch.empty((n_local, 2 * I, D), dtype=dtype, device=device)
+        Wd = torch.empty((n_local, D, I), dtype=dtype, device=device)
+        for e, ex in enumerate(self.experts):
+            if e0 <= e < e0 + n_local:
+                j = e - e0
+                ex.gate_proj.weight = nn.Parameter(Wgu[j, :I], requires_grad=False)
+                ex.up_proj.weight = nn.Parameter(Wgu[j, I:], requires_grad=False)
+                ex.down_proj.weight = nn.Parameter(Wd[j], requires_grad=False)
+            else:
+                for lin in (ex.gate_proj, ex.up_proj, ex.down_proj):
+                    lin.weight = nn.Parameter(torch.empty(lin.weight.shape, dtype=dtype, device="meta"),
+                                              requires_grad=False)
+        self._slab = (Wgu, Wd, e0, n_local)
         self._pk = None
 
     def _pack(self):
@@ -161,10 +190,16 @@ class BailingMoeSparseMoeBlock(nn.Module):
             # per-expert slabs: Wgu[e] = [gate_proj; up_proj] ([2I, D]), Wd[e] = down_proj ([D, I])
             n_local = len(self.experts) // self.ep_size
             pk["e_begin"] = self.ep_rank * n_local
-            local = list(self.experts)[pk["e_begin"]:pk["e_begin"] + n_local]
-            pk["Wgu"] = torch.stack([torch.cat([d(e.gate_proj.weight), d(e.up_proj.weight)], dim=0)
-                                     for e in local]).contiguous()
-            pk["Wd"] = torch.stack([d(e.down_proj.weight) for e in local]).contiguous()
+            slab = getattr(self, "_slab", None)
+            if slab is not None and slab[2] == pk["e_begin"] and slab[3] == n_local and slab[0].device == dev \
+                    and slab[0].dtype == BF16 and \
+                    self.experts[pk["e_begin"]].gate_proj.weight.data_ptr() == slab[0].data_ptr():
+                pk["Wgu"], pk["Wd"] = slab[0], slab[1]  # the parameters ARE the slabs (materialize_experts)
+            else:
+                local = list(self.experts)[pk["e_begin"]:pk["e_begin"] + n_local]
+                pk["Wgu"] = torch.stack([torch.cat([d(e.gate_proj.weight), d(e.up_proj.weight)], dim=0)
+                                         for e in local]).contiguous()
+                pk["Wd"] = torch.stack([d(e.down_proj.weight) for e in local]).contiguous()
             if hasattr(self, "shared_experts"):
                 s = self.shared_experts
                 pk["s12"] = torch.cat([d(s.gate_proj.weight), d(s.up_proj.weight)], dim=0).contiguous()
@@ -176,6 +211,7 @@ class BailingMoeSparseMoeBlock(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._reset_packs()
+        self._slab = None  # .to() / .bfloat16() re-allocate the parameters: they no longer alias the slabs
         _packs.bump()
         return super()._apply(fn, *a, **k)
 
@@ -200,8 +236,21 @@ class BailingMoeSparseMoeBlock(nn.Module):
                 shared = ops.gemv(ops.gemv(x2d, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
             else:
                 shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
+        if self.ep_mode == "dispatch" and self.ep_size > 1:
+            # data parallel x expert parallel: these are THIS rank's rows; dispatch + combine over peer memory (csrc/ep.cu)
+            pd, T = self.ep_peer, x2d.shape[0]
+            n_local = pk["Wgu"].shape[0]
+            ys = []
+            for c0 in range(0, T, pd.t_max):  # every rank makes the same calls (same T everywhere)
+                c1 = min(T, c0 + pd.t_max)
+                ops.ep_dispatch(pd, x2d[c0:c1], idx[c0:c1], w[c0:c1])
+                out_pairs, pair_row = ops.ep_compute(pd, c1 - c0, pk["Wgu"], pk["Wd"], pk["e_begin"], cfg.num_experts)
+                ops.ep_combine(pd, c1 - c0, out_pairs, pair_row, pk["e_begin"], n_local)
+                ys.append(ops.ep_finalize(pd, c1 - c0, None if shared is None else shared[c0:c1],
+                                          None if residual is None else residual[c0:c1]))
+            return (ys[0] if len(ys) == 1 else torch.cat(ys, dim=0)), logits, idx
         y = ops.moe_experts(x2d, idx, w, pk["Wgu"], pk["Wd"], shared, residual, pk["e_begin"], self.ep_group,
-                            self.ep_peer)
+                            self.ep_peer if self.ep_mode == "peer" else None)
         return y, logits, idx
 
     @torch.no_grad()
@@ -269,7 +318,16 @@ class BailingMoeSparseMoeBlock(nn.Module):
         if audio_mask is not None:
             raise NotImplementedError("audio routing is outside the continuous-visual-token path")
         B, S, D = hidden_states.shape
-        y, logits, idx = self._run(hidden_states.reshape(B * S, D).contiguous(), None, image_mask)
+        x2d = hidden_states.reshape(B * S, D).contiguous()
+        y, logits, idx = self._run(x2d, None, image_mask)
+        if logits is None:  # token-sharded all-to-all mode: every rank routed only its slice; redo the (cheap) router here
+            pk, cfg = self._pack(), self.config
+            logits = _dense(x2d, pk["gate"])
+            li, im = None, None
+            if self.multi_gate and image_mask is not None:
+                li, im = _dense(x2d, pk["image_gate"]), image_mask.reshape(-1).to(torch.uint8).contiguous()
+            idx, _ = ops.router_topk(logits, cfg.num_experts_per_tok,
+                                     cfg.num_experts_per_tok > 1 and cfg.norm_topk_prob, li, im)
         return y.view(B, S, D), (logits.view(B, S, -1), idx.view(B, S, -1).long())
 
 
@@ -331,6 +389,19 @@ class BailingKVCache:
     def trim_rows(self) -> None:
         self.batch = 1
 
+    def grow(self, min_len: int) -> None:
+        """Re-allocates the cache for at least `min_len` tokens (doubling), keeping what it holds — the stand-in for the
+        reference's DynamicCache growing with every torch.cat (later editing rounds outgrow any fixed size).  Graph
+        workspaces are keyed on (cache, max_len), so the decode graphs are re-captured on the new buffers."""
+        new_len = max(min_len, 2 * self.max_len)
+        for i in range(len(self.k)):
+            for buf in (self.k, self.v):
+                old = buf[i]
+                new = torch.zeros((old.shape[0], old.shape[1], new_len, old.shape[3]), dtype=old.dtype, device=old.device)
+                new[:, :, :self.seq_len].copy_(old[:, :, :self.seq_len])
+                buf[i] = new
+        self.max_len = new_len
+
 
 class BailingMoeModel(nn.Module):
     def __init__(self, config: BailingMoeConfig):
@@ -366,23 +437,34 @@ class BailingMoeModel(nn.Module):
             self._pk = dict(dev=dev, layers=layers, norm=d(self.norm.weight), emb=d(self.word_embeddings.weight))
         return self._pk
 
-    def set_expert_parallel(self, group=None, mode: str = "allreduce") -> None:
+    def set_expert_parallel(self, group=None, mode: str = "allreduce", t_max: int = 256, peer=None) -> None:
         """Shards the routed experts of every layer over the ranks of `group` (default: the world group); attention,
-        gates, shared experts and norms stay replicated.  One process per GPU; NCCL over NVLink.
-        mode "alltoall" also shards the tokens of prefill-sized MoE inputs (BailingMoeSparseMoeBlock.set_expert_parallel)."""
+        gates, shared experts and norms stay replicated.  One process per GPU.  Modes: see
+        BailingMoeSparseMoeBlock.set_expert_parallel; "dispatch" ("data parallel x expert parallel": every rank runs its
+        own rows, `t_max` = most rows per rank and MoE call) and "peer" exchange through NVLink peer memory without any
+        NCCL call, so the CUDA-graph fast paths stay on.  `peer`: an existing exchange area to reuse."""
         import torch.distributed as dist
 
         size = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
-        peer = None
-        if mode == "peer" and size > 1:  # one exchange area for all layers (stream-ordered calls, epoch protocol)
+        if peer is not None:  # (tests: virtual ranks on one device)
+            size, rank = peer.size, peer.rank
+        elif mode == "peer" and size > 1:  # one exchange area for all layers (stream-ordered calls, epoch protocol)
             from .ep import PeerExchange
 
             peer = PeerExchange(group, self.config.hidden_size, self.norm.weight.device)
+        elif mode == "dispatch" and size > 1:
+            from .ep import PeerDispatch
+
+            peer = PeerDispatch(group, self.config.hidden_size, self.config.num_experts_per_tok, t_max,
+                                self.norm.weight.device)
+        grp = group if group is not None else (dist.group.WORLD if size > 1 and dist.is_initialized() else None)
         for lyr in self.layers:
-            lyr.mlp.set_expert_parallel(group if group is not None else (dist.group.WORLD if size > 1 else None),
-                                        rank, size, mode, peer)
-        self.ep_size = size
+            lyr.mlp.set_expert_parallel(grp, rank, size, mode, peer)
+        self.ep_size, self.ep_mode, self.ep_group, self.ep_peer = size, mode, grp, peer
+        # replicated-token modes need identical inputs (hence identical RF noise) on every rank; "dispatch" does not
+        self.ep_tokens_replicated = mode != "dispatch"
+        self.ep_graphable = size == 1 or mode in ("peer", "dispatch")
 
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:
         """word_embeddings lookup (row gather of the packed bf16 table; pure indexing, no arithmetic)."""
@@ -408,7 +490,7 @@ class BailingMoeModel(nn.Module):
             raise ValueError("t_dev is for the single-token decode step")
         t0 = 0 if graph_mode else cache.seq_len
         if not graph_mode and t0 + S > cache.max_len:
-            raise ValueError(f"KV cache overflow: {t0}+{S} > {cache.max_len}")
+            cache.grow(t0 + S)
         if S > 1 and key_mask is not None and bool((key_mask[:, :t0 + S] == 0).any()):
             raise NotImplementedError("multi-token forward needs an all-ones key mask (causal prefill; a later round's "
                                       "prompt appended behind the cached context)")
@@ -591,7 +673,7 @@ class BailingMoeForCausalLM(nn.Module):
         if B > 1:
             input_embeds = input_embeds.repeat((B, 1, 1))
             cache.repeat_rows(B)
-        if self.use_cuda_graph and getattr(self.model, "ep_size", 1) == 1 and \
+        if self.use_cuda_graph and getattr(self.model, "ep_graphable", True) and \
                 self._graphable(latent_to_sem_func, linear_proj):
             return self._generate_image_graphed(input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func,
                                                 linear_proj, sem_to_pix_func, image_gen_temperature, noises)
@@ -661,8 +743,8 @@ class BailingMoeForCausalLM(nn.Module):
         if cache.batch != 1:
             raise ValueError("text decoding runs on one row")
         if cache.seq_len + max_new_tokens > cache.max_len:
-            raise ValueError("KV cache too small for max_new_tokens")
-        use_graph = self.use_cuda_graph and getattr(self.model, "ep_size", 1) == 1
+            cache.grow(cache.seq_len + max_new_tokens)
+        use_graph = self.use_cuda_graph and getattr(self.model, "ep_graphable", True)
         key = (id(cache), cache.max_len, _packs.epoch())
         ws = self._txt_ws.get(key) if use_graph else None
         if ws is None:
@@ -689,15 +771,17 @@ class BailingMoeForCausalLM(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             reset_state()
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._text_step(ws)
-            ws["graph"] = g
+            ws["graph"], ws["kernels"] = g, _lib.launch_count() - l0
             reset_state()
         out = []
         stop = set(int(t) for t in stop_ids)
         for _ in range(max_new_tokens):
             if use_graph:
                 ws["graph"].replay()
+                _lib.count_replay(ws["kernels"])
             else:
                 self._text_step(ws)
             t = int(ws["tok"].item())
@@ -745,8 +829,10 @@ class BailingMoeForCausalLM(nn.Module):
         dev = input_embeds.device
         vision = latent_to_sem_func.__self__
         t_now = attention_mask.shape[1]
-        if cache.seq_len != t_now - 1 or cache.seq_len + n_tok + 1 > cache.max_len:
-            raise ValueError("KV cache / attention mask length mismatch or cache too small for the generation")
+        if cache.seq_len != t_now - 1:
+            raise ValueError("KV cache / attention mask length mismatch")
+        if cache.seq_len + n_tok + 1 > cache.max_len:
+            cache.grow(cache.seq_len + n_tok + 1)
         R = 1 if self.dedupe_cfg_rows else B
         key = (B, R, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len, _packs.epoch())
         ws = self._gen_ws.get(key)
@@ -784,14 +870,16 @@ class BailingMoeForCausalLM(nn.Module):
             torch.cuda.current_stream().wait_stream(side)
             reset_state()
             g = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
             with torch.cuda.graph(g):
                 self._token_step(ws)
-            ws["graph"] = g
+            ws["graph"], ws["kernels"] = g, _lib.launch_count() - l0
             reset_state()
         for token_idx in range(n_tok + 1):
             # RNG stays on the host side as in the reference (torch.randn(1, C) per token, diff_loss_rf_swiglu.py:118)
             ws["noise"].copy_(self._draw_noise(dev) if noises is None else noises[token_idx].to(dev))
             ws["graph"].replay()
+            _lib.count_replay(ws["kernels"])
         cache.seq_len += n_tok + 1
         cache.trim_rows()
         final_mask = ws["mask"][:, :t_now + n_tok].clone()

@@ -76,6 +76,35 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
 
+    @classmethod
+    def on_device(cls, llm_config: BailingMoeConfig, mingtok_config: MingTokConfig, vishead_diffloss_config: dict,
+                  device, ep_rank: int = 0, ep_size: int = 1, dtype=BF16) -> "MingUniVisionForConditionalGeneration":
+        """Builds the wrapper WITHOUT ever holding an fp32 or duplicated copy of the 16.8 B parameters: the module tree is
+        created on the meta device, then every parameter gets `dtype` storage on `device`; the routed experts of each
+        layer live in the two contiguous slabs the expert kernels stream (BailingMoeSparseMoeBlock.materialize_experts),
+        and with `ep_size` > 1 only this rank's E / ep_size experts are allocated (the others stay meta tensors).  The
+        parameters are uninitialised: follow with `load_state_dict` (copies land in the slabs) or an in-place init."""
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            with torch.device("meta"):
+                m = cls(llm_config, mingtok_config, vishead_diffloss_config)
+        finally:
+            torch.set_default_dtype(prev)
+        expert_params = set()
+        for lyr in m.model.model.layers:
+            lyr.mlp.materialize_experts(device, ep_rank, ep_size, dtype)
+            expert_params.update(id(p) for p in lyr.mlp.experts.parameters())
+        for mod in m.modules():
+            for name, p in list(mod._parameters.items()):
+                if p is not None and p.is_meta and id(p) not in expert_params:
+                    mod._parameters[name] = nn.Parameter(torch.empty(p.shape, dtype=dtype, device=device),
+                                                         requires_grad=False)
+            for name, b in list(mod._buffers.items()):
+                if b is not None and b.is_meta:
+                    mod._buffers[name] = torch.zeros(b.shape, dtype=b.dtype, device=device)
+        return m
+
     def reset_inner_state(self):
         """modeling_bailingmm.py:303-308."""
         self.past_key_values = None

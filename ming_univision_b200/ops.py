@@ -21,6 +21,8 @@ PROFILE: list | None = None
 # buffers, shapes, epilogue): bench.py replays the step's GEMM launches back to back between two events, which times
 # the dominant kernel without the per-launch event pairs (those serialise the PDL chain and add ~2 us per launch).
 REPLAY: list | None = None
+# The same for the weight-streaming kernel (gemv / gemv_norm): (closure, algorithmic bytes = N*K*2, (M, N, K, epi)).
+GEMV_REPLAY: list | None = None
 
 
 def _stream() -> int:
@@ -350,6 +352,9 @@ def gemv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None
                           out.stride(0), M, N, K, epi, _ptr(residual), residual.stride(0) if residual is not None else 0,
                           _ptr(gate), gate.stride(0) if gate is not None else 0, _ptr(out_f32), _stream())
     _lib.check(rc, "mb_gemv_bf16")
+    if GEMV_REPLAY is not None:  # bench.py: re-issue the step's streaming launches back to back (algorithmic bytes = N K 2)
+        GEMV_REPLAY.append((lambda: gemv(x, weight, bias, epi=epi, residual=residual, gate=gate, out=out,
+                                         out_f32=out_f32), 2.0 * N * K, (M, N, K, epi)))
     return out
 
 
@@ -381,6 +386,10 @@ def gemv_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None =
                                _ptr(shift), shift.stride(0) if shift is not None else 0, _ptr(scale),
                                scale.stride(0) if scale is not None else 0, float(eps), _stream())
     _lib.check(rc, "mb_gemv_bf16_norm")
+    if GEMV_REPLAY is not None:
+        GEMV_REPLAY.append((lambda: gemv_norm(x, weight, bias, norm=norm, gamma=gamma, beta=beta, shift=shift,
+                                              scale=scale, eps=eps, epi=epi, residual=residual, gate=gate, out=out,
+                                              out_f32=out_f32), 2.0 * N * K, (M, N, K, epi)))
     return out
 
 
@@ -649,6 +658,80 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
     dist.all_reduce(part, op=dist.ReduceOp.SUM, group=ep_group)
     _lib.check(lib.mb_moe_finalize(part.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(), T, D, s),
                "mb_moe_finalize")
+    return y
+
+
+def moe_local_experts(x: torch.Tensor, idx: torch.Tensor, Wgu: torch.Tensor, Wd: torch.Tensor, e_begin: int,
+                      n_experts_total: int | None = None):
+    """The routed-expert FFNs of the LOCAL experts [e_begin, e_begin + E_local) on rows x [T, D] with GLOBAL expert ids
+    idx [T, k]: returns (out_pairs, pair_row) — out_pairs rows in (token, slot) order with pair_row None (streaming
+    kernels; rows of non-local pairs are never written), or in the grouped layout addressed through pair_row (negative =
+    not local).  The building block of the expert-parallel paths; the weighted combine is the caller's."""
+    _check_bf16(x, Wgu, Wd)
+    lib = _lib.load()
+    T, D = x.shape
+    E, I2, _ = Wgu.shape
+    I = I2 // 2
+    k = idx.shape[1]
+    dev = x.device
+    s = _stream()
+    # the pairs spread over ALL experts, E of which are local: pairs per local expert ~ T k / n_experts_total
+    if _moe_use_grouped(T, k, n_experts_total or E):
+        pair_row, row_token, tile_expert, meta, max_rows = moe_plan(idx, E, e_begin)
+        xg = gather_rows(x, row_token, max_rows, meta)
+        return moe_grouped_ffn(xg, Wgu, Wd, tile_expert, meta), pair_row
+    offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+    sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
+    hid = torch.empty((T * k, I), dtype=BF16, device=dev)
+    out_pairs = torch.empty((T * k, D), dtype=BF16, device=dev)
+    _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
+               "mb_moe_sort")
+    _lib.check(lib.mb_moe_gate_up(x.data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                                  hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
+    _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                               out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+    return out_pairs, None
+
+
+# ---- expert parallelism over peer memory, phase by phase (ep.PeerDispatch; csrc/ep.cu).  A real rank runs the four
+# phases back to back; the single-device test drives G virtual ranks phase by phase.
+def ep_dispatch(pd, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, rank: int | None = None) -> None:
+    _check_bf16(x)
+    T, D = x.shape
+    if T > pd.t_max or D != pd.hidden_size or idx.shape != (T, pd.top_k) or idx.dtype != torch.int32:
+        raise ValueError(f"expert-parallel dispatch: rows {tuple(x.shape)} / idx {tuple(idx.shape)} do not fit the "
+                         f"exchange area (t_max {pd.t_max}, D {pd.hidden_size}, k {pd.top_k})")
+    r = pd.rank if rank is None else rank
+    _lib.check(_lib.load().mb_ep_dispatch_push(x.contiguous().data_ptr(), idx.contiguous().data_ptr(),
+                                               w.contiguous().data_ptr(), pd.peers_dev, r, pd.size, T, pd.t_max, D,
+                                               pd.top_k, _stream()), "mb_ep_dispatch_push")
+
+
+def ep_compute(pd, T: int, Wgu: torch.Tensor, Wd: torch.Tensor, e_begin: int, n_experts_total: int,
+               rank: int | None = None):
+    r = pd.rank if rank is None else rank
+    _lib.check(_lib.load().mb_ep_dispatch_wait(pd.peers_dev, r, pd.size, pd.t_max, pd.hidden_size, pd.top_k, _stream()),
+               "mb_ep_dispatch_wait")
+    x_all, idx_all, _ = pd.gathered(T, r)
+    return moe_local_experts(x_all, idx_all, Wgu, Wd, e_begin, n_experts_total)
+
+
+def ep_combine(pd, T: int, out_pairs: torch.Tensor, pair_row: torch.Tensor | None, e_begin: int, e_local: int,
+               rank: int | None = None) -> None:
+    r = pd.rank if rank is None else rank
+    _lib.check(_lib.load().mb_ep_combine_push(out_pairs.data_ptr(), _ptr(pair_row), pd.peers_dev, r, pd.size, T,
+                                              pd.t_max, pd.hidden_size, pd.top_k, int(e_begin), int(e_local),
+                                              _stream()), "mb_ep_combine_push")
+
+
+def ep_finalize(pd, T: int, shared: torch.Tensor | None, residual: torch.Tensor | None,
+                rank: int | None = None) -> torch.Tensor:
+    _check_bf16(shared, residual)
+    r = pd.rank if rank is None else rank
+    y = torch.empty((T, pd.hidden_size), dtype=BF16, device=pd.area(r).device)
+    _lib.check(_lib.load().mb_ep_reduce_finalize(pd.peers_dev, r, pd.size, T, pd.t_max, pd.hidden_size, pd.top_k,
+                                                 _ptr(shared), _ptr(residual), y.data_ptr(), _stream()),
+               "mb_ep_reduce_finalize")
     return y
 
 

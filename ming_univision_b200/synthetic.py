@@ -304,3 +304,56 @@ def llm_state_dict(cfg: dict, vh: dict | None = None, feature_dim: int | None = 
         for k, v in rf_state_dict(rf_config_from_vishead(vh), seed, dtype).items():
             sd["diffloss." + k] = v
     return sd
+
+
+@torch.no_grad()
+def init_on_device(model, seed: int = 0) -> None:
+    """In-place seeded initialisation of a MingUniVisionForConditionalGeneration on ITS device (device-side generator):
+    the same distributions as mingtok_state_dict / llm_state_dict / rf_state_dict, drawn on the GPU because 16.8 B
+    parameters cannot be drawn on the host in bench time.  The values differ from the CPU factories (another RNG), so
+    this is for full-size timing runs; parity runs load the CPU-seeded state dicts.  Parameters left on the meta device
+    (experts of other expert-parallel ranks) are skipped; every tensor is seeded by (seed, name), so a rank's experts get
+    the values they would have in the unsharded model."""
+    for name, p in model.named_parameters():
+        if p.is_meta:
+            continue
+        h = hashlib.sha256(f"{seed}:dev:{name}".encode()).digest()
+        g = torch.Generator(device=p.device).manual_seed(int.from_bytes(h[:8], "little") % (2 ** 63))
+        key = name.split(".", 1)[1] if name.split(".", 1)[0] in ("vision", "model") else name
+
+        def normal(std, mean=0.0):
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32) * std + mean)
+
+        if name.startswith("vision."):
+            if key.endswith("cls_token") or key.endswith("pos_embed"):
+                normal(0.5)
+            elif ".norm" in key or "out_norm" in key:
+                normal(0.1, 1.0 if key.endswith(".weight") else 0.0)
+            elif key.endswith(".bias"):
+                normal(0.1)
+            else:
+                normal((0.3 if key.startswith("pixel_decoder.head") else 1.0) / math.sqrt(math.prod(p.shape[1:])))
+        elif name.startswith("model.diffloss."):
+            if ".in_ln." in key:
+                normal(0.1, 1.0 if key.endswith(".weight") else 0.0)
+            elif key.endswith(".bias"):
+                normal(0.1)
+            else:
+                std = 1.0 / math.sqrt(p.shape[1])
+                if "adaLN_modulation" in key:
+                    std *= 0.5
+                if "final_layer.linear" in key:
+                    std *= 2.0
+                normal(std)
+        else:  # Bailing-MoE, vis_head, linear_proj (llm_tensor's rules)
+            if "layernorm" in key or key.endswith("norm.weight") or key.startswith("vis_head.1"):
+                normal(0.1, 1.0 if key.endswith(".weight") else 0.0)
+            elif key.endswith(".bias"):
+                normal(0.1)
+            elif "word_embeddings" in key:
+                normal(1.0)
+            else:
+                std = 1.0 / math.sqrt(p.shape[-1])
+                if "gate.weight" in key and "experts" not in key:
+                    std *= 3.0
+                normal(std)

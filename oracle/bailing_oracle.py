@@ -132,15 +132,33 @@ def moe_block(sd, prefix, cfg, h, image_mask=None):
         im = image_mask.reshape(-1, 1)
         idx = idx * ~im + iidx * im
         w = w * ~im + iw * im
-    y = torch.zeros_like(x)
-    for t in range(x.shape[0]):
-        acc = torch.zeros(D)
-        for j in range(idx.shape[1]):
-            acc = acc + w[t, j] * mlp(sd, f"{prefix}.experts.{int(idx[t, j])}", x[t:t + 1])[0]
-        y[t] = acc
+    y = moe_infer(sd, prefix, cfg, x, idx, w)
     if cfg.get("num_shared_experts"):
         y = y + mlp(sd, prefix + ".shared_experts", x)
     return y.view(B, S, D), idx
+
+
+def moe_infer(sd, prefix, cfg, x, topk_ids, topk_weight):
+    """BailingMoeSparseMoeBlock.moe_infer — :608-639, step for step: count the tokens of every expert, argsort the
+    (token, slot) pairs by expert, run each hit expert ONCE on its contiguous group of rows, scatter the rows back to pair
+    order, weight them in the weights' dtype (fp32), sum over the slots, cast back."""
+    n_exp = cfg["num_experts"]
+    cnts = topk_ids.new_zeros((topk_ids.shape[0], n_exp))
+    cnts.scatter_(1, topk_ids, 1)
+    tokens_per_expert = cnts.sum(dim=0).tolist()
+    idxs = topk_ids.reshape(-1).argsort()
+    sorted_tokens = x[idxs // topk_ids.shape[1]]
+    outputs, start = [], 0
+    for e, n in enumerate(tokens_per_expert):
+        if n == 0:
+            continue
+        outputs.append(mlp(sd, f"{prefix}.experts.{e}", sorted_tokens[start:start + n]))
+        start += n
+    outs = torch.cat(outputs, dim=0) if outputs else sorted_tokens.new_empty(0)
+    new_x = torch.empty_like(outs)
+    new_x[idxs] = outs
+    return (new_x.view(*topk_ids.shape, -1).type(topk_weight.dtype).mul_(topk_weight.unsqueeze(dim=-1)).sum(dim=1)
+            .type(new_x.dtype))
 
 
 def decoder_layer(sd, l, cfg, h, mask4d, position_ids, cache, image_mask=None):

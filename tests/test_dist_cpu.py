@@ -19,11 +19,14 @@ WORKER = textwrap.dedent("""
     bench._barrier(world)
     m = bench._max_over_ranks(10.0 + rank, world, torch.device("cpu"))
     assert m == 11.0, m
-    # each rank draws its own images: different seeds per rank (bench.run_ours uses 1234 + 17 * rank + i)
+    # each rank runs its own edit round: different prompt / image per rank (bench.run_ours uses seed 100 * rank + i)
     from ming_univision_b200 import synthetic
-    a = synthetic.synthetic_images(1, 64, seed=1234 + 17 * rank)
+    ids, um, tm, img = bench.round_inputs(synthetic.LLM_CONFIG, 100 * rank)
+    assert ids.shape == (1, bench.PROMPT_LEN) and um.shape == tm.shape == (1, bench.PROMPT_LEN + 1)
+    assert int((ids == synthetic.LLM_CONFIG["image_patch_token"]).sum()) == bench.N_ENC and img.dtype == torch.uint8
+    assert int(tm.sum()) > 0 and not torch.equal(um, tm)          # -> 3 CFG rows (modeling_bailing_moe.py:1867-1891)
     import torch.distributed as dist
-    t = a.flatten()[:8].clone()
+    t = img.flatten()[:64].float().clone()
     gathered = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(gathered, t)
     assert not torch.equal(gathered[0], gathered[1])

@@ -67,6 +67,23 @@ WORKER = textwrap.dedent("""
         dist.all_gather(gathered, y2)
         assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree (peer mode)"
         print("rank", rank, "T", T, "peer-memory rel err vs single GPU", err, flush=True)
+    # "dispatch" mode (data parallel x expert parallel): every rank runs its OWN rows; dispatch and combine both go
+    # through peer memory inside the kernels of csrc/ep.cu.  Each rank's output must match the unsharded block on ITS rows.
+    from ming_univision_b200.ep import PeerDispatch
+    dblk = build()
+    pd = PeerDispatch(dist.group.WORLD, cfg["hidden_size"], cfg["num_experts_per_tok"], 64, dev)
+    dblk.set_expert_parallel(dist.group.WORLD, rank, world, mode="dispatch", peer=pd)
+    gr = torch.Generator().manual_seed(100 + rank)   # different rows on every rank
+    for T in (1, 3, 2, 8, 3, 40, 150):
+        x = torch.randn((1, T, cfg["hidden_size"]), generator=gr).to(dev).to(torch.bfloat16)
+        res = torch.randn((T, cfg["hidden_size"]), generator=gr).to(dev).to(torch.bfloat16)
+        y1, _, i1 = single._run(x.view(T, -1), res, None)
+        y2, _, i2 = dblk._run(x.view(T, -1), res, None)
+        torch.cuda.synchronize(); pd.check()
+        assert torch.equal(i1, i2)
+        err = ((y1.float() - y2.float()).norm() / y1.float().norm()).item()
+        assert err < 5e-3, err
+        print("rank", rank, "T", T, "dispatch-mode rel err vs single GPU", err, flush=True)
     # token- AND expert-sharded block: all-to-all dispatch / combine + all-gather (prefill-sized inputs; T = 7 stays
     # on the all-reduce path, T = 41 gives uneven token slices 21 + 20)
     a2a = build()

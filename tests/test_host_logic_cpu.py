@@ -125,16 +125,17 @@ def test_generate_rejects_misuse(stubbed):
 
 
 def test_committed_bench_line_keeps_the_contract():
-    """profiles/r01e_bench.json is a line bench.py printed on a B200: it must carry every key of the measurement contract
-    (metric / value / e2e / roofline / cpu_baseline / clocks / gpu_launches) with consistent numbers, and the reference
-    arm must print the same metric with its own keys — a guard against editing bench.py out of the contract."""
+    """The newest committed bench line (profiles/r02*_bench.json, else r01e_bench.json — lines bench.py printed on a B200)
+    must carry every key of the measurement contract (metric / value / e2e / roofline / cpu_baseline / clocks /
+    gpu_launches) with consistent numbers — a guard against editing bench.py out of the contract."""
+    import glob
     import json
     import os
-    import subprocess
-    import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    with open(os.path.join(root, "profiles", "r01e_bench.json")) as f:
+    cands = sorted(glob.glob(os.path.join(root, "profiles", "r02*_bench.json"))) or \
+        [os.path.join(root, "profiles", "r01e_bench.json")]
+    with open(cands[-1]) as f:
         d = json.load(f)
     with open(os.path.join(root, "BASELINE.json")) as f:
         base = json.load(f)
@@ -156,14 +157,32 @@ def test_committed_bench_line_keeps_the_contract():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
-    # the reference arm of the live bench.py (CPU, one tiny step)
+
+
+def test_reference_arm_prints_the_same_metric():
+    """The live `bench.py --impl reference` (CPU, one bounded sample step: the round with a 2-layer true-width LLM and
+    2 AR steps, ~1 min here): same metric / unit / workload as the GPU arm, its own keys, steps = the steps it timed."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "0"], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
-    assert line["impl"] == "reference" and line["metric"] == d["metric"] and line["unit"] == d["unit"]
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["steps"] == 1 and line["ms_per_step"] > 0 and line["higher_is_better"] is True
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["cpu_baseline"]["value"] == line["value"] and line["config"]["workload"] == d["config"]["workload"]
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["extrapolated"] is True
+    assert line["config"]["workload"] == bench.WORKLOAD and line["config"]["tokens_per_step"] == bench.TOKENS_PER_STEP
+    full = line["config"]["extrapolated_full_round_ms"] / 1e3
+    assert abs(line["value"] - bench.TOKENS_PER_STEP / full) / line["value"] < 1e-9
 
 
 def test_state_dict_load_through_the_parent_drops_every_pack():

@@ -179,3 +179,27 @@ def test_generate_image_matches_reference(name):
     assert torch.allclose(img, torch.from_numpy(g[f"{name}_image"]), atol=1e-3, rtol=1e-3)
     assert caches[0]["k"].shape[0] == int(g[f"{name}_cache_batch"]) == 1
     assert caches[0]["k"].shape[2] == int(g[f"{name}_cache_len"])
+
+
+def test_moe_block_at_true_widths_matches_reference():
+    """The oracle's MoE block (64 experts top-6, I = 1408, shared 2816, image gate) against the live reference's
+    `BailingMoeSparseMoeBlock.forward` at the true 16B-A3B widths (tests/golden/llm_wide.npz; layer 0 only: 0.55 B
+    parameters, drawn key by key in parallel)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import bailing_oracle as L
+
+    g = _load("llm_wide.npz")
+    cfg = synthetic.LLM_WIDE_CONFIG
+    pre = "model.layers.0.mlp."
+    shapes = {k: v for k, v in synthetic.llm_param_shapes(dict(cfg, num_hidden_layers=1)).items() if k.startswith(pre)}
+    with ThreadPoolExecutor(8) as ex:
+        sd = dict(zip(shapes, ex.map(lambda kv: synthetic.llm_tensor(kv[0], kv[1], 0), shapes.items())))
+    S, D = 192, cfg["hidden_size"]
+    x = torch.randn((1, S, D), generator=torch.Generator().manual_seed(int(g["moe_seed"])))
+    with torch.no_grad():
+        y, idx = L.moe_block(sd, pre[:-1], cfg, x, torch.from_numpy(g["prefill_image_mask"]))
+    rows = torch.from_numpy(g["prefill_rows"]).long()
+    assert torch.equal(idx.reshape(S, -1).sort(-1).values,
+                       torch.from_numpy(g["moe_topk_idx"].astype(np.int64)).sort(-1).values)
+    assert torch.allclose(y[0, rows], torch.from_numpy(g["moe_y_rows"]), atol=2e-5, rtol=1e-5)
