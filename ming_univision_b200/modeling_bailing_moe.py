@@ -320,6 +320,9 @@ class BailingMoeSparseMoeBlock(nn.Module):
         B, S, D = hidden_states.shape
         x2d = hidden_states.reshape(B * S, D).contiguous()
         y, logits, idx = self._run(x2d, None, image_mask)
+        if logits is not None and self.multi_gate and image_mask is not None:
+            # the reference returns the image gate's logits at image positions (:578-581); row selection only
+            logits = torch.where(image_mask.reshape(-1, 1).to(torch.bool), _dense(x2d, self._pack()["image_gate"]), logits)
         if logits is None:  # token-sharded all-to-all mode: every rank routed only its slice; redo the (cheap) router here
             pk, cfg = self._pack(), self.config
             logits = _dense(x2d, pk["gate"])
@@ -328,6 +331,8 @@ class BailingMoeSparseMoeBlock(nn.Module):
                 li, im = _dense(x2d, pk["image_gate"]), image_mask.reshape(-1).to(torch.uint8).contiguous()
             idx, _ = ops.router_topk(logits, cfg.num_experts_per_tok,
                                      cfg.num_experts_per_tok > 1 and cfg.norm_topk_prob, li, im)
+            if li is not None:
+                logits = torch.where(image_mask.reshape(-1, 1).to(torch.bool), li, logits)
         return y.view(B, S, D), (logits.view(B, S, -1), idx.view(B, S, -1).long())
 
 
