@@ -212,6 +212,22 @@ int mb_silu_add_rows(const void* temb, const void* c, void* out, int steps, int 
  * receives the bf16 copy that feeds input_proj on the next step. */
 int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, float dt, float text_cfg,
                      float image_cfg, void* stream);
+/* The whole sampler loop of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:134-179: `steps` Euler steps x
+ * [input_proj :371, `depth` x ResBlock :268-272, FinalLayer :288-292, CFG combine + Euler update]) as ONE persistent
+ * weight-streaming kernel (csrc/rf_fused.cu): one CTA per SM, every CTA owns a fixed slice of the output rows of every
+ * layer, the weights stream through a shared-memory ring by cp.async.bulk ahead of the grid barriers between layers.
+ * mb_rf_pack_weights re-orders one weight matrix W [N, K] (nn.Linear layout; swiglu: N = 2H, gate rows then up rows)
+ * ONCE into the per-CTA stage order for `n_cta` = mb_num_sms() CTAs (same byte count).  block_ptrs: DEVICE table
+ * [depth][6] = {w12 packed, b12 [2H], w3 packed, b3 [W], in_ln weight [W], in_ln bias [W]}; mod [steps * B, ld_mod] =
+ * the adaLN modulations of all steps (depth x (shift | scale | gate) then final (shift | scale)); x [B, C] fp32 is the
+ * noise on entry and the sample on exit; scratch h [B, W], hid [B, H], v [B, C] bf16 and one u32 barrier word.
+ * Supported shapes: mb_rf_fused_supported(B, W, H, C) (B <= 3 CFG rows, W and H multiples of 1024, C <= 32). */
+int mb_rf_fused_supported(int B, int W, int H, int C);
+int mb_rf_pack_weights(const void* W, int N, int K, int swiglu, int n_cta, void* out, void* stream);
+int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_w, const void* in_b, const void* fin_w,
+                       const void* fin_b, const void* mod, int64_t ld_mod, float* x, void* h_scratch, void* hid_scratch,
+                       void* v_scratch, uint32_t* barrier, int B, int W, int H, int C, int depth, int steps,
+                       float text_cfg, float image_cfg, int n_cta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Bailing-MoE AR step (mingunivision/modeling_bailing_moe.py).  `t_dev` arguments are optional DEVICE int32 scalars

@@ -86,6 +86,15 @@ _FUSED_ENV = os.environ.get("MB_FUSED_NORM")
 FUSED_NORM = _FUSED_ENV == "1"  # (LLM decode step: fused RMSNorm only when forced)
 
 
+# MB_RF_FUSED = 0 keeps the launch-per-layer path (A/B timing, tests); default: the persistent sampler kernel whenever
+# the shape fits it (B <= 3 rows, widths multiples of 1024 — the default head; the tiny test heads take the layer path).
+def _use_fused(pk, n_rows: int) -> bool:
+    if os.environ.get("MB_RF_FUSED", "1") == "0":
+        return False
+    H = pk.blocks[0][2].shape[0] // 2
+    return bool(_lib.load().mb_rf_fused_supported(n_rows, pk.W, H, pk.C))
+
+
 def _fuse_adaln(n_rows: int) -> bool:
     return _FUSED_ENV == "1" if _FUSED_ENV in ("0", "1") else n_rows <= 2
 
@@ -126,6 +135,32 @@ class _PackedRF:
             h = ops.gemv(tfreq[s0:s0 + 8], w0, b0, epi=ops.EPI_SILU)
             rows.append(ops.gemv(h, w2, b2))
         self.temb = torch.cat(rows, dim=0).contiguous()  # [steps, W] bf16
+        self._fused = None
+
+    def fused(self):
+        """Per-CTA stage-ordered copies of the w12 / w3 matrices + the device pointer table and scratch of the persistent
+        sampler kernel (mb_rf_sample_fused); built on first use."""
+        if self._fused is None:
+            lib = _lib.load()
+            n_cta = lib.mb_num_sms()
+            dev, W = self.device, self.W
+            H = self.blocks[0][2].shape[0] // 2
+            keep, table = [], []
+            s = torch.cuda.current_stream().cuda_stream
+            for (lnw, lnb, w12, b12, w3, b3) in self.blocks:
+                w12p, w3p = torch.empty_like(w12), torch.empty_like(w3)
+                _lib.check(lib.mb_rf_pack_weights(w12.data_ptr(), w12.shape[0], w12.shape[1], 1, n_cta, w12p.data_ptr(), s),
+                           "mb_rf_pack_weights")
+                _lib.check(lib.mb_rf_pack_weights(w3.data_ptr(), w3.shape[0], w3.shape[1], 0, n_cta, w3p.data_ptr(), s),
+                           "mb_rf_pack_weights")
+                keep += [w12p, w3p]
+                table.append([w12p.data_ptr(), b12.data_ptr(), w3p.data_ptr(), b3.data_ptr(), lnw.data_ptr(),
+                              lnb.data_ptr()])
+            self._fused = dict(n_cta=n_cta, H=H, keep=keep, table=torch.tensor(table, dtype=torch.int64, device=dev),
+                               h=torch.zeros((3, W), dtype=BF16, device=dev), hid=torch.zeros((3, H), dtype=BF16, device=dev),
+                               v=torch.zeros((3, self.C), dtype=BF16, device=dev),
+                               bar=torch.zeros((16,), dtype=torch.int32, device=dev))
+        return self._fused
 
 
 class RectifiedFlowLoss(nn.Module):
@@ -175,6 +210,17 @@ class RectifiedFlowLoss(nn.Module):
         c = ops.gemv(z_bf16, pk.cond_w, pk.cond_b)                       # cond_embed(z), once per token (:374)
         sy = ops.silu_add_rows(pk.temb, c)                               # SiLU(t_emb[s] + c) for every step
         mod = ops.linear(sy, pk.ada_w, pk.ada_b)                         # all adaLN modulations, [steps*B, depth*3W+2W]
+        if _use_fused(pk, B):
+            # the 16-step Euler loop as ONE persistent weight-streaming kernel (csrc/rf_fused.cu)
+            f = pk.fused()
+            lib = _lib.load()
+            _lib.check(lib.mb_rf_sample_fused(f["table"].data_ptr(), pk.in_w.data_ptr(), pk.in_b.data_ptr(),
+                                              pk.fin_w.data_ptr(), pk.fin_b.data_ptr(), mod.data_ptr(), mod.stride(0),
+                                              x_f32.data_ptr(), f["h"].data_ptr(), f["hid"].data_ptr(), f["v"].data_ptr(),
+                                              f["bar"].data_ptr(), B, W, f["H"], pk.C, depth, pk.steps, float(text_cfg),
+                                              float(image_cfg), f["n_cta"], torch.cuda.current_stream().cuda_stream),
+                       "mb_rf_sample_fused")
+            return
         x_bf16 = ops.affine(x_f32, 1.0, 0.0)
         dt = 1.0 / pk.steps
         for s in range(pk.steps):

@@ -51,14 +51,18 @@ def main():
     m = m.to(torch.bfloat16)
     weight_bytes = sum(p.numel() for p in m.parameters()) * 2
     ada = sum(p.numel() for n, p in m.named_parameters() if "adaLN" in n) * 2
-    for B in (2, 3):
-        z = torch.randn((B, cfg["z_channels"]), device=dev)
-        ms = timeit(lambda: m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1), iters=5, do_flush=False)
-        alg = 16 * (weight_bytes - ada) + ada  # bytes that must stream per token after the adaLN hoist
-        res.append({"op": f"rf.sample.B{B}", "ms": round(ms, 3), "tokens_per_s": round(1e3 / ms, 1),
-                    "alg_gb": round(alg / 1e9, 2), "gbs": round(alg / ms / 1e6, 1),
-                    "naive_alg_gb": round(16 * weight_bytes / 1e9, 2)})
-        print(res[-1], flush=True)
+    for fused in ("1", "0"):
+        os.environ["MB_RF_FUSED"] = fused
+        m._graphs = {}
+        for B in (2, 3):
+            z = torch.randn((B, cfg["z_channels"]), device=dev)
+            ms = timeit(lambda: m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1), iters=5, do_flush=False)
+            alg = 16 * (weight_bytes - ada) + ada  # bytes that must stream per token after the adaLN hoist
+            res.append({"op": f"rf.sample.B{B}.{'persistent' if fused == '1' else 'layers'}", "ms": round(ms, 3),
+                        "tokens_per_s": round(1e3 / ms, 1), "alg_gb": round(alg / 1e9, 2),
+                        "gbs": round(alg / ms / 1e6, 1), "naive_alg_gb": round(16 * weight_bytes / 1e9, 2)})
+            print(res[-1], flush=True)
+    os.environ["MB_RF_FUSED"] = "1"
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/bench_rf.json", "w") as f:
         json.dump(res, f, indent=1)
