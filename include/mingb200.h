@@ -223,6 +223,7 @@ int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, flo
  * noise on entry and the sample on exit; scratch h [B, W], hid [B, H], v [B, C] bf16 and one u32 barrier word.
  * Supported shapes: mb_rf_fused_supported(B, W, H, C) (B <= 3 CFG rows, W and H multiples of 1024, C <= 32). */
 int mb_rf_fused_supported(int B, int W, int H, int C);
+int mb_rf_set_debug(void* buf16_u64); /* debug aid: per-phase wall time of the first / last CTA, NULL = off */
 int mb_rf_pack_weights(const void* W, int N, int K, int swiglu, int n_cta, void* out, void* stream);
 int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_w, const void* in_b, const void* fin_w,
                        const void* fin_b, const void* mod, int64_t ld_mod, float* x, void* h_scratch, void* hid_scratch,

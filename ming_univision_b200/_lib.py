@@ -35,6 +35,7 @@ SIGNATURES = {
     "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],
     "mb_rf_fused_supported": [_i, _i, _i, _i],
+    "mb_rf_set_debug": [_vp],
     "mb_rf_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp],
     "mb_rf_sample_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i,
                            _vp],

@@ -21,6 +21,7 @@
 // Algorithmic bytes per launch: steps * depth * (2H*W + W*H) * 2 = 29.0 GB at the default sizes.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -44,6 +45,7 @@ struct RfFusedParams {
   uint32_t* bar;                                            // grid barrier counter (zeroed before the launch)
   int B, W, H, C, depth, steps;
   float dt, text_cfg, image_cfg;
+  unsigned long long* dbg;  // optional [2 CTAs][8] accumulated phase times in ns (mb_rf_set_debug), or null
 };
 
 __host__ __device__ inline int rf_unit_begin(int c, int R, int G) { return static_cast<int>((static_cast<int64_t>(c) * R) / G); }
@@ -60,12 +62,19 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// (not volatile: a pure function of its operands, so the compiler may schedule it around the shared loads)
 __device__ __forceinline__ void mma16816_rf(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                             uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// 16-byte shared load from a 32-bit shared-space address (no generic-address conversion in the hot loop); volatile keeps
+// it behind the mbarrier wait that guards the stage it reads
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
 }
 
 // Grid barrier of the consumer threads of all CTAs (all CTAs are resident: one per SM).  `target` = arrivals expected so
@@ -77,8 +86,7 @@ __device__ __forceinline__ void grid_barrier(uint32_t* bar, uint32_t target) {
     atomicAdd(bar, 1u);
     uint32_t spins = 0;
     while (static_cast<int32_t>(ld_acquire_gpu(bar) - target) < 0) {
-      __nanosleep(20);
-      if (++spins > (1u << 26)) {
+      if (++spins > (1u << 24)) {
         printf("rf_sample_fused: grid barrier timeout (block %d, target %u)\n", static_cast<int>(blockIdx.x), target);
         __trap();
       }
@@ -118,7 +126,8 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
   if (warp == kRfConsumerWarps) {
     // ===================== producer: streams every stage of the whole sample, in consumption order =====================
     if (lane == 0) {
-      uint32_t it = 0;
+      int slot = 0;
+      uint32_t round = 0;
       for (int step = 0; step < p.steps; ++step) {
         for (int blk = 0; blk < p.depth; ++blk) {
           const void* const* bp = p.blocks + blk * 6;
@@ -131,13 +140,15 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
             for (int t0 = u0; t0 < u1; t0 += ut) {
               const int nst = min(ut, u1 - t0) * rows_per_unit;  // storage rows of this tile
               const uint32_t bytes = static_cast<uint32_t>(nst) * kRfKC * 2;
-              for (int kc = 0; kc < K; kc += kRfKC, ++it) {
-                const int slot = it % kRfStages;
-                const uint32_t round = it / kRfStages;
+              for (int kc = 0; kc < K; kc += kRfKC) {
                 if (round > 0) mbar_wait(&empty_bar[slot], (round - 1) & 1);
                 mbar_arrive_expect_tx(&full_bar[slot], bytes);
                 bulk_load(ring + slot * kRfStageBytes, src, bytes, &full_bar[slot]);
                 src += bytes;
+                if (++slot == kRfStages) {
+                  slot = 0;
+                  ++round;
+                }
               }
             }
           }
@@ -149,8 +160,25 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
 
   // ================================================ consumers (256 threads) ================================================
   const int g = lane >> 2, t = lane & 3;
-  uint32_t it = 0;          // stage counter, in lockstep with the producer
+  int cslot = 0;            // ring slot / parity of the next stage, in lockstep with the producer
+  uint32_t cpar = 0;
   uint32_t nbar = 0;        // grid barriers passed
+  const uint32_t ring_s = smem_u32(ring);
+  const uint32_t brow_s = smem_u32(act) + min(g, B - 1) * act_pitch + t * 16;  // this lane's activation row (tokens >= B
+                                                                                // alias the last row: never stored)
+  // debug aid: thread 0 of the first and the last CTA accumulate wall time per phase kind (ns, %globaltimer)
+  const bool dbg_on = p.dbg != nullptr && tid == 0 && (c == 0 || c == G - 1);
+  unsigned long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long dbg_t = 0;
+  auto stamp = [&](int kind) {  // closes the interval since the previous stamp and books it under `kind`
+    if (dbg_on) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+      if (kind >= 0) dbg_acc[kind] += now - dbg_t;
+      dbg_t = now;
+    }
+  };
+  stamp(-1);
   auto block_sum3 = [&](float (&v)[kRfMaxRows]) {  // sums over the 256 consumer threads (fixed order), all rows at once
 #pragma unroll
     for (int b = 0; b < kRfMaxRows; ++b) {
@@ -180,44 +208,52 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
   }
   consumer_sync();
 
-  // streams the stages of one layer phase of this CTA; acc_out(tile_first_unit, n_units_in_tile, e, lane_value...) via red
-  auto stream_phase = [&](int K, int u0, int u1, bool swiglu, auto&& epilogue) {
+  // Streams the stages of one layer phase of this CTA.  Per tile: `epi_preload` requests the per-output parameters of the
+  // epilogue threads early, the 8 warps split every stage's 32 k groups, two accumulators halve the MMA dependency chain,
+  // the warps' partial sums meet in shared memory (double-buffered by tile parity) and `epilogue` finishes the tile.
+  // Rows / tokens a partial tile or B < 8 does not have alias valid ones (clamped addresses): their accumulator elements
+  // are garbage that the epilogues never store — so the hot loop has no predicates.
+  auto stream_phase = [&](int K, int u0, int u1, bool swiglu, auto&& epi_preload, auto&& epilogue) {
     const int ut = swiglu ? 8 : 16, rpu = swiglu ? 2 : 1;
     int tile_idx = 0;
+    constexpr int kJ = kRfKC / 32 / kRfConsumerWarps;  // k groups per warp and chunk
     for (int t0 = u0; t0 < u1; t0 += ut, ++tile_idx) {
       const int nu = min(ut, u1 - t0), nst = nu * rpu;
-      // storage rows of this lane's two MMA rows (g and g + 8), or -1
-      int srow_lo, srow_hi;
-      if (swiglu) {
-        srow_lo = g < nu ? g : -1;
-        srow_hi = g < nu ? nu + g : -1;
-      } else {
-        srow_lo = g < nu ? g : -1;
-        srow_hi = g + 8 < nu ? g + 8 : -1;
-      }
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int kc = 0; kc < K; kc += kRfKC, ++it) {
-        const int slot = it % kRfStages;
-        mbar_wait(&full_bar[slot], (it / kRfStages) & 1);
-        const uint8_t* sb = ring + slot * kRfStageBytes;
-        const uint8_t* arow = act + min(g, B - 1) * act_pitch + (kc * 2) + t * 16;
+      const int srow_lo = min(g, nu - 1);
+      const int srow_hi = swiglu ? nu + min(g, nu - 1) : min(g + 8, nu - 1);
+      const uint32_t off_lo = srow_lo * 64 + t * 16, off_hi = srow_hi * 64 + t * 16;
+      const uint32_t kg_stride = nst * 64;  // bytes per k group in a chunk
+      epi_preload(t0, nu);
+      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+      // one chunk through the shared-memory ring
+      auto ring_chunk = [&](int kc) {
+        const uint32_t bb = brow_s + kc * 2 + warp * 64;
+        mbar_wait(&full_bar[cslot], cpar);
+        const uint32_t sb = ring_s + cslot * kRfStageBytes + warp * kg_stride;
+        uint4 alo[kJ], ahi[kJ], xv[kJ];
 #pragma unroll
-        for (int j = 0; j < kRfKC / 32 / kRfConsumerWarps; ++j) {
-          const int kg = warp + j * kRfConsumerWarps;
-          uint4 alo = make_uint4(0, 0, 0, 0), ahi = make_uint4(0, 0, 0, 0), xb4 = make_uint4(0, 0, 0, 0);
-          if (srow_lo >= 0) alo = *reinterpret_cast<const uint4*>(sb + (kg * nst + srow_lo) * 64 + t * 16);
-          if (srow_hi >= 0) ahi = *reinterpret_cast<const uint4*>(sb + (kg * nst + srow_hi) * 64 + t * 16);
-          if (g < B) xb4 = *reinterpret_cast<const uint4*>(arow + kg * 64);
-          mma16816_rf(acc, alo.x, ahi.x, alo.y, ahi.y, xb4.x, xb4.y);
-          mma16816_rf(acc, alo.z, ahi.z, alo.w, ahi.w, xb4.z, xb4.w);
+        for (int j = 0; j < kJ; ++j) {
+          alo[j] = lds128(sb + j * kRfConsumerWarps * kg_stride + off_lo);
+          ahi[j] = lds128(sb + j * kRfConsumerWarps * kg_stride + off_hi);
+          xv[j] = lds128(bb + j * kRfConsumerWarps * 64);
+        }
+#pragma unroll
+        for (int j = 0; j < kJ; ++j) {
+          mma16816_rf(acc0, alo[j].x, ahi[j].x, alo[j].y, ahi[j].y, xv[j].x, xv[j].y);
+          mma16816_rf(acc1, alo[j].z, ahi[j].z, alo[j].w, ahi[j].w, xv[j].z, xv[j].w);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
-      }
+        if (lane == 0) mbar_arrive(&empty_bar[cslot]);
+        if (++cslot == kRfStages) {
+          cslot = 0;
+          cpar ^= 1;
+        }
+      };
+      for (int kc = 0; kc < K; kc += kRfKC) ring_chunk(kc);
       // cross-warp reduction of the K slices (fixed order), double-buffered by tile parity
       float* rb = red + (tile_idx & 1) * kRfConsumerWarps * 4 * 32;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) rb[(warp * 4 + e) * 32 + lane] = acc[e];
+      for (int e = 0; e < 4; ++e) rb[(warp * 4 + e) * 32 + lane] = acc0[e] + acc1[e];
       consumer_sync();
       epilogue(t0, nu, rb);
     }
@@ -229,6 +265,34 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
     return s;
   };
 
+  // adaLN parameters of the NEXT prologue (this thread's <= 2 chunks of gamma / beta and of every row's shift / scale).
+  // They do not depend on the activations, so they are requested BEFORE the grid barrier that precedes the prologue: their
+  // latency (queued behind the bulk weight stream) overlaps the barrier instead of sitting on the critical path after it.
+  constexpr int kCh = 2;
+  uint4 pre_gm[kCh], pre_bt[kCh], pre_sh[kRfMaxRows][kCh], pre_sc[kRfMaxRows][kCh];
+  auto preload = [&](int step, int blk) {
+    const bool fin = blk == p.depth;
+    if (fin && c >= C) return;
+    const void* const* bp = p.blocks + (fin ? 0 : blk) * 6;
+    const __nv_bfloat16* lnw = fin ? nullptr : static_cast<const __nv_bfloat16*>(bp[4]);
+    const __nv_bfloat16* lnb = fin ? nullptr : static_cast<const __nv_bfloat16*>(bp[5]);
+    const __nv_bfloat16* mb = p.mod + static_cast<int64_t>(step) * B * p.ld_mod + static_cast<int64_t>(blk) * 3 * W;
+#pragma unroll
+    for (int cc = 0; cc < kCh; ++cc) {
+      const int i = tid + cc * kRfConsumerWarps * 32;
+      const bool ok = i < W / 8;
+      pre_gm[cc] = (ok && lnw) ? *reinterpret_cast<const uint4*>(lnw + i * 8) : make_uint4(0, 0, 0, 0);
+      pre_bt[cc] = (ok && lnb) ? *reinterpret_cast<const uint4*>(lnb + i * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int b = 0; b < kRfMaxRows; ++b) {
+        const bool okb = ok && b < B;
+        const __nv_bfloat16* sh = mb + static_cast<int64_t>(b) * p.ld_mod;
+        pre_sh[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + i * 8) : make_uint4(0, 0, 0, 0);
+        pre_sc[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + W + i * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
+
   for (int step = 0; step < p.steps; ++step) {
     // ---- input_proj (:371) on this CTA's columns of h:  h[b][n] = bf16(x_bf16[b] . in_w[n] + in_b[n])
     for (int i = tid; i < (wu1 - wu0) * B; i += kRfConsumerWarps * 32) {
@@ -238,7 +302,10 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
         s += __bfloat162float(p.in_w[static_cast<int64_t>(n) * C + cc]) * __bfloat162float(xb[b * C + cc]);
       p.h[static_cast<int64_t>(b) * W + n] = __float2bfloat16_rn(s + __bfloat162float(p.in_b[n]));
     }
+    preload(step, 0);
+    stamp(5);
     grid_barrier(p.bar, ++nbar * G);
+    stamp(6);
 
     const __nv_bfloat16* mod_step = p.mod + static_cast<int64_t>(step) * B * p.ld_mod;
     for (int blk = 0; blk <= p.depth; ++blk) {
@@ -251,7 +318,6 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
       // (the final layer needs them only in the CTAs that compute an output channel)
       if (!final_layer || c < C) {
         // each thread keeps its 16-byte chunks of all rows in registers (W / 8 <= 2 * 256 chunks per row)
-        constexpr int kCh = 2;
         uint4 raw[kRfMaxRows][kCh];
         float sum[kRfMaxRows], sq[kRfMaxRows];
         auto unpack8 = [](const uint4& q, float (&f)[8]) {
@@ -296,16 +362,15 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
           const int i = tid + cc * kRfConsumerWarps * 32;
           if (i >= W / 8) continue;
           __nv_bfloat16 gm[8], bt[8];
-          if (lnw) *reinterpret_cast<uint4*>(gm) = *reinterpret_cast<const uint4*>(lnw + i * 8);
-          if (lnb) *reinterpret_cast<uint4*>(bt) = *reinterpret_cast<const uint4*>(lnb + i * 8);
+          *reinterpret_cast<uint4*>(gm) = pre_gm[cc];
+          *reinterpret_cast<uint4*>(bt) = pre_bt[cc];
 #pragma unroll
           for (int b = 0; b < kRfMaxRows; ++b) {
             if (b >= B) continue;
             const float mean = sum[b], rstd = rsqrtf(sq[b] / W + 1e-6f);
-            const __nv_bfloat16* sh = mod_blk + static_cast<int64_t>(b) * p.ld_mod;
             __nv_bfloat16 shv[8], scv[8];
-            *reinterpret_cast<uint4*>(shv) = *reinterpret_cast<const uint4*>(sh + i * 8);
-            *reinterpret_cast<uint4*>(scv) = *reinterpret_cast<const uint4*>(sh + W + i * 8);
+            *reinterpret_cast<uint4*>(shv) = pre_sh[b][cc];
+            *reinterpret_cast<uint4*>(scv) = pre_sc[b][cc];
             float f[8], o[8];
             unpack8(raw[b][cc], f);
 #pragma unroll
@@ -322,6 +387,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
         }
       }
       consumer_sync();
+      stamp(0);
       if (final_layer) {
         // ---- FinalLayer linear (:291): v[b][ch] = bf16(a[b] . fin_w[ch] + fin_b[ch]); CTA ch < C computes channel ch
         if (c < C) {
@@ -341,7 +407,9 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
           block_sum3(dot);
           if (tid < B) p.v[tid * C + c] = __float2bfloat16_rn(dot[tid] + __bfloat162float(p.fin_b[c]));
         }
+        stamp(5);
         grid_barrier(p.bar, ++nbar * G);
+        stamp(6);
         // ---- CFG combine + Euler (:145-179), replicated in every CTA on its shared-memory copy of x
         for (int ch = tid; ch < C; ch += kRfConsumerWarps * 32) {
           float stepv[kRfMaxRows];
@@ -369,24 +437,37 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
           }
         }
         consumer_sync();
+        stamp(5);
         break;
       }
 
       // ---- w12 + SwiGLU (:54-72 via :271): hid[b][u] = bf16(silu(bf16(a.Wg[u] + bg[u]))) * bf16(a.Wu[u] + bu[u])
       const __nv_bfloat16* b12 = static_cast<const __nv_bfloat16*>(bp[1]);
-      stream_phase(W, hu0, hu1, true, [&](int t0, int nu, const float* rb) {
-        if (tid < 64) {
-          const int ln = tid & 31, sel = tid >> 5;  // accumulator elements sel (gate) and sel + 2 (up) of lane ln
-          const int gg = ln >> 2, tok = 2 * (ln & 3) + sel;
-          if (gg < nu && tok < B) {
-            const int u = t0 + gg;
-            const float x1 = bf16_round(red_sum(rb, sel, ln) + __bfloat162float(b12[u]));
-            const float x2 = bf16_round(red_sum(rb, sel + 2, ln) + __bfloat162float(b12[H + u]));
-            p.hid[static_cast<int64_t>(tok) * H + u] = __float2bfloat16_rn(bf16_round(silu(x1)) * x2);
-          }
-        }
-      });
+      float e_bg = 0.f, e_bu = 0.f;
+      stream_phase(W, hu0, hu1, true,
+                   [&](int t0, int nu) {
+                     if (tid < 64) {
+                       const int gg = (tid & 31) >> 2, tok = 2 * (tid & 3) + (tid >> 5);
+                       if (gg < nu && tok < B) {
+                         e_bg = __bfloat162float(b12[t0 + gg]);
+                         e_bu = __bfloat162float(b12[H + t0 + gg]);
+                       }
+                     }
+                   },
+                   [&](int t0, int nu, const float* rb) {
+                     if (tid < 64) {
+                       const int ln = tid & 31, sel = tid >> 5;  // accumulator elements sel (gate), sel + 2 (up) of lane ln
+                       const int gg = ln >> 2, tok = 2 * (ln & 3) + sel;
+                       if (gg < nu && tok < B) {
+                         const float x1 = bf16_round(red_sum(rb, sel, ln) + e_bg);
+                         const float x2 = bf16_round(red_sum(rb, sel + 2, ln) + e_bu);
+                         p.hid[static_cast<int64_t>(tok) * H + t0 + gg] = __float2bfloat16_rn(bf16_round(silu(x1)) * x2);
+                       }
+                     }
+                   });
+      stamp(1);
       grid_barrier(p.bar, ++nbar * G);
+      stamp(2);
 
       // ---- w3 + gated residual (:272): h[b][n] = bf16(h[b][n] + bf16(gate[b][n] * bf16(hid[b] . W3[n] + b3[n])))
       for (int i = tid; i < B * (H / 8); i += kRfConsumerWarps * 32) {
@@ -396,23 +477,40 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
       }
       consumer_sync();
       const __nv_bfloat16* b3 = static_cast<const __nv_bfloat16*>(bp[3]);
-      stream_phase(H, wu0, wu1, false, [&](int t0, int nu, const float* rb) {
-        if (tid < 128) {
-          const int ln = tid & 31, e = tid >> 5;
-          const int r = (ln >> 2) + 8 * (e >> 1), tok = 2 * (ln & 3) + (e & 1);
-          if (r < nu && tok < B) {
-            const int n = t0 + r;
-            const float vv = bf16_round(red_sum(rb, e, ln) + __bfloat162float(b3[n]));
-            const float gate = __bfloat162float(mod_blk[static_cast<int64_t>(tok) * p.ld_mod + 2 * W + n]);
-            const float gh = bf16_round(gate * vv);
-            const int64_t o = static_cast<int64_t>(tok) * W + n;
-            p.h[o] = __float2bfloat16_rn(__bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.h) + o))) + gh);
-          }
-        }
-      });
+      float e_b3 = 0.f, e_gate = 0.f, e_h = 0.f;
+      stream_phase(H, wu0, wu1, false,
+                   [&](int t0, int nu) {
+                     if (tid < 128) {
+                       const int ln = tid & 31, e = tid >> 5;
+                       const int r = (ln >> 2) + 8 * (e >> 1), tok = 2 * (ln & 3) + (e & 1);
+                       if (r < nu && tok < B) {
+                         const int n = t0 + r;
+                         e_b3 = __bfloat162float(b3[n]);
+                         e_gate = __bfloat162float(mod_blk[static_cast<int64_t>(tok) * p.ld_mod + 2 * W + n]);
+                         e_h = __bfloat162float(__ushort_as_bfloat16(
+                             __ldcg(reinterpret_cast<const unsigned short*>(p.h) + static_cast<int64_t>(tok) * W + n)));
+                       }
+                     }
+                   },
+                   [&](int t0, int nu, const float* rb) {
+                     if (tid < 128) {
+                       const int ln = tid & 31, e = tid >> 5;
+                       const int r = (ln >> 2) + 8 * (e >> 1), tok = 2 * (ln & 3) + (e & 1);
+                       if (r < nu && tok < B) {
+                         const float vv = bf16_round(red_sum(rb, e, ln) + e_b3);
+                         const float gh = bf16_round(e_gate * vv);
+                         p.h[static_cast<int64_t>(tok) * W + t0 + r] = __float2bfloat16_rn(e_h + gh);
+                       }
+                     }
+                   });
+      preload(step, blk + 1);
+      stamp(3);
       grid_barrier(p.bar, ++nbar * G);
+      stamp(4);
     }
   }
+  if (dbg_on)
+    for (int i = 0; i < 8; ++i) p.dbg[(c == 0 ? 0 : 8) + i] = dbg_acc[i];
   if (c == 0)
     for (int i = tid; i < B * C; i += kRfConsumerWarps * 32) p.x[i] = xs[i];
 }
@@ -459,6 +557,15 @@ extern "C" int mb_rf_pack_weights(const void* W, int N, int K, int swiglu, int n
   return MB_OK;
 }
 
+static unsigned long long* g_rf_dbg = nullptr;
+// Debug aid (tools/debug_rf_timing.py): device buffer of 16 u64 — per phase kind accumulated ns of the first and the last
+// CTA: 0 adaLN prologue, 1 w12 stream + epilogue, 2 barrier after w12, 3 w3 stream + epilogue (incl. staging hid),
+// 4 barrier after w3, 5 input_proj / final layer / Euler, 6 their barriers.  NULL switches it off.
+extern "C" int mb_rf_set_debug(void* buf) {
+  g_rf_dbg = static_cast<unsigned long long*>(buf);
+  return MB_OK;
+}
+
 extern "C" int mb_rf_fused_supported(int B, int W, int H, int C) {
   return (B >= 1 && B <= kRfMaxRows && W % kRfKC == 0 && H % kRfKC == 0 && H >= W && C >= 1 && C <= 32 &&
           kRfStages * kRfStageBytes + kRfMaxRows * (H * 2 + 64) + 10 * 1024 <= 226 * 1024)
@@ -489,6 +596,7 @@ extern "C" int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_
   p.bar = barrier;
   p.B = B; p.W = W; p.H = H; p.C = C; p.depth = depth; p.steps = steps;
   p.dt = 1.0f / steps; p.text_cfg = text_cfg; p.image_cfg = image_cfg;
+  p.dbg = g_rf_dbg;
   const size_t smem = static_cast<size_t>(kRfStages) * kRfStageBytes + static_cast<size_t>(kRfMaxRows) * (H * 2 + 64) +
                       2 * kRfConsumerWarps * 4 * 32 * 4 + 64 * 4 + kRfMaxRows * 32 * 4 + kRfMaxRows * 32 * 2 + 64;
   MB_CHECK_ARG(smem <= 226 * 1024, MB_ERR_SHAPE, "mb_rf_sample_fused: %zu bytes of shared memory", smem);
