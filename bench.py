@@ -30,7 +30,12 @@ tokens alone are reported next to it (`generated_tokens_per_s`).
             sample of the same round — the LLM depth-reduced to 2 of its 28 layers at the true widths and
             2 of the 65 AR steps, every stage timed separately and extrapolated (flagged) to the full round.
 
-N > 1: every rank runs ITS OWN round (its own image / prompt) and the routed experts are SHARDED over the ranks
+Batched serving: `--images G` (default 2) edit rounds are generated TOGETHER on a GPU — G x 3 CFG rows share every pass
+over the LLM / RF-head / semantic-decoder weights (the reference asserts one sequence, modeling_bailing_moe.py:1865; every
+request's image is bit-identical to what it gets alone, tests/test_llm_wide_gpu.py).  tokens per step = G x 128; the
+one-request-at-a-time number is reported as stages.single_request.
+
+N > 1: every rank runs ITS OWN rounds (its own image / prompt) and the routed experts are SHARDED over the ranks
 (expert parallelism, 64 / N experts per GPU): per MoE layer the rows are dispatched to the expert owners and the partial
 sums combined back through NVLink peer memory inside the kernels (csrc/ep.cu; no NCCL call, the whole token step stays
 one CUDA graph).  Per-GPU work is fixed -> "scaling": "weak"; value = all ranks' tokens / max-over-ranks time.
@@ -61,7 +66,7 @@ TOKENS_PER_STEP = N_ENC + N_GEN
 CFG_ROWS = 3
 N_TEXT_HEAD, N_TEXT_TAIL = 8, 32   # prompt = 8 text ids + 64 <imagePatch> + 32 text ids  (+ the <image> start token)
 PROMPT_LEN = N_TEXT_HEAD + N_ENC + N_TEXT_TAIL
-WORKLOAD = ("Ming-UniVision 16B-A3B in-context edit round at 256x256: MingTok enc (64 tokens) -> 104-token prefill -> "
+WORKLOAD = ("Ming-UniVision 16B-A3B in-context edit rounds at 256x256, each: MingTok enc (64 tokens) -> 104-token prefill -> "
             "64 AR steps x (28-layer MoE, B=3 CFG rows, RF head 16 Euler steps, semantic-decoder step) -> pixel decoder; "
             "synthetic weights, synthetic image / prompt")
 MINGTOK_BATCH = 64
@@ -396,19 +401,23 @@ def run_ours(args, world, rank, local):
     # several distinct rounds are cycled (and every rank has its own): inputs differ step to step; the 38 GB of weights
     # a round streams 65 times exceed the 126 MB L2 by far, so nothing a step reads is left over from the previous one
     n_bufs = 3
-    rounds = [round_inputs(llm_cfg, 100 * rank + i) for i in range(n_bufs)]
-    ids_host = [r[0].pin_memory() for r in rounds]
-    img_host = [r[3].pin_memory() for r in rounds]
-    um, tm = rounds[0][1].to(dev), rounds[0][2].to(dev)
-    ids_dev = [r[0].to(dev) for r in rounds]
-    px_dev = [ops.image_preprocess(r[3].to(dev), SIZE, SIZE, out_dtype=torch.bfloat16) for r in rounds]
+    NI = args.images
+    if NI < 1 or NI * CFG_ROWS > 6:
+        raise SystemExit("--images: 1 or 2 rounds per step (images x 3 CFG rows <= 6 rows of the weight-streaming kernels)")
+    rounds = [[round_inputs(llm_cfg, 1000 * rank + 10 * i + j) for j in range(NI)] for i in range(n_bufs)]
+    ids_host = [torch.cat([r[0] for r in rs]).pin_memory() for rs in rounds]                 # [NI, 104]
+    img_host = [torch.stack([r[3] for r in rs]).pin_memory() for rs in rounds]               # [NI, 256, 256, 3] u8
+    um = rounds[0][0][1].to(dev).expand(NI, -1).contiguous()
+    tm = rounds[0][0][2].to(dev).expand(NI, -1).contiguous()
+    ids_dev = [t.to(dev) for t in ids_host]
+    px_dev = [ops.image_preprocess(t.to(dev), SIZE, SIZE, out_dtype=torch.bfloat16) for t in img_host]
 
     def step_resident(i):
         img, _ = model.generate_image_from_prompt(ids_dev[i % n_bufs], pixel_values=px_dev[i % n_bufs],
                                                   uncond_attention_mask=um, text_uncond_attention_mask=tm)
         return img
 
-    host_out = torch.empty((1, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
+    host_out = torch.empty((NI, SIZE, SIZE, 3), dtype=torch.uint8).pin_memory()
 
     def step_e2e(i):
         ids = ids_host[i % n_bufs].to(dev, non_blocking=True)
@@ -473,61 +482,100 @@ def run_ours(args, world, rank, local):
 
     ms_round, _ = timed(lambda: step_resident(0))
     ms_enc, _ = timed(lambda: model.extract_image_feature(px_dev[0]))
-    feats64 = model.vision(px_dev[0])["x_norm_patchtokens"]
+    feats64 = model.vision(px_dev[0])["x_norm_patchtokens"]                   # [NI, 64, 1024]
     ms_pix, _ = timed(lambda: model.vision.forward_pixel_decoder(feats64))
-    z = torch.randn((CFG_ROWS, 3072), device=dev).to(torch.bfloat16)
-    llm.diffloss.sample(z, 1.0, 3.0, 1.1)
-    ms_rf, _ = timed(lambda: [llm.diffloss.sample(z, 1.0, 3.0, 1.1) for _ in range(8)])
+    z = torch.randn((CFG_ROWS * NI, 3072), device=dev).to(torch.bfloat16)
+    llm.diffloss.sample(z, 1.0, 3.0, 1.1, groups=NI)
+    ms_rf, _ = timed(lambda: [llm.diffloss.sample(z, 1.0, 3.0, 1.1, groups=NI) for _ in range(8)])
     ms_rf /= 8
 
-    # ---- roofline of the dominant kernel: every weight-streaming (gemv) launch of TWO token steps is recorded on the eager
-    # path and the list re-issued back to back between two CUDA events (PDL chain intact)
+    # ---- the same round ONE request at a time (the reference's batch-1 semantics, modeling_bailing_moe.py:1865) — all
+    # ranks run it (the MoE layers exchange rows in lockstep)
+    single = None
+    if NI > 1:
+        def step_single(i):
+            return model.generate_image_from_prompt(ids_dev[i % n_bufs][0:1], pixel_values=px_dev[i % n_bufs][0:1],
+                                                    uncond_attention_mask=um[0:1], text_uncond_attention_mask=tm[0:1])[0]
+
+        step_single(0)
+        ms_single, _ = timed(lambda: [step_single(i) for i in range(3)])
+        ms_single /= 3
+        single = {"ms_per_round": ms_single, "tokens_per_s": TOKENS_PER_STEP / (ms_single / 1e3),
+                  "generated_tokens_per_s": N_GEN / (ms_single / 1e3), "steps": 3,
+                  "note": "one edit round per step and GPU (3 rows per pass over the weights instead of 6)"}
+        step_resident(0)
+
+    # ---- roofline of the dominant kernel, the persistent RF sampler (one launch per generated token: 16 Euler steps x 12
+    # residual blocks): CUDA events around its launches on the eager path (launching stream), algorithmic bytes = the
+    # bf16 weights it must stream = steps x depth x 3 H W x 2
+    from ming_univision_b200 import diff_loss_rf_swiglu as rfmod
+
+    llm.diffloss.use_cuda_graph = False
+    llm.diffloss.sample(z, 1.0, 3.0, 1.1, groups=NI)
+    rfmod.FUSED_PROFILE = []
+    for _ in range(5):
+        llm.diffloss.sample(z, 1.0, 3.0, 1.1, groups=NI)
+    torch.cuda.synchronize()
+    rf_prof, rfmod.FUSED_PROFILE = rfmod.FUSED_PROFILE, None
+    llm.diffloss.use_cuda_graph = True
+    rf_bytes = rf_prof[0][0] if rf_prof else 0
+    rf_kernel_ms = statistics.median(a.elapsed_time(b) for _, a, b in rf_prof) if rf_prof else float("nan")
+
+    # ---- second: every launch of the per-layer weight-streaming kernel (gemv: LLM dense layers, semantic decoder, heads)
+    # of TWO token steps is recorded on the eager path and the list re-issued back to back between two CUDA events
     cfg_obj = llm.config
-    saved = (cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph, llm.diffloss.use_cuda_graph)
-    cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph, llm.diffloss.use_cuda_graph = 1, False, False
+    saved = (cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph)
+    cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph = 1, False
     ops.GEMV_REPLAY = []
     step_resident(0)
     torch.cuda.synchronize()
     replay, ops.GEMV_REPLAY = ops.GEMV_REPLAY, None
-    cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph, llm.diffloss.use_cuda_graph = saved
+    cfg_obj.num_image_tokens_for_gen, llm.use_cuda_graph = saved
     n_token_steps = 2
     for fn, _, _ in replay:
         fn()
     ms_gemv, _ = timed(lambda: [fn() for _ in range(3) for fn, _, _ in replay])
     ms_gemv /= 3
     gemv_bytes = sum(b for _, b, _ in replay)
-    step_resident(0)  # re-capture-free sanity: the graph path still works after the eager detour
+    step_resident(0)  # the graph path still works after the eager detour
 
     if rank != 0:
         return
     peaks = _peaks()
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "gemv_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "rf_fused_traffic.json")) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj["mean_dram_bytes_per_launch"], tj["source"]
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     except (OSError, KeyError, ValueError):
         pass
     ms_step = ms_res / args.steps
     ms_ar_step = (ms_round - ms_enc - ms_pix) / (N_GEN + 1)     # includes the prefill's share (one prefill per round)
-    achieved = gemv_bytes / (ms_gemv / 1e3) / 1e9
+    achieved = rf_bytes / (rf_kernel_ms / 1e3) / 1e9
     gemv_ms_per_token = ms_gemv / n_token_steps
-    roofline = {"bound": "hbm", "kernel": "mb::gemv_bf16_kernel (weight streaming: RF head, LLM dense layers, semantic decoder)",
+    roofline = {"bound": "hbm", "kernel": "mb::rf_sample_fused_kernel (persistent weight streaming: the RF head's 16 Euler "
+                                          "steps x 12 residual blocks, cp.async.bulk ring + mma.sync)",
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peaks["source"], "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write)",
-                "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": gemv_bytes / max(len(replay), 1),
-                "avg_launch_us": 1e3 * ms_gemv / max(len(replay), 1),
-                "launches_per_token_step": len(replay) // n_token_steps,
-                "gemv_bytes_per_token_step": gemv_bytes / n_token_steps,
-                "gemv_ms_per_token_step": gemv_ms_per_token, "gemv_share_of_token_step": gemv_ms_per_token / ms_ar_step,
-                "timing": "replay of two token steps' gemv launches back to back, CUDA events",
-                "token_step_ms": ms_ar_step,
-                "token_step_gbs_survey_bytes": 46.0e9 / (ms_ar_step / 1e3) / 1e9,
-                "note": "algorithmic bytes = N*K*2 per launch; the token step also streams the routed experts "
-                        "(mb::moe_expert_kernel, <= 18 x 17.3 MB x 28 layers) and the KV caches, not counted here; "
-                        "token_step_gbs_survey_bytes uses SURVEY.md §8d's 46 GB/token (RF without the adaLN hoist)"}
-    stages = {"round_ms": ms_round, "enc_ms": ms_enc, "pixel_decoder_ms": ms_pix, "rf_sample_ms": ms_rf,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": rf_bytes, "launch_ms": rf_kernel_ms,
+                "launches_per_token_step": 1, "rows_per_launch": CFG_ROWS * NI,
+                "share_of_token_step": rf_kernel_ms / ms_ar_step, "token_step_ms": ms_ar_step,
+                "timing": "CUDA events around the kernel's launches (eager path, launching stream), median of 5",
+                "token_step_gbs_survey_bytes": 46.0e9 * NI / (ms_ar_step / 1e3) / 1e9,
+                "second_kernel": {"kernel": "mb::gemv_bf16_kernel (per-layer weight streaming: LLM dense layers, semantic "
+                                            "decoder, heads)",
+                                  "achieved": gemv_bytes / (ms_gemv / 1e3) / 1e9, "unit": "GB/s",
+                                  "frac": gemv_bytes / (ms_gemv / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                  "launches_per_token_step": len(replay) // n_token_steps,
+                                  "bytes_per_token_step": gemv_bytes / n_token_steps,
+                                  "ms_per_token_step": gemv_ms_per_token,
+                                  "share_of_token_step": gemv_ms_per_token / ms_ar_step,
+                                  "timing": "replay of two token steps' launches back to back, CUDA events"},
+                "note": "algorithmic bytes = the bf16 weights a launch must stream; the token step also streams the routed "
+                        "experts (mb::moe_expert_kernel, <= 18 x 17.3 MB x 28 layers per 3 rows) and the KV caches; "
+                        "token_step_gbs_survey_bytes uses SURVEY.md §8d's 46 GB per token and request (RF without the "
+                        "adaLN hoist) x the requests generated together"}
+    stages = {"single_request": single, "round_ms": ms_round, "enc_ms": ms_enc, "pixel_decoder_ms": ms_pix, "rf_sample_ms": ms_rf,
               "ar_step_ms_incl_prefill_share": ms_ar_step,
               "mingtok_enc_dec": measure_mingtok_stage(model.vision, dev)}
 
@@ -542,20 +590,22 @@ def run_ours(args, world, rank, local):
                "sample": ref.SAMPLE, "extrapolated": True, "stages_s": {k: round(v, 4) for k, v in ex.items()}}
         parity = parity_vs_oracle(ref, t["_keep"], dev)
 
-    tokens_all = TOKENS_PER_STEP * world
+    tokens_all = TOKENS_PER_STEP * world * NI
     line = {"metric": METRIC, "value": tokens_all * args.steps / (ms_res / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "generated_tokens_per_s": N_GEN * world * args.steps / (ms_res / 1e3),
+            "generated_tokens_per_s": N_GEN * world * NI * args.steps / (ms_res / 1e3),
             "config": {"workload": WORKLOAD, "tokens_per_step": tokens_all, "encoded_tokens_per_round": N_ENC,
-                       "generated_tokens_per_round": N_GEN, "cfg_rows": CFG_ROWS, "rounds_per_step": world,
+                       "generated_tokens_per_round": N_GEN, "cfg_rows": CFG_ROWS, "rounds_per_step": world * NI,
+                       "rounds_generated_together_per_gpu": NI,
                        "parallelism": (f"dp{world} x ep{world}: one edit round per GPU, routed experts sharded "
                                        f"{64 // world} per GPU, dispatch / combine through NVLink peer memory in-kernel "
                                        "(no NCCL on the data path)") if world > 1 else "1 GPU, all 64 experts resident",
                        "l2_policy": "3 distinct rounds cycled; the 38 GB of weights streamed per AR step exceed the 126 MB L2",
                        "model_build_s": round(t_build, 1), "weights_gb_per_gpu": round(mem_gb, 1)},
             "e2e": {"value": tokens_all * args.steps / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": SIZE * SIZE * 3 + PROMPT_LEN * 8, "d2h_bytes_per_step": SIZE * SIZE * 3},
+                    "h2d_bytes_per_step": NI * (SIZE * SIZE * 3 + PROMPT_LEN * 8),
+                    "d2h_bytes_per_step": NI * SIZE * SIZE * 3},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
             "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line), flush=True)
@@ -611,6 +661,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline / parity leg (development runs)")
+    ap.add_argument("--images", type=int, default=int(os.environ.get("MB_BENCH_IMAGES", "2")),
+                    help="edit rounds generated TOGETHER per GPU (batched serving; images x 3 CFG rows <= 6); the "
+                         "single-request number (the reference's batch 1) is reported next to it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":  # CPU arm: rank 0 alone works, no process group needed

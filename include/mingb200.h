@@ -207,10 +207,11 @@ int mb_adaln_modulate(const void* x, int64_t ldx, const void* gamma, const void*
  * (28 % of the head) are streamed once per token instead of once per Euler step. */
 int mb_silu_add_rows(const void* temb, const void* c, void* out, int steps, int B, int dim, void* stream);
 /* CFG combine + explicit Euler update of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:145-179):
- * v bf16 [B, C] rows (cond, uncond[, text_uncond]); B == 3: v = v_u + image_cfg (v_tu - v_u) + text_cfg (v_c - v_tu);
- * B == 2: v = v_u + text_cfg (v_c - v_u); otherwise per-row.  x_f32[B, C] += bf16(v * dt) on every row; x_bf16
- * receives the bf16 copy that feeds input_proj on the next step. */
-int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, float dt, float text_cfg,
+ * v bf16 [B, C]: B / cfg_rows independent samples of cfg_rows adjacent rows (cond, uncond[, text_uncond]);
+ * cfg_rows == 3: v = v_u + image_cfg (v_tu - v_u) + text_cfg (v_c - v_tu); 2: v = v_u + text_cfg (v_c - v_u); 1: v.
+ * x_f32[B, C] += bf16(v * dt) on every row of the sample; x_bf16 receives the bf16 copy that feeds input_proj on the
+ * next step. */
+int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int cfg_rows, int C, float dt, float text_cfg,
                      float image_cfg, void* stream);
 /* The whole sampler loop of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:134-179: `steps` Euler steps x
  * [input_proj :371, `depth` x ResBlock :268-272, FinalLayer :288-292, CFG combine + Euler update]) as ONE persistent
@@ -221,14 +222,16 @@ int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, flo
  * [depth][6] = {w12 packed, b12 [2H], w3 packed, b3 [W], in_ln weight [W], in_ln bias [W]}; mod [steps * B, ld_mod] =
  * the adaLN modulations of all steps (depth x (shift | scale | gate) then final (shift | scale)); x [B, C] fp32 is the
  * noise on entry and the sample on exit; scratch h [B, W], hid [B, H], v [B, C] bf16 and one u32 barrier word.
- * Supported shapes: mb_rf_fused_supported(B, W, H, C) (B <= 3 CFG rows, W and H multiples of 1024, C <= 32). */
+ * B rows = B / cfg_rows independent samples (images generated together) of cfg_rows adjacent CFG rows each (cond, uncond
+ * [, text-uncond]): the weights stream ONCE for all of them.  Supported shapes: mb_rf_fused_supported(B, W, H, C)
+ * (B <= 6 rows, W and H multiples of 1024, W <= 4096, C <= 32). */
 int mb_rf_fused_supported(int B, int W, int H, int C);
 int mb_rf_set_debug(void* buf16_u64); /* debug aid: per-phase wall time of the first / last CTA, NULL = off */
 int mb_rf_pack_weights(const void* W, int N, int K, int swiglu, int n_cta, void* out, void* stream);
 int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_w, const void* in_b, const void* fin_w,
                        const void* fin_b, const void* mod, int64_t ld_mod, float* x, void* h_scratch, void* hid_scratch,
-                       void* v_scratch, uint32_t* barrier, int B, int W, int H, int C, int depth, int steps,
-                       float text_cfg, float image_cfg, int n_cta, void* stream);
+                       void* v_scratch, uint32_t* barrier, int B, int cfg_rows, int W, int H, int C, int depth,
+                       int steps, float text_cfg, float image_cfg, int n_cta, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Bailing-MoE AR step (mingunivision/modeling_bailing_moe.py).  `t_dev` arguments are optional DEVICE int32 scalars

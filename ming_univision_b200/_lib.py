@@ -33,12 +33,12 @@ SIGNATURES = {
                           _vp, _i64, _vp, _i64, _f, _vp],
     "mb_adaln_modulate": [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _f, _vp],
     "mb_silu_add_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
-    "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _f, _f, _f, _vp],
+    "mb_rf_euler_step": [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp],
     "mb_rf_fused_supported": [_i, _i, _i, _i],
     "mb_rf_set_debug": [_vp],
     "mb_rf_pack_weights": [_vp, _i, _i, _i, _i, _vp, _vp],
-    "mb_rf_sample_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _i,
-                           _vp],
+    "mb_rf_sample_fused": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f,
+                           _i, _vp],
     "mb_rmsnorm": [_vp, _i64, _vp, _vp, _i64, _i, _i, _f, _vp],
     "mb_rope_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _vp],
     "mb_rope3d_kv_append": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _f, _i, _i, _i, _vp],

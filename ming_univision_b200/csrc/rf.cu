@@ -69,40 +69,35 @@ __global__ void silu_add_rows_kernel(const __nv_bfloat16* __restrict__ temb, con
 }
 
 // CFG combine + explicit Euler step (RectifiedFlowLoss.sample, diff_loss_rf_swiglu.py:138-179).
-// v: bf16 [B, C] rows ordered (cond, uncond[, text_uncond]); x: fp32 [B, C], every row receives the same update.
+// v: bf16 [B, C]; the B rows are B / cfg_rows independent samples of cfg_rows adjacent rows ordered (cond, uncond
+// [, text_uncond]); x: fp32 [B, C], every row of a sample receives the same update.
 // Rounding points mirror the reference's bf16 tensor arithmetic with Python-float scalars.
 __global__ void rf_euler_kernel(float* __restrict__ x, __nv_bfloat16* __restrict__ x_bf16,
-                                const __nv_bfloat16* __restrict__ v, int B, int C, float dt, float text_cfg,
+                                const __nv_bfloat16* __restrict__ v, int B, int cfg_rows, int C, float dt, float text_cfg,
                                 float image_cfg) {
   pdl_launch_dependents();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  if (B == 3) {
-    const float vc = __bfloat162float(v[c]), vu = __bfloat162float(v[C + c]), vt = __bfloat162float(v[2 * C + c]);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (B / cfg_rows) * C) return;
+  const int c = i % C, r0 = (i / C) * cfg_rows;
+  const __nv_bfloat16* vs = v + static_cast<int64_t>(r0) * C;
+  float step;
+  if (cfg_rows == 3) {
+    const float vc = __bfloat162float(vs[c]), vu = __bfloat162float(vs[C + c]), vt = __bfloat162float(vs[2 * C + c]);
     const float t3 = bf16_round(vu + bf16_round(image_cfg * bf16_round(vt - vu)));
     const float vg = bf16_round(t3 + bf16_round(text_cfg * bf16_round(vc - vt)));
-    const float step = bf16_round(vg * dt);
-    for (int b = 0; b < 3; ++b) {
-      const float nx = x[b * C + c] + step;
-      x[b * C + c] = nx;
-      x_bf16[b * C + c] = __float2bfloat16_rn(nx);
-    }
-  } else if (B == 2) {
-    const float vc = __bfloat162float(v[c]), vu = __bfloat162float(v[C + c]);
+    step = bf16_round(vg * dt);
+  } else if (cfg_rows == 2) {
+    const float vc = __bfloat162float(vs[c]), vu = __bfloat162float(vs[C + c]);
     const float vg = bf16_round(vu + bf16_round(text_cfg * bf16_round(vc - vu)));
-    const float step = bf16_round(vg * dt);
-    for (int b = 0; b < 2; ++b) {
-      const float nx = x[b * C + c] + step;
-      x[b * C + c] = nx;
-      x_bf16[b * C + c] = __float2bfloat16_rn(nx);
-    }
+    step = bf16_round(vg * dt);
   } else {
-    for (int b = 0; b < B; ++b) {
-      const float nx = x[b * C + c] + bf16_round(__bfloat162float(v[b * C + c]) * dt);
-      x[b * C + c] = nx;
-      x_bf16[b * C + c] = __float2bfloat16_rn(nx);
-    }
+    step = bf16_round(__bfloat162float(vs[c]) * dt);
+  }
+  for (int b = 0; b < cfg_rows; ++b) {
+    const float nx = x[(r0 + b) * C + c] + step;
+    x[(r0 + b) * C + c] = nx;
+    x_bf16[(r0 + b) * C + c] = __float2bfloat16_rn(nx);
   }
 }
 
@@ -139,13 +134,15 @@ extern "C" int mb_silu_add_rows(const void* temb, const void* c, void* out, int 
   return MB_OK;
 }
 
-extern "C" int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int C, float dt, float text_cfg,
-                                float image_cfg, void* stream_) {
+extern "C" int mb_rf_euler_step(void* x_f32, void* x_bf16, const void* v, int B, int cfg_rows, int C, float dt,
+                                float text_cfg, float image_cfg, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_rf_euler_step: no sm_100 device");
-  MB_CHECK_ARG(B >= 1 && B <= 8 && C >= 1, MB_ERR_SHAPE, "mb_rf_euler_step: bad shape B=%d C=%d", B, C);
-  MB_CHECK_CUDA(launch_pdl(rf_euler_kernel, dim3((C + 63) / 64), dim3(64), 0, stream, static_cast<float*>(x_f32),
-                           static_cast<__nv_bfloat16*>(x_bf16), static_cast<const __nv_bfloat16*>(v), B, C, dt,
+  MB_CHECK_ARG(B >= 1 && B <= 8 && C >= 1 && cfg_rows >= 1 && cfg_rows <= 3 && B % cfg_rows == 0, MB_ERR_SHAPE,
+               "mb_rf_euler_step: bad shape B=%d cfg_rows=%d C=%d", B, cfg_rows, C);
+  const int n = (B / cfg_rows) * C;
+  MB_CHECK_CUDA(launch_pdl(rf_euler_kernel, dim3((n + 63) / 64), dim3(64), 0, stream, static_cast<float*>(x_f32),
+                           static_cast<__nv_bfloat16*>(x_bf16), static_cast<const __nv_bfloat16*>(v), B, cfg_rows, C, dt,
                            text_cfg, image_cfg));
   return MB_OK;
 }

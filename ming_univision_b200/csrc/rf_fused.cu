@@ -33,7 +33,8 @@ constexpr int kRfThreads = (kRfConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kRfKC = 1024;                               // K elements per pipeline stage
 constexpr int kRfStageBytes = 16 * kRfKC * 2;             // a full 16-row tile chunk: 32 KB
 constexpr int kRfStages = 5;
-constexpr int kRfMaxRows = 3;                             // CFG rows
+constexpr int kRfRowGroup = 3;                            // rows handled per register round of the row-wise parts
+constexpr int kRfMaxRows = 6;                             // rows per launch: CFG rows x images generated together
 
 struct RfFusedParams {
   const void* const* blocks;  // device table [depth][6]: w12 packed, b12, w3 packed, b3, ln weight, ln bias
@@ -43,7 +44,10 @@ struct RfFusedParams {
   float* x;                                                 // [B, C] fp32, in / out
   __nv_bfloat16* h; __nv_bfloat16* hid; __nv_bfloat16* v;  // global scratch [B, W], [B, H], [B, C]
   uint32_t* bar;                                            // grid barrier counter (zeroed before the launch)
-  int B, W, H, C, depth, steps;
+  int B;         // rows of this launch = cfg_rows x independent samples (images); rows of one sample are adjacent
+  int cfg_rows;  // rows per sample: 1 (no guidance), 2 (cond, uncond) or 3 (+ text-uncond)
+  int nstages;   // ring slots in use (what fits next to the B activation rows)
+  int W, H, C, depth, steps;
   float dt, text_cfg, image_cfg;
   unsigned long long* dbg;  // optional [2 CTAs][8] accumulated phase times in ns (mb_rf_set_debug), or null
 };
@@ -100,8 +104,8 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
   // layout: ring [kRfStages][32 KB] | act [B][act_pitch] | red [2][8][4][32] f32 | small
   uint8_t* ring = smem;
   const int act_pitch = p.H * 2 + 64;  // bytes per activation row (H >= W); + 64: consecutive rows in other bank halves
-  uint8_t* act = ring + kRfStages * kRfStageBytes;
-  float* red = reinterpret_cast<float*>(act + kRfMaxRows * act_pitch);
+  uint8_t* act = ring + p.nstages * kRfStageBytes;
+  float* red = reinterpret_cast<float*>(act + p.B * act_pitch);
   float* small = red + 2 * kRfConsumerWarps * 4 * 32;       // [64]: block-reduction scratch
   float* xs = small + 64;                                    // [B][C] fp32 Euler state (replicated in every CTA)
   __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(xs + kRfMaxRows * 32);  // [B][C] bf16 copy
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
                 mbar_arrive_expect_tx(&full_bar[slot], bytes);
                 bulk_load(ring + slot * kRfStageBytes, src, bytes, &full_bar[slot]);
                 src += bytes;
-                if (++slot == kRfStages) {
+                if (++slot == p.nstages) {
                   slot = 0;
                   ++round;
                 }
@@ -179,20 +183,20 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
     }
   };
   stamp(-1);
-  auto block_sum3 = [&](float (&v)[kRfMaxRows]) {  // sums over the 256 consumer threads (fixed order), all rows at once
+  auto block_sum3 = [&](float (&v)[kRfRowGroup]) {  // sums over the 256 consumer threads (fixed order), a row group at once
 #pragma unroll
-    for (int b = 0; b < kRfMaxRows; ++b) {
+    for (int b = 0; b < kRfRowGroup; ++b) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v[b] += __shfl_xor_sync(0xffffffffu, v[b], o);
     }
     consumer_sync();
     if (lane == 0) {
 #pragma unroll
-      for (int b = 0; b < kRfMaxRows; ++b) small[b * kRfConsumerWarps + warp] = v[b];
+      for (int b = 0; b < kRfRowGroup; ++b) small[b * kRfConsumerWarps + warp] = v[b];
     }
     consumer_sync();
 #pragma unroll
-    for (int b = 0; b < kRfMaxRows; ++b) {
+    for (int b = 0; b < kRfRowGroup; ++b) {
       float s = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < kRfConsumerWarps; ++w2) s += small[b * kRfConsumerWarps + w2];
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[cslot]);
-        if (++cslot == kRfStages) {
+        if (++cslot == p.nstages) {
           cslot = 0;
           cpar ^= 1;
         }
@@ -269,28 +273,35 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
   // They do not depend on the activations, so they are requested BEFORE the grid barrier that precedes the prologue: their
   // latency (queued behind the bulk weight stream) overlaps the barrier instead of sitting on the critical path after it.
   constexpr int kCh = 2;
-  uint4 pre_gm[kCh], pre_bt[kCh], pre_sh[kRfMaxRows][kCh], pre_sc[kRfMaxRows][kCh];
+  uint4 pre_gm[kCh], pre_bt[kCh], pre_sh[kRfRowGroup][kCh], pre_sc[kRfRowGroup][kCh];
+  auto load_mod = [&](int step, int blk, int row0) {  // shift / scale of rows row0 .. row0 + 2 of (step, blk)
+    const __nv_bfloat16* mb = p.mod + static_cast<int64_t>(step) * B * p.ld_mod + static_cast<int64_t>(blk) * 3 * W;
+#pragma unroll
+    for (int cc = 0; cc < kCh; ++cc) {
+      const int i = tid + cc * kRfConsumerWarps * 32;
+#pragma unroll
+      for (int b = 0; b < kRfRowGroup; ++b) {
+        const bool okb = i < W / 8 && row0 + b < B;
+        const __nv_bfloat16* sh = mb + static_cast<int64_t>(row0 + b) * p.ld_mod;
+        pre_sh[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + i * 8) : make_uint4(0, 0, 0, 0);
+        pre_sc[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + W + i * 8) : make_uint4(0, 0, 0, 0);
+      }
+    }
+  };
   auto preload = [&](int step, int blk) {
     const bool fin = blk == p.depth;
     if (fin && c >= C) return;
     const void* const* bp = p.blocks + (fin ? 0 : blk) * 6;
     const __nv_bfloat16* lnw = fin ? nullptr : static_cast<const __nv_bfloat16*>(bp[4]);
     const __nv_bfloat16* lnb = fin ? nullptr : static_cast<const __nv_bfloat16*>(bp[5]);
-    const __nv_bfloat16* mb = p.mod + static_cast<int64_t>(step) * B * p.ld_mod + static_cast<int64_t>(blk) * 3 * W;
 #pragma unroll
     for (int cc = 0; cc < kCh; ++cc) {
       const int i = tid + cc * kRfConsumerWarps * 32;
       const bool ok = i < W / 8;
       pre_gm[cc] = (ok && lnw) ? *reinterpret_cast<const uint4*>(lnw + i * 8) : make_uint4(0, 0, 0, 0);
       pre_bt[cc] = (ok && lnb) ? *reinterpret_cast<const uint4*>(lnb + i * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int b = 0; b < kRfMaxRows; ++b) {
-        const bool okb = ok && b < B;
-        const __nv_bfloat16* sh = mb + static_cast<int64_t>(b) * p.ld_mod;
-        pre_sh[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + i * 8) : make_uint4(0, 0, 0, 0);
-        pre_sc[b][cc] = okb ? *reinterpret_cast<const uint4*>(sh + W + i * 8) : make_uint4(0, 0, 0, 0);
-      }
     }
+    load_mod(step, blk, 0);
   };
 
   for (int step = 0; step < p.steps; ++step) {
@@ -317,72 +328,77 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
       // ---- adaLN prologue (ResBlock :270 / FinalLayer :290): every CTA normalises the full rows of h into shared memory
       // (the final layer needs them only in the CTAs that compute an output channel)
       if (!final_layer || c < C) {
-        // each thread keeps its 16-byte chunks of all rows in registers (W / 8 <= 2 * 256 chunks per row)
-        uint4 raw[kRfMaxRows][kCh];
-        float sum[kRfMaxRows], sq[kRfMaxRows];
+        // rows in groups of 3: each thread keeps its 16-byte chunks of the group's rows in registers (W / 8 <= 2 * 256
+        // chunks per row); the first group's shift / scale were requested before the grid barrier, later groups' here
         auto unpack8 = [](const uint4& q, float (&f)[8]) {
           const float2 f0 = unpack_bf16x2(q.x), f1 = unpack_bf16x2(q.y), f2 = unpack_bf16x2(q.z), f3 = unpack_bf16x2(q.w);
           f[0] = f0.x; f[1] = f0.y; f[2] = f1.x; f[3] = f1.y; f[4] = f2.x; f[5] = f2.y; f[6] = f3.x; f[7] = f3.y;
         };
+        for (int row0 = 0; row0 < B; row0 += kRfRowGroup) {
+          if (row0 > 0) load_mod(step, blk, row0);
+          uint4 raw[kRfRowGroup][kCh];
+          float sum[kRfRowGroup], sq[kRfRowGroup];
 #pragma unroll
-        for (int b = 0; b < kRfMaxRows; ++b) {
-          sum[b] = 0.f;
+          for (int b = 0; b < kRfRowGroup; ++b) {
+            sum[b] = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < kCh; ++cc) {
-            const int i = tid + cc * kRfConsumerWarps * 32;
-            raw[b][cc] = (b < B && i < W / 8) ? __ldcg(reinterpret_cast<const uint4*>(p.h + static_cast<int64_t>(b) * W) + i)
-                                              : make_uint4(0, 0, 0, 0);
-            float f[8];
-            unpack8(raw[b][cc], f);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sum[b] += f[e];
-          }
-        }
-        block_sum3(sum);
-#pragma unroll
-        for (int b = 0; b < kRfMaxRows; ++b) {
-          sum[b] /= W;  // mean
-          sq[b] = 0.f;
-#pragma unroll
-          for (int cc = 0; cc < kCh; ++cc) {
-            if (tid + cc * kRfConsumerWarps * 32 < W / 8) {
+            for (int cc = 0; cc < kCh; ++cc) {
+              const int i = tid + cc * kRfConsumerWarps * 32;
+              raw[b][cc] = (row0 + b < B && i < W / 8)
+                               ? __ldcg(reinterpret_cast<const uint4*>(p.h + static_cast<int64_t>(row0 + b) * W) + i)
+                               : make_uint4(0, 0, 0, 0);
               float f[8];
               unpack8(raw[b][cc], f);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float d = f[e] - sum[b];
-                sq[b] += d * d;
+              for (int e = 0; e < 8; ++e) sum[b] += f[e];
+            }
+          }
+          block_sum3(sum);
+#pragma unroll
+          for (int b = 0; b < kRfRowGroup; ++b) {
+            sum[b] /= W;  // mean
+            sq[b] = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < kCh; ++cc) {
+              if (tid + cc * kRfConsumerWarps * 32 < W / 8) {
+                float f[8];
+                unpack8(raw[b][cc], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float d = f[e] - sum[b];
+                  sq[b] += d * d;
+                }
               }
             }
           }
-        }
-        block_sum3(sq);
+          block_sum3(sq);
 #pragma unroll
-        for (int cc = 0; cc < kCh; ++cc) {
-          const int i = tid + cc * kRfConsumerWarps * 32;
-          if (i >= W / 8) continue;
-          __nv_bfloat16 gm[8], bt[8];
-          *reinterpret_cast<uint4*>(gm) = pre_gm[cc];
-          *reinterpret_cast<uint4*>(bt) = pre_bt[cc];
+          for (int cc = 0; cc < kCh; ++cc) {
+            const int i = tid + cc * kRfConsumerWarps * 32;
+            if (i >= W / 8) continue;
+            __nv_bfloat16 gm[8], bt[8];
+            *reinterpret_cast<uint4*>(gm) = pre_gm[cc];
+            *reinterpret_cast<uint4*>(bt) = pre_bt[cc];
 #pragma unroll
-          for (int b = 0; b < kRfMaxRows; ++b) {
-            if (b >= B) continue;
-            const float mean = sum[b], rstd = rsqrtf(sq[b] / W + 1e-6f);
-            __nv_bfloat16 shv[8], scv[8];
-            *reinterpret_cast<uint4*>(shv) = pre_sh[b][cc];
-            *reinterpret_cast<uint4*>(scv) = pre_sc[b][cc];
-            float f[8], o[8];
-            unpack8(raw[b][cc], f);
+            for (int b = 0; b < kRfRowGroup; ++b) {
+              if (row0 + b >= B) continue;
+              const float mean = sum[b], rstd = rsqrtf(sq[b] / W + 1e-6f);
+              __nv_bfloat16 shv[8], scv[8];
+              *reinterpret_cast<uint4*>(shv) = pre_sh[b][cc];
+              *reinterpret_cast<uint4*>(scv) = pre_sc[b][cc];
+              float f[8], o[8];
+              unpack8(raw[b][cc], f);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float xv = (f[e] - mean) * rstd;
-              if (lnw) xv = xv * __bfloat162float(gm[e]) + (lnb ? __bfloat162float(bt[e]) : 0.f);
-              o[e] = xv * bf16_round(1.f + __bfloat162float(scv[e])) + __bfloat162float(shv[e]);
+              for (int e = 0; e < 8; ++e) {
+                float xv = (f[e] - mean) * rstd;
+                if (lnw) xv = xv * __bfloat162float(gm[e]) + (lnb ? __bfloat162float(bt[e]) : 0.f);
+                o[e] = xv * bf16_round(1.f + __bfloat162float(scv[e])) + __bfloat162float(shv[e]);
+              }
+              uint4 o4;
+              o4.x = pack_bf16x2(o[0], o[1]); o4.y = pack_bf16x2(o[2], o[3]);
+              o4.z = pack_bf16x2(o[4], o[5]); o4.w = pack_bf16x2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(act + (row0 + b) * act_pitch + i * 16) = o4;
             }
-            uint4 o4;
-            o4.x = pack_bf16x2(o[0], o[1]); o4.y = pack_bf16x2(o[2], o[3]);
-            o4.z = pack_bf16x2(o[4], o[5]); o4.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(act + b * act_pitch + i * 16) = o4;
           }
         }
       }
@@ -391,49 +407,52 @@ __global__ void __launch_bounds__(kRfThreads, 1) rf_sample_fused_kernel(const Rf
       if (final_layer) {
         // ---- FinalLayer linear (:291): v[b][ch] = bf16(a[b] . fin_w[ch] + fin_b[ch]); CTA ch < C computes channel ch
         if (c < C) {
-          float dot[kRfMaxRows] = {0.f, 0.f, 0.f};
-          for (int i = tid; i < W / 8; i += kRfConsumerWarps * 32) {
-            __nv_bfloat16 w8[8];
-            *reinterpret_cast<uint4*>(w8) = *reinterpret_cast<const uint4*>(p.fin_w + static_cast<int64_t>(c) * W + i * 8);
+          for (int row0 = 0; row0 < B; row0 += kRfRowGroup) {
+            float dot[kRfRowGroup] = {0.f, 0.f, 0.f};
+            for (int i = tid; i < W / 8; i += kRfConsumerWarps * 32) {
+              __nv_bfloat16 w8[8];
+              *reinterpret_cast<uint4*>(w8) = *reinterpret_cast<const uint4*>(p.fin_w + static_cast<int64_t>(c) * W + i * 8);
 #pragma unroll
-            for (int b = 0; b < kRfMaxRows; ++b) {
-              if (b >= B) continue;
-              __nv_bfloat16 a8[8];
-              *reinterpret_cast<uint4*>(a8) = *reinterpret_cast<const uint4*>(act + b * act_pitch + i * 16);
+              for (int b = 0; b < kRfRowGroup; ++b) {
+                if (row0 + b >= B) continue;
+                __nv_bfloat16 a8[8];
+                *reinterpret_cast<uint4*>(a8) = *reinterpret_cast<const uint4*>(act + (row0 + b) * act_pitch + i * 16);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) dot[b] += __bfloat162float(a8[e]) * __bfloat162float(w8[e]);
+                for (int e = 0; e < 8; ++e) dot[b] += __bfloat162float(a8[e]) * __bfloat162float(w8[e]);
+              }
             }
+            block_sum3(dot);
+            if (tid < kRfRowGroup && row0 + tid < B)
+              p.v[(row0 + tid) * C + c] = __float2bfloat16_rn(dot[tid] + __bfloat162float(p.fin_b[c]));
           }
-          block_sum3(dot);
-          if (tid < B) p.v[tid * C + c] = __float2bfloat16_rn(dot[tid] + __bfloat162float(p.fin_b[c]));
         }
         stamp(5);
         grid_barrier(p.bar, ++nbar * G);
         stamp(6);
         // ---- CFG combine + Euler (:145-179), replicated in every CTA on its shared-memory copy of x
-        for (int ch = tid; ch < C; ch += kRfConsumerWarps * 32) {
-          float stepv[kRfMaxRows];
+        for (int i = tid; i < (B / p.cfg_rows) * C; i += kRfConsumerWarps * 32) {
+          const int ch = i % C, r0 = (i / C) * p.cfg_rows;  // sample i / C owns rows r0 .. r0 + cfg_rows - 1
           auto vld = [&](int b) {  // written by other CTAs before the grid barrier: read through L2
-            return __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.v) + b * C + ch)));
+            return __bfloat162float(
+                __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p.v) + (r0 + b) * C + ch)));
           };
-          if (B == 3) {
+          float stepv;  // every row of a sample receives the same update
+          if (p.cfg_rows == 3) {
             const float vc = vld(0), vu = vld(1), vt = vld(2);
             const float t3 = bf16_round(vu + bf16_round(p.image_cfg * bf16_round(vt - vu)));
             const float vg = bf16_round(t3 + bf16_round(p.text_cfg * bf16_round(vc - vt)));
-            stepv[0] = stepv[1] = stepv[2] = bf16_round(vg * p.dt);
-          } else if (B == 2) {
+            stepv = bf16_round(vg * p.dt);
+          } else if (p.cfg_rows == 2) {
             const float vc = vld(0), vu = vld(1);
             const float vg = bf16_round(vu + bf16_round(p.text_cfg * bf16_round(vc - vu)));
-            stepv[0] = stepv[1] = bf16_round(vg * p.dt);
-            stepv[2] = 0.f;
+            stepv = bf16_round(vg * p.dt);
           } else {
-            stepv[0] = bf16_round(vld(0) * p.dt);
-            stepv[1] = stepv[2] = 0.f;
+            stepv = bf16_round(vld(0) * p.dt);
           }
-          for (int b = 0; b < B; ++b) {
-            const float nx = xs[b * C + ch] + stepv[b];
-            xs[b * C + ch] = nx;
-            xb[b * C + ch] = __float2bfloat16_rn(nx);
+          for (int b = 0; b < p.cfg_rows; ++b) {
+            const float nx = xs[(r0 + b) * C + ch] + stepv;
+            xs[(r0 + b) * C + ch] = nx;
+            xb[(r0 + b) * C + ch] = __float2bfloat16_rn(nx);
           }
         }
         consumer_sync();
@@ -566,21 +585,30 @@ extern "C" int mb_rf_set_debug(void* buf) {
   return MB_OK;
 }
 
+static int rf_stages_for(int B, int H) {  // ring slots that fit next to B activation rows (<= kRfStages)
+  const long avail = 226L * 1024 - 10 * 1024 - static_cast<long>(B) * (H * 2 + 64);
+  const long n = avail / kRfStageBytes;
+  return n > kRfStages ? kRfStages : static_cast<int>(n);
+}
+
 extern "C" int mb_rf_fused_supported(int B, int W, int H, int C) {
-  return (B >= 1 && B <= kRfMaxRows && W % kRfKC == 0 && H % kRfKC == 0 && H >= W && C >= 1 && C <= 32 &&
-          kRfStages * kRfStageBytes + kRfMaxRows * (H * 2 + 64) + 10 * 1024 <= 226 * 1024)
+  return (B >= 1 && B <= kRfMaxRows && W % kRfKC == 0 && H % kRfKC == 0 && H >= W && W / 8 <= 2 * kRfConsumerWarps * 32 &&
+          C >= 1 && C <= 32 && rf_stages_for(B, H) >= 2)
              ? 1
              : 0;
 }
 
 extern "C" int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_w, const void* in_b, const void* fin_w,
                                   const void* fin_b, const void* mod, int64_t ld_mod, float* x, void* h_scratch,
-                                  void* hid_scratch, void* v_scratch, uint32_t* barrier, int B, int W, int H, int C,
-                                  int depth, int steps, float text_cfg, float image_cfg, int n_cta, void* stream_) {
+                                  void* hid_scratch, void* v_scratch, uint32_t* barrier, int B, int cfg_rows, int W,
+                                  int H, int C, int depth, int steps, float text_cfg, float image_cfg, int n_cta,
+                                  void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_rf_sample_fused: no sm_100 device");
   MB_CHECK_ARG(mb_rf_fused_supported(B, W, H, C) && depth >= 1 && steps >= 1, MB_ERR_SHAPE,
                "mb_rf_sample_fused: unsupported shape (B=%d W=%d H=%d C=%d)", B, W, H, C);
+  MB_CHECK_ARG(cfg_rows >= 1 && cfg_rows <= 3 && B % cfg_rows == 0, MB_ERR_SHAPE,
+               "mb_rf_sample_fused: %d rows are not whole samples of %d CFG rows", B, cfg_rows);
   MB_CHECK_ARG(n_cta == num_sms(), MB_ERR_SHAPE, "mb_rf_sample_fused: weights packed for %d CTAs, device has %d SMs",
                n_cta, num_sms());
   MB_CHECK_ARG(ld_mod % 8 == 0 && (reinterpret_cast<uintptr_t>(mod) & 15) == 0, MB_ERR_ALIGN,
@@ -594,10 +622,11 @@ extern "C" int mb_rf_sample_fused(const void* const* block_ptrs, const void* in_
   p.h = static_cast<__nv_bfloat16*>(h_scratch); p.hid = static_cast<__nv_bfloat16*>(hid_scratch);
   p.v = static_cast<__nv_bfloat16*>(v_scratch);
   p.bar = barrier;
-  p.B = B; p.W = W; p.H = H; p.C = C; p.depth = depth; p.steps = steps;
+  p.B = B; p.cfg_rows = cfg_rows; p.nstages = rf_stages_for(B, H);
+  p.W = W; p.H = H; p.C = C; p.depth = depth; p.steps = steps;
   p.dt = 1.0f / steps; p.text_cfg = text_cfg; p.image_cfg = image_cfg;
   p.dbg = g_rf_dbg;
-  const size_t smem = static_cast<size_t>(kRfStages) * kRfStageBytes + static_cast<size_t>(kRfMaxRows) * (H * 2 + 64) +
+  const size_t smem = static_cast<size_t>(p.nstages) * kRfStageBytes + static_cast<size_t>(B) * (H * 2 + 64) +
                       2 * kRfConsumerWarps * 4 * 32 * 4 + 64 * 4 + kRfMaxRows * 32 * 4 + kRfMaxRows * 32 * 2 + 64;
   MB_CHECK_ARG(smem <= 226 * 1024, MB_ERR_SHAPE, "mb_rf_sample_fused: %zu bytes of shared memory", smem);
   static size_t attr_smem = 0;  // (the kernel also has ~1 KB of static shared memory: 227 KB is the sum's limit)

@@ -95,6 +95,11 @@ def _use_fused(pk, n_rows: int) -> bool:
     return bool(_lib.load().mb_rf_fused_supported(n_rows, pk.W, H, pk.C))
 
 
+# bench.py: when set to a list, every launch of the persistent sampler kernel is bracketed by CUDA events on the launching
+# stream and (algorithmic weight bytes, start, end) is appended (eager path only; events cannot be captured into a graph)
+FUSED_PROFILE: list | None = None
+
+
 def _fuse_adaln(n_rows: int) -> bool:
     return _FUSED_ENV == "1" if _FUSED_ENV in ("0", "1") else n_rows <= 2
 
@@ -157,8 +162,8 @@ class _PackedRF:
                 table.append([w12p.data_ptr(), b12.data_ptr(), w3p.data_ptr(), b3.data_ptr(), lnw.data_ptr(),
                               lnb.data_ptr()])
             self._fused = dict(n_cta=n_cta, H=H, keep=keep, table=torch.tensor(table, dtype=torch.int64, device=dev),
-                               h=torch.zeros((3, W), dtype=BF16, device=dev), hid=torch.zeros((3, H), dtype=BF16, device=dev),
-                               v=torch.zeros((3, self.C), dtype=BF16, device=dev),
+                               h=torch.zeros((8, W), dtype=BF16, device=dev), hid=torch.zeros((8, H), dtype=BF16, device=dev),
+                               v=torch.zeros((8, self.C), dtype=BF16, device=dev),
                                bar=torch.zeros((16,), dtype=torch.int32, device=dev))
         return self._fused
 
@@ -204,8 +209,11 @@ class RectifiedFlowLoss(nn.Module):
 
     # -- the sampler body (graph-capturable: fixed shapes, no host sync) ---------------------------------------
     def _sample_body(self, pk: _PackedRF, z_bf16: torch.Tensor, x_f32: torch.Tensor, text_cfg: float,
-                     image_cfg: float) -> None:
+                     image_cfg: float, cfg_rows: int | None = None) -> None:
+        """z_bf16 [B, Z], x_f32 [B, C] (noise in, sample out).  The B rows are B / cfg_rows independent samples (images
+        generated together) of `cfg_rows` adjacent CFG rows each — the weights stream once for all of them."""
         B, W, depth = z_bf16.shape[0], pk.W, len(pk.blocks)
+        cfg_rows = B if cfg_rows is None else cfg_rows
         fuse = _fuse_adaln(B)
         c = ops.gemv(z_bf16, pk.cond_w, pk.cond_b)                       # cond_embed(z), once per token (:374)
         sy = ops.silu_add_rows(pk.temb, c)                               # SiLU(t_emb[s] + c) for every step
@@ -214,12 +222,19 @@ class RectifiedFlowLoss(nn.Module):
             # the 16-step Euler loop as ONE persistent weight-streaming kernel (csrc/rf_fused.cu)
             f = pk.fused()
             lib = _lib.load()
+            prof = FUSED_PROFILE
+            if prof is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             _lib.check(lib.mb_rf_sample_fused(f["table"].data_ptr(), pk.in_w.data_ptr(), pk.in_b.data_ptr(),
                                               pk.fin_w.data_ptr(), pk.fin_b.data_ptr(), mod.data_ptr(), mod.stride(0),
                                               x_f32.data_ptr(), f["h"].data_ptr(), f["hid"].data_ptr(), f["v"].data_ptr(),
-                                              f["bar"].data_ptr(), B, W, f["H"], pk.C, depth, pk.steps, float(text_cfg),
-                                              float(image_cfg), f["n_cta"], torch.cuda.current_stream().cuda_stream),
-                       "mb_rf_sample_fused")
+                                              f["bar"].data_ptr(), B, cfg_rows, W, f["H"], pk.C, depth, pk.steps,
+                                              float(text_cfg), float(image_cfg), f["n_cta"],
+                                              torch.cuda.current_stream().cuda_stream), "mb_rf_sample_fused")
+            if prof is not None:
+                ev1.record()
+                prof.append((pk.steps * depth * 3 * f["H"] * W * 2, ev0, ev1))
             return
         x_bf16 = ops.affine(x_f32, 1.0, 0.0)
         dt = 1.0 / pk.steps
@@ -241,27 +256,35 @@ class RectifiedFlowLoss(nn.Module):
             else:
                 a = ops.adaln_modulate(h, None, None, ms[:, o:o + W], ms[:, o + W:o + 2 * W])
                 v = ops.gemv(a, pk.fin_w, pk.fin_b)
-            ops.rf_euler_step(x_f32, x_bf16, v, dt, text_cfg, image_cfg)  # CFG combine + Euler (:145-179)
+            ops.rf_euler_step(x_f32, x_bf16, v, dt, text_cfg, image_cfg, cfg_rows)  # CFG combine + Euler (:145-179)
 
     @torch.no_grad()
     def sample(self, z, temperature=1.0, text_cfg=1.0, image_cfg=1.0, cfg_renorm_type=None,
-               time_shifting_factor=None, noise=None):
+               time_shifting_factor=None, noise=None, groups: int = 1):
         """diff_loss_rf_swiglu.py:103-181.  z: [B, z_channels] (fp32 or bf16, CUDA).  Returns x: [B, C] fp32.
-        `noise` (optional, test hook) replaces the torch.randn draw: [1, C] if text_cfg != 1 else [B, C]."""
+        `noise` (optional, test hook) replaces the torch.randn draw: [groups, C] if text_cfg != 1 else [B, C].
+        `groups` > 1 (extension; the reference samples one image at a time): the B rows are `groups` independent samples of
+        B / groups adjacent CFG rows — several images share every pass over the weights."""
         if cfg_renorm_type is not None or time_shifting_factor:
             raise NotImplementedError("cfg_renorm_type / time_shifting_factor are always None on the reference path "
                                       "(modeling_bailing_moe.py:1859-1860)")
         pk = self._pack()
         B = z.shape[0]
+        if groups < 1 or B % groups != 0 or B > 8:
+            raise ValueError(f"{B} rows are not {groups} whole samples (<= 8 rows per call)")
+        rows = B // groups
         device = z.device
         # RNG stays on the host side exactly as in the reference (:117-122) so the Philox stream matches
         if noise is None:
-            noise = torch.randn(1 if text_cfg != 1.0 else B, self.in_channels, device=device)
-        x0 = (torch.cat([noise] * B, dim=0) if text_cfg != 1.0 else noise) * temperature
-        key = (B, float(text_cfg), float(image_cfg), _packs.epoch())
+            noise = torch.randn(groups if text_cfg != 1.0 else B, self.in_channels, device=device)
+        x0 = (noise.repeat_interleave(rows, dim=0) if text_cfg != 1.0 else noise) * temperature
+        # the reference selects the CFG combine by the ROW COUNT of the sample (b_num == 3 / == 2, :146-171), any other
+        # count integrates every row on its own (:172-173)
+        cfg_rows = rows if rows in (2, 3) else 1
+        key = (B, cfg_rows, float(text_cfg), float(image_cfg), _packs.epoch())
         if not self.use_cuda_graph:
             x = x0.float().contiguous().clone()
-            self._sample_body(pk, ops.affine(z.reshape(B, -1), 1.0, 0.0), x, text_cfg, image_cfg)
+            self._sample_body(pk, ops.affine(z.reshape(B, -1), 1.0, 0.0), x, text_cfg, image_cfg, cfg_rows)
             return x
         if key not in self._graphs:
             z_buf = torch.zeros((B, z.shape[-1]), dtype=BF16, device=device)
@@ -269,12 +292,12 @@ class RectifiedFlowLoss(nn.Module):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):  # warm-up outside capture (sets kernel attributes, fills the allocator)
-                self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg)
+                self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg, cfg_rows)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
             with torch.cuda.graph(g):
-                self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg)
+                self._sample_body(pk, z_buf, x_buf, text_cfg, image_cfg, cfg_rows)
             self._graphs[key] = (g, z_buf, x_buf, _lib.launch_count() - l0)
         g, z_buf, x_buf, n_kernels = self._graphs[key]
         z_buf.copy_(z.reshape(B, -1))

@@ -394,6 +394,29 @@ class BailingKVCache:
     def trim_rows(self) -> None:
         self.batch = 1
 
+    def expand_groups(self, G: int, B: int) -> None:
+        """Rows 0 .. G-1 (the cond prefills of G samples generated together) -> rows g*B + b, b < B: every sample's CFG
+        rows start as copies of its cond row (the batched form of repeat_rows)."""
+        if G * B > self.max_batch:
+            raise ValueError("KV cache allocated for fewer rows")
+        if B > 1:
+            for k, v in zip(self.k, self.v):
+                for g in range(G - 1, -1, -1):  # downwards: a destination row never holds a source that is still needed
+                    for b in range(B - 1, -1, -1):
+                        if g * B + b != g:
+                            k[g * B + b, :, :self.seq_len].copy_(k[g, :, :self.seq_len])
+                            v[g * B + b, :, :self.seq_len].copy_(v[g, :, :self.seq_len])
+        self.batch = G * B
+
+    def trim_groups(self, G: int, B: int) -> None:
+        """Back to one (cond) row per sample: row g*B -> row g (the batched form of trim_rows)."""
+        if B > 1:
+            for k, v in zip(self.k, self.v):
+                for g in range(1, G):
+                    k[g, :, :self.seq_len].copy_(k[g * B, :, :self.seq_len])
+                    v[g, :, :self.seq_len].copy_(v[g * B, :, :self.seq_len])
+        self.batch = G
+
     def grow(self, min_len: int) -> None:
         """Re-allocates the cache for at least `min_len` tokens (doubling), keeping what it holds — the stand-in for the
         reference's DynamicCache growing with every torch.cat (later editing rounds outgrow any fixed size).  Graph
@@ -637,13 +660,13 @@ class BailingMoeForCausalLM(nn.Module):
     @torch.no_grad()
     def forward_for_image_generation_inner(self, inputs_embeds, attention_mask, position_ids, past_key_values,
                                            image_gen_temperature=1.0, image_gen_text_cfg=3.0, image_gen_image_cfg=1.1,
-                                           noise=None, **kwargs):
+                                           noise=None, groups: int = 1, **kwargs):
         """:1622-1673: one LLM step on the given embeddings, z = vis_head(last hidden), latent = diffloss.sample(z).
         attention_mask: int32 [B, >= cache_len + S] key mask (see BailingMoeModel.forward_tokens)."""
         hidden = self.model.forward_tokens(inputs_embeds, position_ids, past_key_values, key_mask=attention_mask)
         z = self.compute_vis_z(hidden[:, -1])
         x = self.diffloss.sample(z, temperature=image_gen_temperature, text_cfg=image_gen_text_cfg,
-                                 image_cfg=image_gen_image_cfg, noise=noise)
+                                 image_cfg=image_gen_image_cfg, noise=noise, groups=groups)
         return x.unsqueeze(1), hidden
 
     @torch.no_grad()
@@ -654,37 +677,49 @@ class BailingMoeForCausalLM(nn.Module):
         prefill is replicated to the rows and trimmed back to row 0 afterwards.  As in the reference, the CFG scales
         handed to the sampler are the hard-wired defaults 3.0 / 1.1: `generate_image` passes them under the wrong
         keyword names so they never reach `diffloss.sample` — only the temperature propagates.
-        `noises` (test hook): sequence of [1, C] tensors replacing the per-token torch.randn draw."""
+        `noises` (test hook): sequence of [G, C] tensors replacing the per-token torch.randn draw.
+
+        Extension (the reference asserts one sequence, :1865): G > 1 independent requests generated
+        TOGETHER — input_embeds [G, 1, D], masks [G, n], the cache holding the G cond prefills in rows 0 .. G-1.  Sample g
+        owns rows g*B .. g*B + B-1; every weight-streaming kernel of the step (LLM, RF head, semantic decoder) then serves
+        G*B <= 8 rows per pass over the weights.  Returns images [G, 3, H, W] (G = 1: [B, ...] as the reference)."""
         cfg = self.config
         dev = input_embeds.device
-        assert attention_mask.shape[0] == 1
+        G = attention_mask.shape[0]
         attention_mask = attention_mask.to(torch.int32)
+        rows = [attention_mask]
         if uncond_attention_mask is not None:
             uncond_attention_mask = uncond_attention_mask.to(torch.int32)
             n_c, n_u = attention_mask.shape[1], uncond_attention_mask.shape[1]
             if n_u < n_c:
                 uncond_attention_mask = torch.cat((uncond_attention_mask, attention_mask[:, n_u:]), dim=1)
-            attention_mask = torch.cat((attention_mask, uncond_attention_mask), dim=0)
+            rows.append(uncond_attention_mask)
         if text_uncond_attention_mask is not None and int(text_uncond_attention_mask.sum()) > 0:
             text_uncond_attention_mask = text_uncond_attention_mask.to(torch.int32)
             n_c, n_u = attention_mask.shape[1], text_uncond_attention_mask.shape[1]
             if n_u < n_c:
-                text_uncond_attention_mask = torch.cat((text_uncond_attention_mask, attention_mask[0:1, n_u:]), dim=1)
+                text_uncond_attention_mask = torch.cat((text_uncond_attention_mask, attention_mask[:, n_u:]), dim=1)
             if int((text_uncond_attention_mask == uncond_attention_mask).sum()) != uncond_attention_mask.numel():
-                attention_mask = torch.cat((attention_mask, text_uncond_attention_mask), dim=0)
-        B = attention_mask.shape[0]
+                rows.append(text_uncond_attention_mask)
+        B = len(rows)
+        attention_mask = torch.stack(rows, dim=1).reshape(G * B, -1)  # row g*B + b = mask b of sample g
+        R = G * B
+        if R > 8:
+            raise ValueError(f"{G} requests x {B} CFG rows: at most 8 rows per generation step")
         n_tok = cfg.num_image_tokens_for_gen
         cache = past_key_values
+        if cache.batch != G:
+            raise ValueError(f"the KV cache holds {cache.batch} prefilled rows, the masks describe {G} requests")
         if B > 1:
-            input_embeds = input_embeds.repeat((B, 1, 1))
-            cache.repeat_rows(B)
+            input_embeds = input_embeds.repeat_interleave(B, dim=0)
+            cache.expand_groups(G, B)
         if self.use_cuda_graph and getattr(self.model, "ep_graphable", True) and \
                 self._graphable(latent_to_sem_func, linear_proj):
-            return self._generate_image_graphed(input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func,
+            return self._generate_image_graphed(input_embeds, cache, attention_mask, B, G, n_tok, latent_to_sem_func,
                                                 linear_proj, sem_to_pix_func, image_gen_temperature, noises)
         # key mask buffer for the whole generation: prompt part now, one more "1" column per generated token
         t_now = attention_mask.shape[1]
-        mask = torch.ones((B, t_now + n_tok + 1), dtype=torch.int32, device=dev)
+        mask = torch.ones((R, t_now + n_tok + 1), dtype=torch.int32, device=dev)
         mask[:, :t_now] = attention_mask.to(dev)
         pos0 = (attention_mask.long().cumsum(-1) - 1)[:, -1:].to(dev)  # position of the current token per row
         output_tokens, sem_cache, hidden = [], None, None
@@ -693,28 +728,30 @@ class BailingMoeForCausalLM(nn.Module):
             position_ids = (pos0 + token_idx).to(torch.int32)
             latent, hidden = self.forward_for_image_generation_inner(
                 inputs_embeds=input_embeds, attention_mask=mask, position_ids=position_ids, past_key_values=cache,
-                image_gen_temperature=image_gen_temperature,
-                noise=self._draw_noise(dev) if noises is None else noises[token_idx].to(dev))
+                image_gen_temperature=image_gen_temperature, groups=G,
+                noise=self._draw_noise(dev, G) if noises is None else noises[token_idx].to(dev))
             if token_idx < n_tok:
-                feat = latent_to_sem_func(latent[0:1] if one_row else latent, past_key_values=sem_cache)
+                feat = latent_to_sem_func(latent[0::B].contiguous() if one_row else latent, past_key_values=sem_cache)
                 sem_cache = feat["past_key_values"]
                 output_token = feat["x_norm_patchtokens"]
                 output_tokens.append(output_token)
                 input_embeds = linear_proj(output_token)
                 if one_row:
-                    input_embeds = input_embeds.expand(B, -1, -1)
-        cache.trim_rows()
+                    input_embeds = input_embeds.repeat_interleave(B, dim=0)
+        cache.trim_groups(G, B)
         final_mask = mask[:, :t_now + n_tok]
         image_tensor = sem_to_pix_func(torch.cat(output_tokens, dim=1))
-        if one_row:
+        if G == 1 and one_row:
             image_tensor = image_tensor.expand(B, *image_tensor.shape[1:])
+        elif G > 1 and not one_row:
+            image_tensor = image_tensor[0::B]
         return image_tensor, hidden, final_mask
 
-    def _draw_noise(self, dev) -> torch.Tensor:
+    def _draw_noise(self, dev, groups: int = 1) -> torch.Tensor:
         """The per-token torch.randn(1, C) of RectifiedFlowLoss.sample (diff_loss_rf_swiglu.py:118).  Expert-parallel
         modes that REPLICATE the tokens on every rank need the same draw everywhere (the ranks' partial expert sums are
         added): rank 0 draws, the others receive it, so differently seeded processes cannot diverge silently."""
-        noise = torch.randn(1, self.diffloss.in_channels, device=dev)
+        noise = torch.randn(groups, self.diffloss.in_channels, device=dev)
         if getattr(self.model, "ep_size", 1) > 1 and getattr(self.model, "ep_tokens_replicated", True):
             import torch.distributed as dist
 
@@ -814,47 +851,63 @@ class BailingMoeForCausalLM(nn.Module):
 
     def _token_step(self, ws) -> None:
         """LLM step -> vis_head -> RF sampler (hard-wired CFG 3.0 / 1.1) -> semantic-decoder step -> linear_proj, all on
-        static buffers and device-side positions (forward_for_image_generation_inner + the loop body of generate_image)."""
+        static buffers and device-side positions (forward_for_image_generation_inner + the loop body of generate_image).
+        R = G * B rows: G requests generated together, B CFG rows each (row g*B + b)."""
+        B, G = ws["B"], ws["G"]
         hidden = self.model.forward_tokens(ws["embeds"], ws["pos"], ws["cache"], key_mask=ws["mask"], t_dev=ws["t_llm"])
         ws["hidden"].copy_(hidden)
         z = self.compute_vis_z(hidden[:, -1])
-        ws["x"].copy_(ws["noise"].expand(ws["B"], -1) * ws["temperature"])
-        self.diffloss._sample_body(self.diffloss._pack(), z, ws["x"], 3.0, 1.1)
-        R = ws["sem_rows"]  # 1 when the CFG rows are de-duplicated (identical latents), else B
-        feat = ws["vision"]._decode_step(ws["x"][0:R], ws["sem_cache"], 0, ws["sem_cache"].t_dev)
+        C = ws["noise"].shape[1]
+        ws["x"].view(G, B, C).copy_((ws["noise"] * ws["temperature"]).unsqueeze(1).expand(G, B, C))
+        self.diffloss._sample_body(self.diffloss._pack(), z, ws["x"], 3.0, 1.1, B if B in (2, 3) else 1)
+        if ws["sem_rows"] == G * B:   # one semantic-decoder row per LLM row (CFG rows not de-duplicated)
+            lat = ws["x"]
+        elif G == 1:
+            lat = ws["x"][0:1]
+        else:                          # row 0 of every sample (the CFG rows of a sample carry identical latents)
+            ws["lat"].copy_(ws["x"].view(G, B, C)[:, 0])
+            lat = ws["lat"]
+        feat = ws["vision"]._decode_step(lat, ws["sem_cache"], 0, ws["sem_cache"].t_dev)
         ws["feats"].index_copy_(1, ws["t_idx"], feat.unsqueeze(1))
-        ws["embeds"].copy_(ws["linear_proj"](feat.unsqueeze(1)).expand(ws["B"], -1, -1))
+        e = ws["linear_proj"](feat.unsqueeze(1))
+        D = e.shape[-1]
+        if ws["sem_rows"] == G * B:
+            ws["embeds"].copy_(e)
+        else:
+            ws["embeds"].view(G, B, 1, D).copy_(e.view(G, 1, 1, D).expand(G, B, 1, D))
         ws["t_llm"].add_(1)
         ws["sem_cache"].t_dev.add_(1)
         ws["t_idx"].add_(1)
         ws["pos"].add_(1)
 
-    def _generate_image_graphed(self, input_embeds, cache, attention_mask, B, n_tok, latent_to_sem_func, linear_proj,
+    def _generate_image_graphed(self, input_embeds, cache, attention_mask, B, G, n_tok, latent_to_sem_func, linear_proj,
                                 sem_to_pix_func, temperature, noises):
         dev = input_embeds.device
         vision = latent_to_sem_func.__self__
         t_now = attention_mask.shape[1]
+        R = G * B
         if cache.seq_len != t_now - 1:
             raise ValueError("KV cache / attention mask length mismatch")
         if cache.seq_len + n_tok + 1 > cache.max_len:
             cache.grow(cache.seq_len + n_tok + 1)
-        R = 1 if self.dedupe_cfg_rows else B
-        key = (B, R, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len, _packs.epoch())
+        S = G if self.dedupe_cfg_rows else R   # semantic-decoder rows
+        key = (B, G, S, id(cache), id(vision), id(linear_proj), n_tok, float(temperature), cache.max_len, _packs.epoch())
         ws = self._gen_ws.get(key)
         if ws is None:
             C, D, F = self.diffloss.in_channels, self.config.hidden_size, vision.feature_dim
-            ws = dict(B=B, sem_rows=R, temperature=float(temperature), cache=cache, vision=vision,
+            ws = dict(B=B, G=G, sem_rows=S, temperature=float(temperature), cache=cache, vision=vision,
                       linear_proj=linear_proj,
-                      embeds=torch.zeros((B, 1, D), dtype=BF16, device=dev),
-                      hidden=torch.zeros((B, 1, D), dtype=BF16, device=dev),
-                      noise=torch.zeros((1, C), dtype=torch.float32, device=dev),
-                      x=torch.zeros((B, C), dtype=torch.float32, device=dev),
-                      feats=torch.zeros((R, n_tok + 1, F), dtype=BF16, device=dev),
-                      pos=torch.zeros((B, 1), dtype=torch.int32, device=dev),
-                      mask=torch.ones((B, cache.max_len), dtype=torch.int32, device=dev),
+                      embeds=torch.zeros((R, 1, D), dtype=BF16, device=dev),
+                      hidden=torch.zeros((R, 1, D), dtype=BF16, device=dev),
+                      noise=torch.zeros((G, C), dtype=torch.float32, device=dev),
+                      x=torch.zeros((R, C), dtype=torch.float32, device=dev),
+                      lat=torch.zeros((G, C), dtype=torch.float32, device=dev),
+                      feats=torch.zeros((S, n_tok + 1, F), dtype=BF16, device=dev),
+                      pos=torch.zeros((R, 1), dtype=torch.int32, device=dev),
+                      mask=torch.ones((R, cache.max_len), dtype=torch.int32, device=dev),
                       t_llm=torch.zeros((1,), dtype=torch.int32, device=dev),
                       t_idx=torch.zeros((1,), dtype=torch.int64, device=dev),
-                      sem_cache=vision.new_decode_cache(R, n_tok + 8), graph=None)
+                      sem_cache=vision.new_decode_cache(S, n_tok + 8), graph=None)
             self._gen_ws = {key: ws}  # one workspace at a time (a new cache / batch size re-captures)
 
         def reset_state():
@@ -882,14 +935,16 @@ class BailingMoeForCausalLM(nn.Module):
             reset_state()
         for token_idx in range(n_tok + 1):
             # RNG stays on the host side as in the reference (torch.randn(1, C) per token, diff_loss_rf_swiglu.py:118)
-            ws["noise"].copy_(self._draw_noise(dev) if noises is None else noises[token_idx].to(dev))
+            ws["noise"].copy_(self._draw_noise(dev, G) if noises is None else noises[token_idx].to(dev))
             ws["graph"].replay()
             _lib.count_replay(ws["kernels"])
         cache.seq_len += n_tok + 1
-        cache.trim_rows()
+        cache.trim_groups(G, B)
         final_mask = ws["mask"][:, :t_now + n_tok].clone()
         image_tensor = sem_to_pix_func(ws["feats"][:, :n_tok])
-        if R != B:
+        if G == 1 and S != R:
             image_tensor = image_tensor.expand(B, *image_tensor.shape[1:])
+        elif G > 1 and S == R:
+            image_tensor = image_tensor[0::B]
         self._last_gen_latent_hidden = ws["hidden"]
         return image_tensor, ws["hidden"].clone(), final_mask

@@ -251,24 +251,29 @@ class MingUniVisionForConditionalGeneration(nn.Module):
                                    text_uncond_attention_mask=None, image_gen_temperature=1.0, noises=None):
         """Prefill `input_ids` (optionally with an input image scattered at its `<imagePatch>` positions), then run
         BailingMoeForCausalLM.generate_image on the `<image>` start token — the sequence forward() performs when HF
-        generate feeds it that token (modeling_bailing_moe.py:1769-1796).  Returns (image [1,3,H,W], final mask)."""
+        generate feeds it that token (modeling_bailing_moe.py:1769-1796).  Returns (image [1,3,H,W], final mask).
+
+        Batched serving (extension): input_ids [G, S] — G requests of equal prompt length (masks [G, S+1],
+        pixel_values [G, 3, H, W]) — are prefilled and generated TOGETHER, G x CFG rows <= 8; returns images [G, 3, H, W].
+        Every request's result is what it would be on its own (the kernels are row-independent)."""
         llm, cfg = self.model, self.model.config
         dev = input_ids.device
-        S = input_ids.shape[1]
+        G, S = input_ids.shape
         emb = llm.model.embed(input_ids)
         image_mask = None
         if pixel_values is not None:
             emb, image_mask = self.prompt_wrap_vision(input_ids, emb, self.extract_image_feature(pixel_values))
         # a persistent workspace cache (so the captured AR-step graph stays valid across calls)
         need = S + 1 + cfg.num_image_tokens_for_gen + 8
+        rows = max(3, 3 * G)
         cache = getattr(self, "_ws_cache", None)
-        if cache is None or cache.max_len < need or cache.k[0].device != dev:
-            cache = self._ws_cache = llm.new_cache(max_len=max(need, 512))
-        cache.seq_len, cache.batch = 0, 1
-        pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0)
+        if cache is None or cache.max_len < need or cache.k[0].device != dev or cache.max_batch < rows:
+            cache = self._ws_cache = llm.new_cache(max_len=max(need, 512), max_batch=rows)
+        cache.seq_len, cache.batch = 0, G
+        pos = torch.arange(S, device=dev, dtype=torch.int32).unsqueeze(0).expand(G, S)
         llm.model.forward_tokens(emb, pos, cache, key_mask=None, image_mask=image_mask)
-        start = llm.model.embed(torch.tensor([[cfg.image_start_token]], device=dev))
-        am = torch.ones((1, S + 1), dtype=torch.int32, device=dev)
+        start = llm.model.embed(torch.full((G, 1), cfg.image_start_token, device=dev, dtype=torch.long))
+        am = torch.ones((G, S + 1), dtype=torch.int32, device=dev)
         img, _, fmask = llm.generate_image(
             input_embeds=start, past_key_values=cache, attention_mask=am, uncond_attention_mask=uncond_attention_mask,
             text_uncond_attention_mask=text_uncond_attention_mask,
@@ -276,7 +281,7 @@ class MingUniVisionForConditionalGeneration(nn.Module):
             sem_to_pix_func=self.vision.forward_pixel_decoder, image_gen_temperature=image_gen_temperature,
             noises=noises)
         self.past_key_values, self.past_attention_mask = cache, fmask[0:1]
-        return img[0:1], fmask
+        return (img[0:1] if G == 1 else img), fmask
 
     @torch.no_grad()
     def generate_text(self, input_ids, pixel_values=None, max_new_tokens: int = 32, eos_token_id=None):

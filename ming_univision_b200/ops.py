@@ -421,15 +421,16 @@ def silu_add_rows(temb: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
 
 
 def rf_euler_step(x_f32: torch.Tensor, x_bf16: torch.Tensor, v: torch.Tensor, dt: float, text_cfg: float,
-                  image_cfg: float) -> None:
-    """In-place CFG combine + Euler update of the fp32 state x (and its bf16 copy)."""
+                  image_cfg: float, cfg_rows: int | None = None) -> None:
+    """In-place CFG combine + Euler update of the fp32 state x (and its bf16 copy); the B rows are B / cfg_rows
+    independent samples of `cfg_rows` adjacent CFG rows (default: one sample)."""
     _check_bf16(x_bf16, v)
     if x_f32.dtype != torch.float32 or not x_f32.is_contiguous() or not v.is_contiguous():
         raise TypeError("x_f32 must be a contiguous fp32 tensor and v contiguous bf16")
     lib = _lib.load()
     B, C = x_f32.shape
-    _lib.check(lib.mb_rf_euler_step(x_f32.data_ptr(), x_bf16.data_ptr(), v.data_ptr(), B, C, float(dt),
-                                    float(text_cfg), float(image_cfg), _stream()), "mb_rf_euler_step")
+    _lib.check(lib.mb_rf_euler_step(x_f32.data_ptr(), x_bf16.data_ptr(), v.data_ptr(), B, int(cfg_rows or B), C,
+                                    float(dt), float(text_cfg), float(image_cfg), _stream()), "mb_rf_euler_step")
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -247,3 +247,60 @@ def test_state_dict_reload_drops_packs_and_graphs(wide_model, gold, cuda_device)
     finally:
         wide_model.load_state_dict(sd, strict=True)
     assert torch.equal(a, run())
+
+
+@pytest.mark.parametrize("name,G", [("edit", 2), ("t2i", 3)])
+def test_wide_batched_generation_equals_single(wide_model, gold, cuda_device, name, G):
+    """SURVEY.md §8f.1 (the reference asserts one sequence, modeling_bailing_moe.py:1865): G requests generated TOGETHER
+    (G x CFG rows = 6 rows per pass over the LLM / RF-head / semantic-decoder weights) must give every request exactly the
+    image it gets on its own — all kernels of the step are row-independent, so this is bit-for-bit."""
+    g = gold
+    base = torch.from_numpy(g["gen_ids"])
+    gen = torch.Generator().manual_seed(77)
+    ids = torch.cat([base] + [torch.randint(0, 100000, base.shape, generator=gen) for _ in range(G - 1)]).to(cuda_device)
+    n_tok = wide_model.model.config.num_image_tokens_for_gen
+    noises = [torch.randn((G, 32), generator=gen) for _ in range(n_tok + 1)]
+    um = torch.from_numpy(g[f"{name}_uncond"]).to(cuda_device)
+    tm = torch.from_numpy(g[f"{name}_text_uncond"]).to(cuda_device)
+    singles = []
+    for i in range(G):
+        img, fmask = wide_model.generate_image_from_prompt(ids[i:i + 1], uncond_attention_mask=um,
+                                                           text_uncond_attention_mask=tm, image_gen_temperature=0.9,
+                                                           noises=[n[i:i + 1] for n in noises])
+        singles.append((img.float().cpu(), fmask.cpu()))
+    for graph in (True, False):
+        wide_model.model.use_cuda_graph = graph
+        try:
+            imgs, fmask = wide_model.generate_image_from_prompt(ids, uncond_attention_mask=um.expand(G, -1),
+                                                                text_uncond_attention_mask=tm.expand(G, -1),
+                                                                image_gen_temperature=0.9, noises=noises)
+        finally:
+            wide_model.model.use_cuda_graph = True
+        B = singles[0][1].shape[0]
+        assert tuple(imgs.shape) == (G,) + tuple(singles[0][0].shape[1:]) and fmask.shape[0] == G * B
+        assert wide_model.past_key_values.batch == G
+        for i in range(G):
+            assert torch.equal(imgs[i:i + 1].float().cpu(), singles[i][0]), (graph, i)
+            assert torch.equal(fmask[i * B:(i + 1) * B].cpu(), singles[i][1]), (graph, i)
+
+
+def test_rf_sampler_groups_equal_single_samples(cuda_device):
+    """RectifiedFlowLoss.sample(groups=G): G samples of B CFG rows through ONE pass over the weights == G separate calls."""
+    from ming_univision_b200.diff_loss_rf_swiglu import RectifiedFlowLoss
+
+    cfg = synthetic.RF_CONFIG
+    with torch.device(cuda_device):
+        m = RectifiedFlowLoss(cfg["target_channels"], cfg["z_channels"], cfg["depth"], cfg["width"],
+                              str(cfg["num_sampling_steps"]), mlp_mult=cfg["mlp_mult"])
+    m.load_state_dict({k: v.to(cuda_device) for k, v in synthetic.rf_state_dict(cfg, 0).items()})
+    m = m.to(BF16)
+    gen = torch.Generator().manual_seed(3)
+    for B, G in ((3, 2), (2, 3), (1, 4)):
+        z = torch.randn((G * B, cfg["z_channels"]), generator=gen).to(cuda_device)
+        noise = torch.randn((G, 32), generator=gen).to(cuda_device)
+        tc = 3.0 if B > 1 else 1.0
+        both = m.sample(z, temperature=0.9, text_cfg=tc, image_cfg=1.1, groups=G,
+                        noise=noise if B > 1 else noise.repeat_interleave(B, 0))
+        for i in range(G):
+            one = m.sample(z[i * B:(i + 1) * B], temperature=0.9, text_cfg=tc, image_cfg=1.1, noise=noise[i:i + 1])
+            assert torch.equal(both[i * B:(i + 1) * B], one), (B, G, i)

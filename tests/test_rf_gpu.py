@@ -99,7 +99,7 @@ def test_rf_row_helpers(cuda_device):
         v = _rand((Bc, 32), cuda_device, 1.0, 16 + Bc)
         x0 = torch.randn((1, 32), device=cuda_device).repeat(Bc, 1).contiguous()
         xf, xb = x0.clone(), torch.zeros((Bc, 32), dtype=BF16, device=cuda_device)
-        ops.rf_euler_step(xf, xb, v, 1 / 16, 3.0, 1.1)
+        ops.rf_euler_step(xf, xb, v, 1 / 16, 3.0, 1.1)  # one sample of Bc CFG rows
         vf = v.float()
         if Bc == 3:
             vg = vf[1] + 1.1 * (vf[2] - vf[1]) + 3.0 * (vf[0] - vf[2])
