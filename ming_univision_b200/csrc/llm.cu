@@ -383,13 +383,17 @@ __device__ __forceinline__ void mma16816_f(float (&c)[4], uint32_t a0, uint32_t 
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int PHASE>
+// NT = 8-row column groups per pass: an expert's pairs are walked in chunks of 8 * NT rows, so its weights stream ONCE
+// per 8 * NT pairs (NT = 1: the CFG rows of one request; NT = 4: rows gathered from several requests / ranks, or a short
+// prefill — up to 32 pairs per expert and pass).
+template <int PHASE, int NT>
 __global__ void __launch_bounds__(256)
 moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                   const int32_t* __restrict__ expert_offsets, const int32_t* __restrict__ sorted_pair,
                   __nv_bfloat16* __restrict__ dst, int topk, int K, int n_cols, int64_t expert_stride) {
   constexpr int kTiles = (PHASE == 0) ? 2 : 1;
   constexpr int kUnroll = (PHASE == 0) ? 4 : 8;
+  constexpr int kRows = 8 * NT;
   extern __shared__ __align__(16) uint8_t moe_smem[];
   const int e = blockIdx.y;
   const int beg = expert_offsets[e], end = expert_offsets[e + 1];
@@ -401,8 +405,8 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   const int row_bytes = kgroups * 64 + 64;
   const __nv_bfloat16* We = W + static_cast<int64_t>(e) * expert_stride;
   const int n_items = (n_cols + 15) / 16;
-  for (int p0 = beg; p0 < end; p0 += 8) {
-    const int cnt = min(8, end - p0);
+  for (int p0 = beg; p0 < end; p0 += kRows) {
+    const int cnt = min(kRows, end - p0);
     __syncthreads();  // previous chunk fully consumed
     for (int i = tid; i < (cnt + 1) * (row_bytes / 16); i += blockDim.x) {
       const int m = i / (row_bytes / 16), c = i % (row_bytes / 16);
@@ -415,7 +419,9 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
       *reinterpret_cast<uint4*>(moe_smem + m * row_bytes + c * 16) = v;
     }
     __syncthreads();
-    const uint8_t* xrow = moe_smem + min(g, cnt) * row_bytes + t * 16;
+    const uint8_t* xrow[NT];  // this lane's activation row in every column group (rows >= cnt: the shared zero row)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) xrow[nt] = moe_smem + min(g + 8 * nt, cnt) * row_bytes + t * 16;
     const int nwarps = blockDim.x >> 5;
     for (int item = blockIdx.x * nwarps + warp; item < n_items; item += gridDim.x * nwarps) {
       const int n0 = item * 16;
@@ -426,9 +432,11 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
         wr[tl][0] = We + static_cast<int64_t>(base + min(n0 + g, n_cols - 1)) * K + t * 8;
         wr[tl][1] = We + static_cast<int64_t>(base + min(n0 + g + 8, n_cols - 1)) * K + t * 8;
       }
-      float acc[kTiles][4];
+      float acc[kTiles][NT][4];
 #pragma unroll
-      for (int tl = 0; tl < kTiles; ++tl) acc[tl][0] = acc[tl][1] = acc[tl][2] = acc[tl][3] = 0.f;
+      for (int tl = 0; tl < kTiles; ++tl)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[tl][nt][0] = acc[tl][nt][1] = acc[tl][nt][2] = acc[tl][nt][3] = 0.f;
       for (int kg0 = 0; kg0 < kgroups; kg0 += kUnroll) {
         uint4 w[kTiles][2][kUnroll];
 #pragma unroll
@@ -445,26 +453,33 @@ moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
         for (int u = 0; u < kUnroll; ++u) {
           const int kg = kg0 + u;
           if (kg < kgroups) {
-            const uint4 xb = *reinterpret_cast<const uint4*>(xrow + kg * 64);
 #pragma unroll
-            for (int tl = 0; tl < kTiles; ++tl) {
-              mma16816_f(acc[tl], w[tl][0][u].x, w[tl][1][u].x, w[tl][0][u].y, w[tl][1][u].y, xb.x, xb.y);
-              mma16816_f(acc[tl], w[tl][0][u].z, w[tl][1][u].z, w[tl][0][u].w, w[tl][1][u].w, xb.z, xb.w);
+            for (int nt = 0; nt < NT; ++nt) {
+              if (nt * 8 >= cnt) continue;  // (uniform per chunk) column groups without rows
+              const uint4 xb = *reinterpret_cast<const uint4*>(xrow[nt] + kg * 64);
+#pragma unroll
+              for (int tl = 0; tl < kTiles; ++tl) {
+                mma16816_f(acc[tl][nt], w[tl][0][u].x, w[tl][1][u].x, w[tl][0][u].y, w[tl][1][u].y, xb.x, xb.y);
+                mma16816_f(acc[tl][nt], w[tl][0][u].z, w[tl][1][u].z, w[tl][0][u].w, w[tl][1][u].w, xb.z, xb.w);
+              }
             }
           }
         }
       }
-      // accumulator element ei: weight row n0 + g + 8 (ei >> 1), chunk row (token) 2 t + (ei & 1)
+      // accumulator element ei: weight row n0 + g + 8 (ei >> 1), chunk row (token) 8 nt + 2 t + (ei & 1)
 #pragma unroll
-      for (int ei = 0; ei < 4; ++ei) {
-        const int n = n0 + g + 8 * (ei >> 1);
-        const int m = 2 * t + (ei & 1);
-        if (n < n_cols && m < cnt) {
-          if (PHASE == 0) {
-            const float gg = bf16_round(acc[0][ei]), uu = bf16_round(acc[kTiles - 1][ei]);
-            dst[static_cast<int64_t>(p0 + m) * n_cols + n] = __float2bfloat16_rn(bf16_round(silu(gg)) * uu);
-          } else {
-            dst[static_cast<int64_t>(sorted_pair[p0 + m]) * n_cols + n] = __float2bfloat16_rn(acc[0][ei]);
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int ei = 0; ei < 4; ++ei) {
+          const int n = n0 + g + 8 * (ei >> 1);
+          const int m = 8 * nt + 2 * t + (ei & 1);
+          if (n < n_cols && m < cnt) {
+            if (PHASE == 0) {
+              const float gg = bf16_round(acc[0][nt][ei]), uu = bf16_round(acc[kTiles - 1][nt][ei]);
+              dst[static_cast<int64_t>(p0 + m) * n_cols + n] = __float2bfloat16_rn(bf16_round(silu(gg)) * uu);
+            } else {
+              dst[static_cast<int64_t>(sorted_pair[p0 + m]) * n_cols + n] = __float2bfloat16_rn(acc[0][nt][ei]);
+            }
           }
         }
       }
@@ -848,18 +863,17 @@ extern "C" int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t*
   return MB_OK;
 }
 
-static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
-                            void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, int active_max,
-                            cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(9) * (((K / 8 + 3) / 4) * 64 + 64);
-  MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= 8192");
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[phase]) {
-    if (phase == 0)
-      MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    else
-      MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set[phase] = true;
+template <int PHASE, int NT>
+static int launch_moe_phase_nt(const void* A, const void* W, const int32_t* offs, const int32_t* sorted, void* dst,
+                               int topk, int E, int K, int n_cols, int64_t expert_stride, int active_max,
+                               cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(8 * NT + 1) * (((K / 8 + 3) / 4) * 64 + 64);
+  MB_CHECK_ARG(K % 8 == 0 && smem <= 160 * 1024, MB_ERR_SHAPE, "moe: K must be a multiple of 8 and <= %d",
+               NT == 1 ? 8192 : 2048);
+  static bool attr_set = false;
+  if (!attr_set) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<PHASE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
   }
   // One 16-row weight tile per warp.  Only the experts that received pairs do any work (at most `active_max` of the E
   // CTA columns): with a single decode row (<= 8 active experts) eight-warp CTAs would leave more than half of the SMs
@@ -870,18 +884,25 @@ static int launch_moe_phase(int phase, const void* A, const void* W, const int32
   int xblocks = (n_items + warps - 1) / warps;
   if (xblocks < 1) xblocks = 1;
   dim3 grid(xblocks, E);
-  if (phase == 0)
-    moe_expert_kernel<0><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
-                                                             static_cast<const __nv_bfloat16*>(W), offs, sorted,
-                                                             static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
-                                                             expert_stride);
-  else
-    moe_expert_kernel<1><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
-                                                             static_cast<const __nv_bfloat16*>(W), offs, sorted,
-                                                             static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
-                                                             expert_stride);
+  moe_expert_kernel<PHASE, NT><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
+                                                                    static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                                                                    static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
+                                                                    expert_stride);
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
+}
+
+// `rows` = token rows of the call: up to 8 rows no expert can receive more than 8 pairs (one pass of the 8-column kernel);
+// more rows (requests generated together, rows gathered from expert-parallel ranks, a short prefill) take the 32-row form.
+static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
+                            void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, int active_max,
+                            int rows, cudaStream_t stream) {
+  const bool wide = rows > 8 && K <= 2048;
+  if (phase == 0)
+    return wide ? launch_moe_phase_nt<0, 4>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream)
+                : launch_moe_phase_nt<0, 1>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream);
+  return wide ? launch_moe_phase_nt<1, 4>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream)
+              : launch_moe_phase_nt<1, 1>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream);
 }
 
 extern "C" int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
@@ -889,7 +910,7 @@ extern "C" int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* exp
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_gate_up: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(0, x, Wgu, expert_offsets, sorted_pair, hid, k, E, D, I, static_cast<int64_t>(2) * I * D,
-                          T * k < E ? T * k : E, static_cast<cudaStream_t>(stream_));
+                          T * k < E ? T * k : E, T, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
@@ -897,7 +918,7 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_down: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(1, hid, Wd, expert_offsets, sorted_pair, out_pairs, k, E, I, D, static_cast<int64_t>(D) * I,
-                          T * k < E ? T * k : E, static_cast<cudaStream_t>(stream_));
+                          T * k < E ? T * k : E, T, static_cast<cudaStream_t>(stream_));
 }
 
 
