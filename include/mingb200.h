@@ -280,9 +280,11 @@ int mb_router_topk(const void* logits, const void* logits_img, const uint8_t* im
 int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t* sorted_pair, int T, int k, int E, int e_begin,
                 void* stream);
 int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
-                   void* hid, int T, int k, int E, int D, int I, void* stream);
+                   void* hid, int T, int k, int E, int D, int I, int mean_pairs, void* stream);
 int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
-                void* out_pairs, int T, int k, int E, int D, int I, void* stream);
+                void* out_pairs, int T, int k, int E, int D, int I, int mean_pairs, void* stream);
+/* (mean_pairs: expected pairs per expert of the call, ceil(T k / number of experts the pairs spread over) — selects the
+ * 8- or the 32-rows-per-pass form of the streaming kernel.) */
 /* pair_row == NULL: out_pairs is in (token, slot) order; else pair p = t*k+j lives in row pair_row[p] of out_pairs
  * (grouped layout of mb_moe_plan; negative = expert not local, contributes zero). */
 int mb_moe_combine(const void* out_pairs, const float* weights, const void* shared, const void* residual, void* y,

@@ -46,8 +46,8 @@ SIGNATURES = {
     "mb_argmax_f32": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "mb_router_topk": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
-    "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_moe_plan": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -875,10 +875,10 @@ static int launch_moe_phase_nt(const void* A, const void* W, const int32_t* offs
     MB_CHECK_CUDA(cudaFuncSetAttribute(moe_expert_kernel<PHASE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  // One 16-row weight tile per warp.  Only the experts that received pairs do any work (at most `active_max` of the E
-  // CTA columns): with a single decode row (<= 8 active experts) eight-warp CTAs would leave more than half of the SMs
-  // idle, so that case runs four-warp CTAs (measured: 3.47 -> 3.33 ms per text token); two or more CFG rows keep the
-  // eight-warp shape (smaller CTAs measured slower there: the activation rows are re-staged by every CTA).
+  // One 16-row weight tile per warp.  Only the experts that received pairs do any work (at most `active_max` = the
+  // call's pair count of the E CTA columns): with a single decode row (<= 8 pairs) eight-warp CTAs would leave more than
+  // half of the SMs idle, so that case runs four-warp CTAs (measured: 3.47 -> 3.33 ms per text token); two or more CFG
+  // rows keep the eight-warp shape (smaller CTAs measured slower there: the activation rows are re-staged by every CTA).
   const int n_items = (n_cols + 15) / 16;
   const int warps = (active_max <= 8) ? 4 : 8;
   int xblocks = (n_items + warps - 1) / warps;
@@ -892,12 +892,14 @@ static int launch_moe_phase_nt(const void* A, const void* W, const int32_t* offs
   return MB_OK;
 }
 
-// `rows` = token rows of the call: up to 8 rows no expert can receive more than 8 pairs (one pass of the 8-column kernel);
-// more rows (requests generated together, rows gathered from expert-parallel ranks, a short prefill) take the 32-row form.
+// `mean_pairs` = expected (token, slot) pairs per expert of the call (T k / all experts, rounded up).  Up to ~6 the 8-column
+// kernel almost always finishes an expert in one pass (P[Poisson(6) > 8] = 15 %, and a second pass re-reads the expert from
+// L2) and keeps 2+ CTAs per SM in flight; beyond that (a short prefill, many requests per step) the 32-row form streams
+// every expert once per 32 pairs.
 static int launch_moe_phase(int phase, const void* A, const void* W, const int32_t* offs, const int32_t* sorted,
                             void* dst, int topk, int E, int K, int n_cols, int64_t expert_stride, int active_max,
-                            int rows, cudaStream_t stream) {
-  const bool wide = rows > 8 && K <= 2048;
+                            int mean_pairs, cudaStream_t stream) {
+  const bool wide = mean_pairs > 6 && K <= 2048;
   if (phase == 0)
     return wide ? launch_moe_phase_nt<0, 4>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream)
                 : launch_moe_phase_nt<0, 1>(A, W, offs, sorted, dst, topk, E, K, n_cols, expert_stride, active_max, stream);
@@ -906,19 +908,19 @@ static int launch_moe_phase(int phase, const void* A, const void* W, const int32
 }
 
 extern "C" int mb_moe_gate_up(const void* x, const void* Wgu, const int32_t* expert_offsets, const int32_t* sorted_pair,
-                              void* hid, int T, int k, int E, int D, int I, void* stream_) {
+                              void* hid, int T, int k, int E, int D, int I, int mean_pairs, void* stream_) {
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_gate_up: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(0, x, Wgu, expert_offsets, sorted_pair, hid, k, E, D, I, static_cast<int64_t>(2) * I * D,
-                          T * k < E ? T * k : E, T, static_cast<cudaStream_t>(stream_));
+                          T * k, mean_pairs, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* expert_offsets, const int32_t* sorted_pair,
-                           void* out_pairs, int T, int k, int E, int D, int I, void* stream_) {
+                           void* out_pairs, int T, int k, int E, int D, int I, int mean_pairs, void* stream_) {
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_down: no sm_100 device");
   if (T == 0) return MB_OK;
   return launch_moe_phase(1, hid, Wd, expert_offsets, sorted_pair, out_pairs, k, E, I, D, static_cast<int64_t>(D) * I,
-                          T * k < E ? T * k : E, T, static_cast<cudaStream_t>(stream_));
+                          T * k, mean_pairs, static_cast<cudaStream_t>(stream_));
 }
 
 

@@ -230,20 +230,26 @@ class BailingMoeSparseMoeBlock(nn.Module):
             im = image_mask.reshape(-1).to(torch.uint8).contiguous()
         idx, w = ops.router_topk(logits, cfg.num_experts_per_tok, cfg.num_experts_per_tok > 1 and cfg.norm_topk_prob,
                                  logits_img, im)
+        dispatch = self.ep_mode == "dispatch" and self.ep_size > 1
+        if dispatch and x2d.shape[0] <= self.ep_peer.t_max:
+            # push this rank's rows to the expert owners FIRST: the shared-expert GEMMs below then run while the rows cross
+            # NVLink and while slower ranks catch up
+            ops.ep_dispatch(self.ep_peer, x2d, idx, w)
         shared = None
         if "s12" in pk:
             if x2d.shape[0] <= 8:
                 shared = ops.gemv(ops.gemv(x2d, pk["s12"], None, epi=ops.EPI_SWIGLU), pk["s3"])
             else:
                 shared = ops.linear(ops.linear(x2d, pk["s12p"], None, epi=ops.EPI_SWIGLU), pk["s3p"])
-        if self.ep_mode == "dispatch" and self.ep_size > 1:
+        if dispatch:
             # data parallel x expert parallel: these are THIS rank's rows; dispatch + combine over peer memory (csrc/ep.cu)
             pd, T = self.ep_peer, x2d.shape[0]
             n_local = pk["Wgu"].shape[0]
             ys = []
             for c0 in range(0, T, pd.t_max):  # every rank makes the same calls (same T everywhere)
                 c1 = min(T, c0 + pd.t_max)
-                ops.ep_dispatch(pd, x2d[c0:c1], idx[c0:c1], w[c0:c1])
+                if T > pd.t_max:
+                    ops.ep_dispatch(pd, x2d[c0:c1], idx[c0:c1], w[c0:c1])
                 out_pairs, pair_row = ops.ep_compute(pd, c1 - c0, pk["Wgu"], pk["Wd"], pk["e_begin"], cfg.num_experts)
                 ops.ep_combine(pd, c1 - c0, out_pairs, pair_row, pk["e_begin"], n_local)
                 ys.append(ops.ep_finalize(pd, c1 - c0, None if shared is None else shared[c0:c1],

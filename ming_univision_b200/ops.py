@@ -631,10 +631,17 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
         out_pairs = (torch.zeros if ep else torch.empty)((T * k, D), dtype=BF16, device=dev)
         _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
                    "mb_moe_sort")
+        # (with ep_group the slabs hold E of E * world experts; the pairs spread over all of them)
+        n_all = E
+        if ep:
+            import torch.distributed as dist
+
+            n_all = E * dist.get_world_size(ep_group)
+        mean_pairs = -(-T * k // n_all)
         _lib.check(lib.mb_moe_gate_up(x.data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                                      hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
+                                      hid.data_ptr(), T, k, E, D, I, mean_pairs, s), "mb_moe_gate_up")
         _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                                   out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+                                   out_pairs.data_ptr(), T, k, E, D, I, mean_pairs, s), "mb_moe_down")
         pr = None
     if not ep:
         _lib.check(lib.mb_moe_combine(out_pairs.data_ptr(), w.data_ptr(), _ptr(shared), _ptr(residual), y.data_ptr(),
@@ -687,10 +694,11 @@ def moe_local_experts(x: torch.Tensor, idx: torch.Tensor, Wgu: torch.Tensor, Wd:
     out_pairs = torch.empty((T * k, D), dtype=BF16, device=dev)
     _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
                "mb_moe_sort")
+    mean_pairs = -(-T * k // (n_experts_total or E))
     _lib.check(lib.mb_moe_gate_up(x.data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                                  hid.data_ptr(), T, k, E, D, I, s), "mb_moe_gate_up")
+                                  hid.data_ptr(), T, k, E, D, I, mean_pairs, s), "mb_moe_gate_up")
     _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
-                               out_pairs.data_ptr(), T, k, E, D, I, s), "mb_moe_down")
+                               out_pairs.data_ptr(), T, k, E, D, I, mean_pairs, s), "mb_moe_down")
     return out_pairs, None
 
 

@@ -66,6 +66,54 @@ if world > 1:
     y_px, _, _ = blk._run(x, res, None)
     out["rel_err_peer_vs_unsharded"] = float(((y_px.float() - y_single.float()).norm() / y_single.float().norm()).item())
     out["ms_layer_ep_peer"] = round(timeit(lambda: blk._run(x, res, None)), 4)
+# ---- "dispatch" mode (data parallel x expert parallel, csrc/ep.cu): every rank has its OWN rows; the MoE part of a token
+# step (28 consecutive layer calls) captured in ONE CUDA graph on both sides, so host launch time is out of the picture
+def graph_ms(fn, layers=28, reps=10):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    if world > 1:
+        dist.barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(layers):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([s.elapsed_time(e) / reps / layers], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+if world > 1:
+    blk.set_expert_parallel(None, 0, 1)
+for R in (3, 6):
+    xr = torch.randn((R, 2048), generator=torch.Generator(device=dev).manual_seed(100 + rank), device=dev).to(torch.bfloat16)
+    rr = torch.randn((R, 2048), generator=torch.Generator(device=dev).manual_seed(200 + rank), device=dev).to(torch.bfloat16)
+    out[f"ms_layer_graph_unsharded_rows{R}"] = round(graph_ms(lambda: blk._run(xr, rr, None)), 4)
+if world > 1:
+    from ming_univision_b200.ep import PeerDispatch  # noqa: E402
+    pd = PeerDispatch(dist.group.WORLD, 2048, cfg.num_experts_per_tok, 64, dev)
+    blk.set_expert_parallel(dist.group.WORLD, rank, world, mode="dispatch", peer=pd)
+    for R in (3, 6):
+        xr = torch.randn((R, 2048), generator=torch.Generator(device=dev).manual_seed(100 + rank), device=dev).to(torch.bfloat16)
+        rr = torch.randn((R, 2048), generator=torch.Generator(device=dev).manual_seed(200 + rank), device=dev).to(torch.bfloat16)
+        out[f"ms_layer_graph_dispatch_rows{R}"] = round(graph_ms(lambda: blk._run(xr, rr, None)), 4)
+        torch.cuda.synchronize()
+        pd.check()
+    blk.set_expert_parallel(None, 0, 1)
+
 # ---- prefill-sized input (BASELINE configs[2] shape: 1552 tokens): unsharded grouped tcgen05 GEMMs vs expert-parallel
 # all-reduce (tokens replicated) vs token-sharded all-to-all dispatch / combine + all-gather
 T = int(os.environ.get("EP_PREFILL_TOKENS", "1552"))
