@@ -344,6 +344,9 @@ int mb_ep_area_layout(int G, int Tmax, int D, int k, int64_t* offsets6);
 int mb_ep_dispatch_push(const void* x, const int32_t* idx, const float* w, void* const* peers, int my_rank, int G, int T,
                         int Tmax, int D, int k, void* stream);
 int mb_ep_dispatch_wait(void* const* peers, int my_rank, int G, int Tmax, int D, int k, void* stream);
+/* mb_ep_dispatch_wait + mb_moe_sort of the gathered pairs (expert_offsets [E + 1], sorted_pair [G*T*k]) in one launch. */
+int mb_ep_wait_sort(void* const* peers, int my_rank, int G, int T, int Tmax, int D, int k, int32_t* expert_offsets,
+                    int32_t* sorted_pair, int E, int e_begin, void* stream);
 int mb_ep_combine_push(const void* out_pairs, const int32_t* pair_row, void* const* peers, int my_rank, int G, int T,
                        int Tmax, int D, int k, int e_begin, int e_local, void* stream);
 int mb_ep_reduce_finalize(void* const* peers, int my_rank, int G, int T, int Tmax, int D, int k, const void* shared,

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mb_ep_area_layout": [_i, _i, _i, _i, _vp],
     "mb_ep_dispatch_push": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "mb_ep_dispatch_wait": [_vp, _i, _i, _i, _i, _i, _vp],
+    "mb_ep_wait_sort": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp],
     "mb_ep_combine_push": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mb_ep_reduce_finalize": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mb_image_preprocess_workspace_bytes": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -137,6 +137,52 @@ ep_dispatch_wait_kernel(uint8_t* const* __restrict__ peers, int my_rank, int G, 
   for (int s = threadIdx.x; s < G; s += 32) ep_wait_flag(flags, s, epoch, ctl, timeout_ns, 1);
 }
 
+// mb_ep_dispatch_wait fused with the counting sort of the gathered pairs by LOCAL expert (mb_moe_sort's job on the
+// streaming path): one launch less per layer.  Single CTA; pairs routed to other ranks' experts are not listed.
+__global__ void __launch_bounds__(256)
+ep_wait_sort_kernel(uint8_t* const* __restrict__ peers, int my_rank, int G, int T, int Tmax, int D, int k,
+                    int32_t* __restrict__ expert_offsets, int32_t* __restrict__ sorted_pair, int E, int e_begin,
+                    uint64_t timeout_ns) {
+  extern __shared__ int32_t sm[];  // counts[E], cursor[E], idx[G*T*k] (local expert index of every pair, or -1)
+  const EpLayout L(G, Tmax, D, k);
+  uint32_t* flags = ep_ctrl(peers[my_rank], L);
+  uint32_t* ctl = flags + 2 * G;
+  const uint32_t epoch = ctl[kEpEpoch] + 1;
+  if (threadIdx.x < G) ep_wait_flag(flags, threadIdx.x, epoch, ctl, timeout_ns, 1);
+  __syncthreads();
+  const int32_t* idx = reinterpret_cast<const int32_t*>(peers[my_rank] + L.idx);
+  const int npairs = G * T * k;
+  int32_t* counts = sm;
+  int32_t* cursor = sm + E;
+  int32_t* loc = sm + 2 * E;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) counts[e] = 0;
+  __syncthreads();
+  // one coalesced pass over the gathered ids (written by the peers: read through L2), everything else in shared memory
+  for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+    int e = __ldcg(idx + p) - e_begin;
+    if (e < 0 || e >= E) e = -1;
+    loc[p] = e;
+    if (e >= 0) atomicAdd(&counts[e], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int e = 0; e < E; ++e) {
+      expert_offsets[e] = acc;
+      cursor[e] = acc;
+      acc += counts[e];
+    }
+    expert_offsets[E] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {  // deterministic order inside an expert: increasing pair index
+    int c = cursor[e];
+    if (counts[e] == 0) continue;
+    for (int p = 0; p < npairs; ++p)
+      if (loc[p] == e) sorted_pair[c++] = p;
+  }
+}
+
 // grid-stride over the G*T*D/4 float4 elements of the partial sums
 __global__ void __launch_bounds__(256)
 ep_combine_push_kernel(const __nv_bfloat16* __restrict__ out_pairs, const int32_t* __restrict__ pair_row,
@@ -290,6 +336,21 @@ extern "C" int mb_ep_dispatch_wait(void* const* peers, int my_rank, int G, int T
   MB_EP_COMMON_CHECKS("mb_ep_dispatch_wait");
   ep_dispatch_wait_kernel<<<1, 32, 0, stream>>>(reinterpret_cast<uint8_t* const*>(peers), my_rank, G, Tmax, D, k,
                                                 ep_timeout_ns());
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MB_OK;
+}
+
+extern "C" int mb_ep_wait_sort(void* const* peers, int my_rank, int G, int T, int Tmax, int D, int k,
+                               int32_t* expert_offsets, int32_t* sorted_pair, int E, int e_begin, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MB_EP_COMMON_CHECKS("mb_ep_wait_sort");
+  MB_CHECK_ARG(E >= 1 && E <= 4096 && expert_offsets != nullptr && sorted_pair != nullptr, MB_ERR_SHAPE,
+               "mb_ep_wait_sort: bad expert range");
+  const size_t smem = (2 * static_cast<size_t>(E) + static_cast<size_t>(G) * T * k) * sizeof(int32_t);
+  MB_CHECK_ARG(smem <= 48 * 1024, MB_ERR_SHAPE, "mb_ep_wait_sort: %d gathered pairs do not fit shared memory", G * T * k);
+  ep_wait_sort_kernel<<<1, 256, smem, stream>>>(reinterpret_cast<uint8_t* const*>(peers), my_rank, G, T,
+                                                                    Tmax, D, k, expert_offsets, sorted_pair, E, e_begin,
+                                                                    ep_timeout_ns());
   MB_CHECK_CUDA(cudaGetLastError());
   return MB_OK;
 }

@@ -719,10 +719,30 @@ def ep_dispatch(pd, x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, rank: i
 def ep_compute(pd, T: int, Wgu: torch.Tensor, Wd: torch.Tensor, e_begin: int, n_experts_total: int,
                rank: int | None = None):
     r = pd.rank if rank is None else rank
-    _lib.check(_lib.load().mb_ep_dispatch_wait(pd.peers_dev, r, pd.size, pd.t_max, pd.hidden_size, pd.top_k, _stream()),
-               "mb_ep_dispatch_wait")
+    lib = _lib.load()
     x_all, idx_all, _ = pd.gathered(T, r)
-    return moe_local_experts(x_all, idx_all, Wgu, Wd, e_begin, n_experts_total)
+    Ta, k = x_all.shape[0], pd.top_k
+    E, I2, D = Wgu.shape
+    if _moe_use_grouped(Ta, k, n_experts_total) or (2 * E + Ta * k) * 4 > 48 * 1024:
+        # prefill-sized: wait, then the tile plan + grouped tcgen05 GEMMs (or the plain sort when the pairs are too many
+        # for the fused kernel's shared memory)
+        _lib.check(lib.mb_ep_dispatch_wait(pd.peers_dev, r, pd.size, pd.t_max, pd.hidden_size, k, _stream()),
+                   "mb_ep_dispatch_wait")
+        return moe_local_experts(x_all, idx_all, Wgu, Wd, e_begin, n_experts_total)
+    # decode-sized: the wait rides in the sort kernel of the streaming path
+    dev, s = x_all.device, _stream()
+    offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
+    sorted_pair = torch.empty((Ta * k,), dtype=torch.int32, device=dev)
+    hid = torch.empty((Ta * k, I2 // 2), dtype=BF16, device=dev)
+    out_pairs = torch.empty((Ta * k, D), dtype=BF16, device=dev)
+    _lib.check(lib.mb_ep_wait_sort(pd.peers_dev, r, pd.size, T, pd.t_max, pd.hidden_size, k, offs.data_ptr(),
+                                   sorted_pair.data_ptr(), E, int(e_begin), s), "mb_ep_wait_sort")
+    mean_pairs = -(-Ta * k // n_experts_total)
+    _lib.check(lib.mb_moe_gate_up(x_all.data_ptr(), Wgu.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                                  hid.data_ptr(), Ta, k, E, D, I2 // 2, mean_pairs, s), "mb_moe_gate_up")
+    _lib.check(lib.mb_moe_down(hid.data_ptr(), Wd.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(),
+                               out_pairs.data_ptr(), Ta, k, E, D, I2 // 2, mean_pairs, s), "mb_moe_down")
+    return out_pairs, None
 
 
 def ep_combine(pd, T: int, out_pairs: torch.Tensor, pair_row: torch.Tensor | None, e_begin: int, e_local: int,

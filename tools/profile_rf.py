@@ -17,10 +17,11 @@ with torch.device(dev):
 m.load_state_dict({k: v.to(dev) for k, v in synthetic.rf_state_dict(cfg, 0).items()})
 m = m.to(torch.bfloat16)
 m.use_cuda_graph = False
-z = torch.randn((int(os.environ.get("RF_ROWS", "3")), cfg["z_channels"]), device=dev)
-m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1)
+B = int(os.environ.get("RF_ROWS", "3"))
+z = torch.randn((B, cfg["z_channels"]), device=dev)
+m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1, groups=max(1, B // 3))
 torch.cuda.synchronize()
 torch.cuda.profiler.start()
-m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1)
+m.sample(z, temperature=1.0, text_cfg=3.0, image_cfg=1.1, groups=max(1, B // 3))
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
