@@ -45,6 +45,8 @@ __device__ __forceinline__ float dot8f(const uint4& w, const uint4& a) {
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                __nv_bfloat16* __restrict__ y, int64_t ldy, int rows, int dim, float eps) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const __nv_bfloat16* xr = x + static_cast<int64_t>(row) * ldx;
@@ -79,6 +81,8 @@ rope_kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __re
                       __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ kcache,
                       __nv_bfloat16* __restrict__ vcache, int B, int S, int H, int Hkv, int hd, int Tmax,
                       const int32_t* __restrict__ t_dev, int t_host, float theta) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   const int row = blockIdx.x;  // b * S + s
   const int b = row / S, s = row % S;
   const int slot = (t_dev ? *t_dev : 0) + t_host + s;
@@ -128,6 +132,8 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
                           int64_t mask_stride, __nv_bfloat16* __restrict__ out, int B, int H, int Hkv, int Tmax,
                           const int32_t* __restrict__ t_dev, int t_host, float scale, float* __restrict__ partial,
                           int chunk) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   // one CTA (4 warps) per (batch row, q head): the warps take interleaved groups of 4 keys, then merge their partial
   // (max, sum, output) triples through shared memory — 4x shorter dependent chain than one warp per head
   __shared__ float s_m[4], s_l[4], s_o[4][128];
@@ -201,6 +207,8 @@ attn_decode_gqa128_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat
 // one warp per (batch row, q head): combines the per-chunk partials of attn_decode_gqa128_kernel
 __global__ void __launch_bounds__(128)
 attn_decode_merge_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int n_heads, int n_splits) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   const int bh = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (bh >= n_heads) return;
   const float* src = partial + static_cast<int64_t>(bh) * n_splits * 130;
@@ -278,6 +286,8 @@ __global__ void __launch_bounds__(128)
 router_topk_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16* __restrict__ logits_img,
                    const uint8_t* __restrict__ image_mask, int32_t* __restrict__ idx, float* __restrict__ wout, int T,
                    int E, int k, int renorm) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (t >= T) return;
   const __nv_bfloat16* lg = (logits_img != nullptr && image_mask != nullptr && image_mask[t]) ? logits_img : logits;
@@ -335,6 +345,8 @@ router_topk_kernel(const __nv_bfloat16* __restrict__ logits, const __nv_bfloat16
 __global__ void __launch_bounds__(256)
 moe_sort_kernel(const int32_t* __restrict__ idx, int32_t* __restrict__ expert_offsets,
                 int32_t* __restrict__ sorted_pair, int npairs, int E, int e_begin) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   // E = number of LOCAL experts [e_begin, e_begin + E); pairs routed elsewhere (expert parallelism) are not listed
   extern __shared__ int32_t sm[];  // counts[E], cursor[E]
   int32_t* counts = sm;
@@ -391,6 +403,8 @@ __global__ void __launch_bounds__(256)
 moe_expert_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
                   const int32_t* __restrict__ expert_offsets, const int32_t* __restrict__ sorted_pair,
                   __nv_bfloat16* __restrict__ dst, int topk, int K, int n_cols, int64_t expert_stride) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   constexpr int kTiles = (PHASE == 0) ? 2 : 1;
   constexpr int kUnroll = (PHASE == 0) ? 4 : 8;
   constexpr int kRows = 8 * NT;
@@ -583,6 +597,8 @@ __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ out_pairs, 
                                    const __nv_bfloat16* __restrict__ shared, const __nv_bfloat16* __restrict__ residual,
                                    __nv_bfloat16* __restrict__ y, float* __restrict__ y_partial,
                                    const int32_t* __restrict__ pair_row, int T, int k, int D) {
+  pdl_launch_dependents();  // (PDL: the next kernel of the stream may start launching; it waits below us)
+  pdl_wait();
   const int64_t total = static_cast<int64_t>(T) * D;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -782,10 +798,9 @@ extern "C" int mb_rmsnorm(const void* x, int64_t ldx, const void* w, void* y, in
   MB_CHECK_ARG(rows >= 0 && dim >= 8 && dim % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, MB_ERR_SHAPE,
                "mb_rmsnorm: dim, ldx, ldy must be multiples of 8");
   if (rows == 0) return MB_OK;
-  rmsnorm_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ldx,
-                                                     static_cast<const __nv_bfloat16*>(w),
-                                                     static_cast<__nv_bfloat16*>(y), ldy, rows, dim, eps);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(rmsnorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream,
+                           static_cast<const __nv_bfloat16*>(x), ldx, static_cast<const __nv_bfloat16*>(w),
+                           static_cast<__nv_bfloat16*>(y), ldy, rows, dim, eps));
   return MB_OK;
 }
 
@@ -798,12 +813,10 @@ extern "C" int mb_rope_kv_append(const void* qkv, const int32_t* position_ids, v
   MB_CHECK_ARG(t_dev != nullptr || (t_host >= 0 && t_host + S <= Tmax), MB_ERR_SHAPE,
                "mb_rope_kv_append: cache overflow (t=%d S=%d Tmax=%d)", t_host, S, Tmax);
   if (B * S == 0) return MB_OK;
-  rope_kv_append_kernel<<<B * S, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(qkv), position_ids,
-                                                   static_cast<__nv_bfloat16*>(q_out),
-                                                   static_cast<__nv_bfloat16*>(kcache),
-                                                   static_cast<__nv_bfloat16*>(vcache), B, S, H, Hkv, hd, Tmax, t_dev,
-                                                   t_host, rope_theta);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(rope_kv_append_kernel, dim3(B * S), dim3(256), 0, stream,
+                           static_cast<const __nv_bfloat16*>(qkv), position_ids, static_cast<__nv_bfloat16*>(q_out),
+                           static_cast<__nv_bfloat16*>(kcache), static_cast<__nv_bfloat16*>(vcache), B, S, H, Hkv, hd, Tmax,
+                           t_dev, t_host, rope_theta));
   return MB_OK;
 }
 
@@ -819,24 +832,22 @@ extern "C" int mb_attn_decode_gqa(const void* q, const void* kcache, const void*
                "mb_attn_decode_gqa: n_splits > 1 needs a workspace of B * H * n_splits * 130 floats");
   if (B == 0) return MB_OK;
   if (n_splits == 1) {
-    attn_decode_gqa128_kernel<<<B * H, 128, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
-        static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
-        Tmax, t_dev, t_host, scale, nullptr, 0);
-    MB_CHECK_CUDA(cudaGetLastError());
+    MB_CHECK_CUDA(launch_pdl(attn_decode_gqa128_kernel, dim3(B * H), dim3(128), 0, stream,
+                             static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+                             static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride,
+                             static_cast<__nv_bfloat16*>(out), B, H, Hkv, Tmax, t_dev, t_host, scale, nullptr, 0));
     return MB_OK;
   }
   // the longest context this call can see: the host length, or the whole cache when the length lives on the device
   const int t_bound = (t_dev != nullptr) ? Tmax : t_host;
   const int chunk = ((t_bound + n_splits - 1) / n_splits + 15) / 16 * 16;
-  attn_decode_gqa128_kernel<<<dim3(B * H, n_splits), 128, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
-      static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride, static_cast<__nv_bfloat16*>(out), B, H, Hkv,
-      Tmax, t_dev, t_host, scale, workspace, chunk < 16 ? 16 : chunk);
-  MB_CHECK_CUDA(cudaGetLastError());
-  attn_decode_merge_kernel<<<(B * H + 3) / 4, 128, 0, stream>>>(workspace, static_cast<__nv_bfloat16*>(out), B * H,
-                                                                n_splits);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(attn_decode_gqa128_kernel, dim3(B * H, n_splits), dim3(128), 0, stream,
+                           static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kcache),
+                           static_cast<const __nv_bfloat16*>(vcache), key_mask, mask_stride,
+                           static_cast<__nv_bfloat16*>(out), B, H, Hkv, Tmax, t_dev, t_host, scale, workspace,
+                           chunk < 16 ? 16 : chunk));
+  MB_CHECK_CUDA(launch_pdl(attn_decode_merge_kernel, dim3((B * H + 3) / 4), dim3(128), 0, stream, workspace,
+                           static_cast<__nv_bfloat16*>(out), B * H, n_splits));
   return MB_OK;
 }
 
@@ -846,10 +857,9 @@ extern "C" int mb_router_topk(const void* logits, const void* logits_img, const 
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_router_topk: no sm_100 device");
   MB_CHECK_ARG(E >= 1 && E <= 256 && k >= 1 && k <= 32 && k <= E, MB_ERR_SHAPE, "mb_router_topk: E <= 256, k <= 32");
   if (T == 0) return MB_OK;
-  router_topk_kernel<<<(T + 3) / 4, 128, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits),
-                                                      static_cast<const __nv_bfloat16*>(logits_img), image_mask, idx,
-                                                      weights, T, E, k, renorm);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(router_topk_kernel, dim3((T + 3) / 4), dim3(128), 0, stream,
+                           static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(logits_img),
+                           image_mask, idx, weights, T, E, k, renorm));
   return MB_OK;
 }
 
@@ -858,8 +868,8 @@ extern "C" int mb_moe_sort(const int32_t* idx, int32_t* expert_offsets, int32_t*
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_sort: no sm_100 device");
   MB_CHECK_ARG(E >= 1 && E <= 4096 && e_begin >= 0, MB_ERR_SHAPE, "mb_moe_sort: bad expert range");
-  moe_sort_kernel<<<1, 256, 2 * E * sizeof(int32_t), stream>>>(idx, expert_offsets, sorted_pair, T * k, E, e_begin);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(moe_sort_kernel, dim3(1), dim3(256), 2 * E * sizeof(int32_t), stream, idx, expert_offsets,
+                           sorted_pair, T * k, E, e_begin));
   return MB_OK;
 }
 
@@ -884,11 +894,9 @@ static int launch_moe_phase_nt(const void* A, const void* W, const int32_t* offs
   int xblocks = (n_items + warps - 1) / warps;
   if (xblocks < 1) xblocks = 1;
   dim3 grid(xblocks, E);
-  moe_expert_kernel<PHASE, NT><<<grid, warps * 32, smem, stream>>>(static_cast<const __nv_bfloat16*>(A),
-                                                                    static_cast<const __nv_bfloat16*>(W), offs, sorted,
-                                                                    static_cast<__nv_bfloat16*>(dst), topk, K, n_cols,
-                                                                    expert_stride);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(moe_expert_kernel<PHASE, NT>, grid, dim3(warps * 32), smem, stream,
+                           static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(W), offs, sorted,
+                           static_cast<__nv_bfloat16*>(dst), topk, K, n_cols, expert_stride));
   return MB_OK;
 }
 
@@ -1024,10 +1032,9 @@ extern "C" int mb_moe_combine(const void* out_pairs, const float* weights, const
   if (total == 0) return MB_OK;
   int grid = static_cast<int>((total + 255) / 256);
   if (grid > num_sms() * 8) grid = num_sms() * 8;
-  moe_combine_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(out_pairs), weights,
-                                               static_cast<const __nv_bfloat16*>(shared),
-                                               static_cast<const __nv_bfloat16*>(residual),
-                                               static_cast<__nv_bfloat16*>(y), y_partial, pair_row, T, k, D);
-  MB_CHECK_CUDA(cudaGetLastError());
+  MB_CHECK_CUDA(launch_pdl(moe_combine_kernel, dim3(grid), dim3(256), 0, stream,
+                           static_cast<const __nv_bfloat16*>(out_pairs), weights, static_cast<const __nv_bfloat16*>(shared),
+                           static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(y), y_partial, pair_row,
+                           T, k, D));
   return MB_OK;
 }
