@@ -222,3 +222,29 @@ def test_state_dict_load_through_the_parent_drops_every_pack():
     poison()
     m.float()                                                # _apply path (.to / .float / .bfloat16)
     assert clean()
+
+
+def test_flat_module_names_of_the_reference_resolve_to_the_package():
+    """The reference's scripts import `modeling_bailingmm`, `mingunivisioninfer`, `mingtok.modeling_mingtok`, ... as
+    top-level modules (mingunivisioninfer.py:1-7, modeling_bailingmm.py:25-28); install_flat_modules() makes exactly those
+    import lines work against this package (run in a fresh interpreter so no reference checkout is involved)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import ming_univision_b200 as pkg\n"
+        "names = pkg.install_flat_modules()\n"
+        "from modeling_bailingmm import MingUniVisionForConditionalGeneration\n"
+        "from modeling_bailing_moe import BailingMoeForCausalLM, BailingMoeSparseMoeBlock, BailingMoeConfig\n"
+        "from diff_loss_rf_swiglu import RectifiedFlowLoss\n"
+        "from mingtok.modeling_mingtok import MingTok, MingTokConfig\n"
+        "from mingtok.utils.processor import CenterCropProcessor\n"
+        "from mingunivisioninfer import MingUniVisionInfer\n"
+        "from image_processing_bailingmm import BailingMMImageProcessor, smart_resize\n"
+        "assert MingTok.__module__.startswith('ming_univision_b200.') and len(names) == 9, names\n"
+        "print('flat ok')\n" % root)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "flat ok" in r.stdout, r.stdout + r.stderr
