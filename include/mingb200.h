@@ -305,6 +305,14 @@ int mb_moe_gather_rows(const void* x, const int32_t* row_token, const int32_t* m
                        void* stream);
 int mb_moe_grouped_gemm(const void* A, const void* W, void* out, const int32_t* tile_expert,
                         const int32_t* num_m_tiles, int max_rows, int N, int K, int E, int swiglu, void* stream);
+/* Whole-stage driver for decode-sized inputs: mb_moe_sort -> mb_moe_gate_up -> mb_moe_down -> mb_moe_combine chained on
+ * the caller's stream inside a caller-provided workspace (mb_moe_ffn_workspace_bytes; 256-byte aligned): y [T, D] =
+ * bf16(bf16(bf16(sum_j w[t,j] expert_{idx[t,j]}(x[t])) + shared[t]) + residual[t]) — one call per MoE layer for a host
+ * that does not want to orchestrate the four kernels (BailingMoeSparseMoeBlock.moe_infer :608-639, :604-605, :1226). */
+int mb_moe_ffn_workspace_bytes(int T, int k, int E, int D, int I, int64_t* bytes);
+int mb_moe_ffn(const void* x, const int32_t* idx, const float* weights, const void* Wgu, const void* Wd,
+               const void* shared, const void* residual, void* y, void* workspace, int64_t workspace_bytes, int T, int k,
+               int E, int e_begin, int n_experts_total, int D, int I, void* stream);
 /* Expert parallelism (no reference implementation — the reference keeps all experts on one device):
  * rank r owns experts [e_begin, e_begin + E) — mb_moe_sort lists only the pairs routed to them, mb_moe_gate_up /
  * mb_moe_down run on the local slabs, mb_moe_combine with y_partial != NULL writes this rank's fp32 share of the

@@ -48,6 +48,8 @@ SIGNATURES = {
     "mb_moe_sort": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "mb_moe_gate_up": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_down": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "mb_moe_ffn_workspace_bytes": [_i, _i, _i, _i, _i, _vp],
+    "mb_moe_ffn": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_combine": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "mb_moe_plan": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
     "mb_moe_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],

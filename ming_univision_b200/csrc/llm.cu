@@ -933,6 +933,59 @@ extern "C" int mb_moe_down(const void* hid, const void* Wd, const int32_t* exper
 
 
 
+// ------------------------------------------------------------------------------------------------------------
+// Whole-stage driver of the routed-expert FFN for decode-sized inputs (moe_infer :608-639 + shared-expert add :604-605 +
+// layer residual :1226): sort -> gate/up + SwiGLU -> down -> weighted combine, chained on the caller's stream with a
+// caller-provided workspace (no allocation, no host synchronisation) — what a non-Python host calls per MoE layer.
+// ------------------------------------------------------------------------------------------------------------
+static size_t moe_ffn_ws_layout(int T, int k, int E, int D, int I, size_t (&off)[4]) {
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  off[0] = 0;                                                        // expert_offsets [E + 1] i32
+  off[1] = up(off[0] + (static_cast<size_t>(E) + 1) * 4);            // sorted_pair [T k] i32
+  off[2] = up(off[1] + static_cast<size_t>(T) * k * 4);              // hid [T k, I] bf16
+  off[3] = up(off[2] + static_cast<size_t>(T) * k * I * 2);          // out_pairs [T k, D] bf16
+  return up(off[3] + static_cast<size_t>(T) * k * D * 2);
+}
+
+extern "C" int mb_moe_ffn_workspace_bytes(int T, int k, int E, int D, int I, int64_t* bytes) {
+  MB_CHECK_ARG(T >= 0 && k >= 1 && E >= 1 && D >= 8 && I >= 8 && bytes != nullptr, MB_ERR_SHAPE,
+               "mb_moe_ffn_workspace_bytes: bad shape");
+  size_t off[4];
+  *bytes = static_cast<int64_t>(moe_ffn_ws_layout(T, k, E, D, I, off));
+  return MB_OK;
+}
+
+extern "C" int mb_moe_ffn(const void* x, const int32_t* idx, const float* weights, const void* Wgu, const void* Wd,
+                          const void* shared, const void* residual, void* y, void* workspace, int64_t workspace_bytes,
+                          int T, int k, int E, int e_begin, int n_experts_total, int D, int I, void* stream_) {
+  MB_CHECK_ARG(mb_device_ok(), MB_ERR_ARCH, "mb_moe_ffn: no sm_100 device");
+  MB_CHECK_ARG(T >= 0 && k >= 1 && E >= 1 && n_experts_total >= E && D % 8 == 0 && I % 8 == 0, MB_ERR_SHAPE,
+               "mb_moe_ffn: bad shape (T=%d k=%d E=%d D=%d I=%d)", T, k, E, D, I);
+  if (T == 0) return MB_OK;
+  size_t off[4];
+  const size_t need = moe_ffn_ws_layout(T, k, E, D, I, off);
+  MB_CHECK_ARG(workspace != nullptr && static_cast<size_t>(workspace_bytes) >= need &&
+                   (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               MB_ERR_SHAPE, "mb_moe_ffn: workspace of %lld bytes, %zu needed (256-byte aligned)",
+               static_cast<long long>(workspace_bytes), need);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  int32_t* offs = reinterpret_cast<int32_t*>(ws + off[0]);
+  int32_t* sorted = reinterpret_cast<int32_t*>(ws + off[1]);
+  void* hid = ws + off[2];
+  void* out_pairs = ws + off[3];
+  const int mean_pairs = (T * k + n_experts_total - 1) / n_experts_total;
+  int rc = mb_moe_sort(idx, offs, sorted, T, k, E, e_begin, stream_);
+  if (rc != MB_OK) return rc;
+  rc = mb_moe_gate_up(x, Wgu, offs, sorted, hid, T, k, E, D, I, mean_pairs, stream_);
+  if (rc != MB_OK) return rc;
+  rc = mb_moe_down(hid, Wd, offs, sorted, out_pairs, T, k, E, D, I, mean_pairs, stream_);
+  if (rc != MB_OK) return rc;
+  // (pairs of experts outside [e_begin, e_begin + E) were never written: only the unsharded call may combine directly)
+  MB_CHECK_ARG(E == n_experts_total && e_begin == 0, MB_ERR_SHAPE,
+               "mb_moe_ffn: expert-parallel slabs combine through mb_ep_combine_push / mb_moe_combine(y_partial)");
+  return mb_moe_combine(out_pairs, weights, shared, residual, y, nullptr, nullptr, T, k, D, stream_);
+}
+
 extern "C" int mb_moe_peer_area_bytes(int G, int Tmax, int D, int64_t* bytes) {
   MB_CHECK_ARG(G >= 1 && Tmax >= 1 && D >= 1 && bytes != nullptr, MB_ERR_SHAPE, "mb_moe_peer_area_bytes: bad shape");
   *bytes = static_cast<int64_t>(PeerArea::slot_floats(G, Tmax, D) * 4 + (static_cast<size_t>(G) + 3) * 4);

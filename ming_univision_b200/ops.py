@@ -624,11 +624,23 @@ def moe_experts(x: torch.Tensor, idx: torch.Tensor, w: torch.Tensor, Wgu: torch.
         xg = gather_rows(x, row_token, max_rows, meta)
         out_pairs = moe_grouped_ffn(xg, Wgu, Wd, tile_expert, meta)
         pr = pair_row.data_ptr()
+    elif not ep:
+        # decode-sized, all experts local: the whole-stage C driver (sort -> gate/up -> down -> combine, one call)
+        import ctypes
+
+        nbytes = ctypes.c_int64(0)
+        _lib.check(lib.mb_moe_ffn_workspace_bytes(T, k, E, D, I, ctypes.byref(nbytes)), "mb_moe_ffn_workspace_bytes")
+        ws = torch.empty((nbytes.value,), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mb_moe_ffn(x.data_ptr(), idx.data_ptr(), w.data_ptr(), Wgu.data_ptr(), Wd.data_ptr(), _ptr(shared),
+                                  _ptr(residual), y.data_ptr(), ws.data_ptr(), ws.numel(), T, k, E, int(e_begin), E, D, I,
+                                  s), "mb_moe_ffn")
+        _lib.count_replay(3)  # (four kernels behind one C call)
+        return y
     else:
         offs = torch.empty((E + 1,), dtype=torch.int32, device=dev)
         sorted_pair = torch.empty((T * k,), dtype=torch.int32, device=dev)
         hid = torch.empty((T * k, I), dtype=BF16, device=dev)
-        out_pairs = (torch.zeros if ep else torch.empty)((T * k, D), dtype=BF16, device=dev)
+        out_pairs = torch.zeros((T * k, D), dtype=BF16, device=dev)
         _lib.check(lib.mb_moe_sort(idx.data_ptr(), offs.data_ptr(), sorted_pair.data_ptr(), T, k, E, int(e_begin), s),
                    "mb_moe_sort")
         # (with ep_group the slabs hold E of E * world experts; the pairs spread over all of them)
