@@ -248,7 +248,7 @@ gemv_bf16_kernel(const GemvParams p) {
               if (p.pro_gamma) x = x * __bfloat162float(gm[i]) + (p.pro_beta ? __bfloat162float(bt[i]) : 0.f);
               o[i] = x * bf16_round(1.f + __bfloat162float(sc[i])) + __bfloat162float(sh[i]);
             } else {
-              o[i] = __bfloat162float(gm[i]) * bf16_round(f[i] * rstd[r]);
+              o[i] = __bfloat162float(gm[i]) * (f[i] * rstd[r]);  // one rounding, as BailingMoeRMSNorm (:131-136)
             }
           }
           uint4 o4;

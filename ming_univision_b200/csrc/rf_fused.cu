@@ -30,9 +30,12 @@ namespace mb {
 
 constexpr int kRfConsumerWarps = 8;
 constexpr int kRfThreads = (kRfConsumerWarps + 1) * 32;  // + 1 producer warp
-constexpr int kRfKC = 1024;                               // K elements per pipeline stage
+#ifndef MB_RF_KC
+#define MB_RF_KC 1024  // (512 / 256 measured: 7.90 / 8.73 ms against 7.98 ms per 6-row sample, profiles/r02_rf_experiments.md)
+#endif
+constexpr int kRfKC = MB_RF_KC;                           // K elements per pipeline stage
 constexpr int kRfStageBytes = 16 * kRfKC * 2;             // a full 16-row tile chunk: 32 KB
-constexpr int kRfStages = 5;
+constexpr int kRfStages = 160 * 1024 / kRfStageBytes;     // ring slots (as many as fit next to the activation rows)
 constexpr int kRfRowGroup = 3;                            // rows handled per register round of the row-wise parts
 constexpr int kRfMaxRows = 6;                             // rows per launch: CFG rows x images generated together
 

@@ -543,9 +543,11 @@ class BailingMoeModel(nn.Module):
         eps = cfg.rms_norm_eps
         im = None if image_mask is None else image_mask.reshape(-1)
         for li, (lp, lyr) in enumerate(zip(pk["layers"], self.layers)):
-            # decode: RMSNorm fused into the staging of the qkv streaming GEMM where it wins — measured on the full-size
-            # edit round: 771.6 -> 737.9 ms with 3 rows, no change with 6 (the rows take three register rounds there)
-            if B * S <= 8 and (FUSED_NORM or (_FUSED_ENV is None and B * S <= 4)):
+            # decode: RMSNorm fused into the staging of the qkv streaming GEMM — measured on the full-size edit round:
+            # 771.6 -> 737.9 ms with 3 rows, no change with 6 (the rows take three register rounds there).  Every
+            # decode-sized input takes the SAME form, so that requests generated together (6 rows) get bit for bit the
+            # result they get alone (3 rows): the fused statistics are reduced in another order than rmsnorm_kernel's
+            if B * S <= 8 and D <= 4096 and (FUSED_NORM or _FUSED_ENV is None):
                 qkv = ops.gemv_norm(h, lp["qkv_w"], lp["qkv_b"], norm="rms", gamma=lp["ln1"], eps=eps)
             else:
                 qkv = _dense(ops.rmsnorm(h, lp["ln1"], eps), lp["qkv_w"], lp["qkv_b"])
