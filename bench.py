@@ -598,7 +598,7 @@ def run_ours(args, world, rank, local):
             "config": {"workload": WORKLOAD, "tokens_per_step": tokens_all, "encoded_tokens_per_round": N_ENC,
                        "generated_tokens_per_round": N_GEN, "cfg_rows": CFG_ROWS, "rounds_per_step": world * NI,
                        "rounds_generated_together_per_gpu": NI,
-                       "parallelism": (f"dp{world} x ep{world}: one edit round per GPU, routed experts sharded "
+                       "parallelism": (f"dp{world} x ep{world}: every GPU generates its own {NI} edit round(s), routed experts sharded "
                                        f"{64 // world} per GPU, dispatch / combine through NVLink peer memory in-kernel "
                                        "(no NCCL on the data path)") if world > 1 else "1 GPU, all 64 experts resident",
                        "l2_policy": "3 distinct rounds cycled; the 38 GB of weights streamed per AR step exceed the 126 MB L2",

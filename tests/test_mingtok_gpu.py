@@ -44,7 +44,7 @@ def full(cuda_device):
     return cfg, sd, _build(cfg, sd, cuda_device)
 
 
-@pytest.mark.parametrize("size,batch", [(128, 2), (64, 3), (96, 1)])
+@pytest.mark.parametrize("size,batch", [(128, 2), (64, 3), (96, 1), (256, 1)])  # 256: the position table is UPSAMPLED
 def test_tiny_stagewise_vs_oracle(tiny, cuda_device, size, batch):
     cfg, sd, model = tiny
     img = synthetic.synthetic_images(batch, size, seed=1234)
@@ -63,7 +63,7 @@ def test_tiny_stagewise_vs_oracle(tiny, cuda_device, size, batch):
     # forward_enc_dec is the composition (modeling_mingtok.py:150-153)
     recon2 = model.forward_enc_dec(img.to(cuda_device))
     assert torch.equal(recon2.float(), recon.to(torch.bfloat16).float())
-    if size in (128, 64):  # committed outputs of the unmodified reference
+    if size in (128, 64, 256):  # committed outputs of the unmodified reference
         g = np.load(os.path.join(GOLD, f"mingtok_tiny_{size}.npz"))
         assert rel_l2(recon, torch.from_numpy(g["recon"])) < 3e-2
         assert rel_l2(out["x_norm_patchtokens"], torch.from_numpy(g["feats"])) < 2e-2
@@ -117,6 +117,32 @@ def test_full_size_recon_parity(full, cuda_device):
     for key, got in (("latent", out1["latent"]), ("feats", out1["x_norm_patchtokens"]), ("recon", rec1)):
         sel = got.float().cpu().flatten()[torch.from_numpy(g[key + "_idx"])]
         assert rel_l2(sel, torch.from_numpy(g[key + "_val"])) < 3e-2, key
+
+
+def test_full_size_understanding_1024(full, cuda_device):
+    """BASELINE configs[2] image path: the full-size encoder + causal semantic decoder at 1 x 3 x 1024 x 1024 — 32 x 32
+    patches + cls = 1025 tokens on a position table trained for 16 x 16 (bicubic upsampling, vision_transformer.py:183-215)
+    — against strided samples of the UNMODIFIED reference's run (tests/golden/make_golden_upsample.py), and the
+    `extract_image_feature` shapes the LLM prefill consumes (modeling_bailingmm.py:131-138)."""
+    cfg, sd, model = full
+    g = np.load(os.path.join(GOLD, "mingtok_full_1024.npz"))
+    img = synthetic.synthetic_images(1, 1024, seed=int(g["img_seed"])).to(cuda_device)
+    out = model.forward(img)
+    torch.cuda.synchronize()
+    assert tuple(out["latent"].shape) == (1, 1025, 32) and tuple(out["x_norm_patchtokens"].shape) == (1, 1024, 1024)
+    errs = {}
+    for key, got in (("latent", out["latent"]), ("feats", out["x_norm_patchtokens"])):
+        assert tuple(got.shape) == tuple(g[key + "_shape"])
+        flat = got.float().cpu().flatten()
+        sel = flat[torch.from_numpy(g[key + "_idx"])]
+        errs[key] = rel_l2(sel, torch.from_numpy(g[key + "_val"]))
+        mean, std, amax = g[key + "_stats"]
+        assert abs(flat.std().item() - std) < 2e-2 * std
+    print(f"1024 x 1024 understanding path vs the reference: latent {errs['latent']:.3e} feats {errs['feats']:.3e}")
+    assert errs["latent"] < 3e-2 and errs["feats"] < 3e-2, errs
+    # a batch of two at this size reproduces the single image (independent units)
+    two = model.forward(torch.cat((img, img.flip(-1))))
+    assert torch.equal(two["x_norm_patchtokens"][0:1], out["x_norm_patchtokens"])
 
 
 def test_full_size_batch_invariance(full, cuda_device):

@@ -63,6 +63,38 @@ def test_full_size_mingtok_matches_reference_samples():
         assert abs(flat.std().item() - std) < 1e-3 * std + 1e-4
 
 
+def test_upsampled_position_table_matches_reference():
+    """Inputs LARGER than the native resolution (the understanding path: 1024 x 1024 on a 16 x 16 table,
+    vision_transformer.py:183-215): the tiny model at 256 px (4 x 4 -> 8 x 8), full tensors, and the full-size encoder +
+    semantic decoder at 1 x 3 x 1024 x 1024 (S = 1025), strided samples (tests/golden/make_golden_upsample.py)."""
+    g = _load("mingtok_tiny_256.npz")
+    cfg = synthetic.MINGTOK_TINY_CONFIG
+    sd = synthetic.mingtok_state_dict(cfg, int(g["seed"]))
+    img = synthetic.synthetic_images(1, 256, seed=int(g["img_seed"]))
+    with torch.no_grad():
+        out = O.mingtok_forward(sd, img, cfg)
+        recon = O.pixel_decoder_forward(sd, out["x_norm_patchtokens"], cfg["semantic_decoder"], cfg["pixel_decoder"])
+    for key, got in (("latent", out["latent"]), ("feats", out["x_norm_patchtokens"]), ("recon", recon)):
+        ref = torch.from_numpy(g[key])
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5), f"{key}: max diff {(got - ref).abs().max()}"
+    g = _load("mingtok_full_1024.npz")
+    cfg = synthetic.MINGTOK_CONFIG
+    sd = synthetic.mingtok_state_dict(cfg, int(g["seed"]))
+    img = synthetic.synthetic_images(1, 1024, seed=int(g["img_seed"]))
+    with torch.no_grad():
+        out = O.mingtok_forward(sd, img, cfg)
+    for key, got in (("latent", out["latent"]), ("feats", out["x_norm_patchtokens"])):
+        assert tuple(got.shape) == tuple(g[key + "_shape"])
+        flat = got.flatten()
+        ref = torch.from_numpy(g[key + "_val"])
+        sel = flat[torch.from_numpy(g[key + "_idx"])]
+        assert torch.allclose(sel, ref, atol=2e-3, rtol=1e-3), f"{key}: max diff {(sel - ref).abs().max()}"
+        mean, std, amax = g[key + "_stats"]
+        assert abs(flat.mean().item() - mean) < 1e-3 + 1e-3 * abs(mean)
+        assert abs(flat.std().item() - std) < 1e-3 * std + 1e-4
+
+
 def test_param_count_matches_survey():
     """697.7 M parameters."""
     shapes = synthetic.mingtok_param_shapes(synthetic.MINGTOK_CONFIG)
