@@ -28,12 +28,23 @@ from .modeling_bailing_moe import BailingMoeConfig
 from .modeling_bailingmm import MingUniVisionForConditionalGeneration
 
 
-def load_checkpoint(model_dir: str, device="cuda") -> MingUniVisionForConditionalGeneration:
+_LOAD_CHUNK_BYTES = 2 << 30  # staging memory of load_checkpoint: tensors are copied into the model in chunks of this size
+
+
+def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
+                    ep_size: int = 1) -> MingUniVisionForConditionalGeneration:
     """Builds the wrapper from an HF-layout checkpoint directory: `config.json` with `llm_config`,
     `vishead_diffloss_config` (modeling_bailingmm.py:93-129) and the MingTok config either inline (`mingtok_config`) or
     in `models/MingTok-Vision/config.json` (the reference's hard-wired relative path, :102); weights from every
-    `*.safetensors` shard (reference key schema)."""
-    from safetensors.torch import load_file
+    `*.safetensors` shard (reference key schema).
+
+    Direct safetensors -> kernel layout: the module tree is built on the meta device with bf16 storage
+    (no HF `from_pretrained`, no fp32 copy, no weight init), the tensors are read straight from the
+    memory-mapped shards (`safe_open`, 2 GiB of staging at a time) and copied into place — the routed experts directly into the two contiguous slabs
+    per layer that the expert kernels stream, so they are never re-packed.  With `ep_size` > 1 (expert parallelism) only
+    this rank's 64 / ep_size routed experts are allocated AND read: the other ranks' expert tensors are skipped without
+    touching their bytes (follow with `model.model.model.set_expert_parallel(...)`)."""
+    from safetensors import safe_open
 
     with open(os.path.join(model_dir, "config.json")) as f:
         cfg = json.load(f)
@@ -56,26 +67,48 @@ def load_checkpoint(model_dir: str, device="cuda") -> MingUniVisionForConditiona
         warnings.warn("config rope_scaling '3D' -> None: the generation path uses 2-D position ids and the 1-D legacy "
                       "rotary embedding (pass 3-D position ids to forward_tokens for the M-RoPE variant)")
     llm_cfg["rope_scaling"] = None
-    # meta-device construction + bf16 storage (routed experts straight in their kernel slabs): never an fp32 copy of the
-    # 16.8 B parameters, never per-expert tensors next to a stacked copy
+    if not (ep_size >= 1 and 0 <= ep_rank < ep_size):
+        raise ValueError(f"ep_rank {ep_rank} / ep_size {ep_size}")
     model = MingUniVisionForConditionalGeneration.on_device(BailingMoeConfig(**llm_cfg), MingTokConfig(**tok_cfg),
-                                                            cfg["vishead_diffloss_config"], device)
-    expected = {k for k, v in model.state_dict().items() if not v.is_meta}
+                                                            cfg["vishead_diffloss_config"], device, ep_rank=ep_rank,
+                                                            ep_size=ep_size)
+    state = model.state_dict()
+    expected = {k for k, v in state.items() if not v.is_meta}
+    elsewhere = {k for k, v in state.items() if v.is_meta}  # routed experts owned by other ranks
+    del state
     loaded = set()
     shards = [(s, "") for s in sorted(glob.glob(os.path.join(model_dir, "*.safetensors")))]
     tok_dir = os.path.join(model_dir, "models", "MingTok-Vision")
     shards += [(s, "vision.") for s in sorted(glob.glob(os.path.join(tok_dir, "*.safetensors")))]
     unexpected = []
-    for shard, prefix in shards:  # shard by shard: the host / device never holds more than one shard beside the model
-        part = {prefix + k: v for k, v in load_file(shard, device=str(device)).items()}
-        # only the three sub-trees of the continuous-visual-token path (audio encoder / talker weights of an omni
-        # checkpoint are ignored); the reference-only rotary buffers are derived from rope_theta here
-        part = {k: v for k, v in part.items()
-                if k.split(".")[0] in ("model", "vision", "linear_proj") and not k.endswith("rotary_emb.inv_freq")}
-        unexpected += [k for k in part if k not in expected]
-        model.load_state_dict({k: v for k, v in part.items() if k in expected}, strict=False)
-        loaded.update(k for k in part if k in expected)
-        del part
+    part, part_bytes = {}, 0
+
+    def flush():  # (one load_state_dict walks the whole module tree: batch the tensors, bounded staging memory)
+        nonlocal part, part_bytes
+        if part:
+            model.load_state_dict(part, strict=False)
+            loaded.update(part)
+        part, part_bytes = {}, 0
+
+    for shard, prefix in shards:
+        with safe_open(shard, framework="pt", device=str(device)) as f:
+            for key in f.keys():
+                k = prefix + key
+                # only the three sub-trees of the continuous-visual-token path (audio encoder / talker weights of an
+                # omni checkpoint are ignored); the reference-only rotary buffers are derived from rope_theta here
+                if k.split(".")[0] not in ("model", "vision", "linear_proj") or k.endswith("rotary_emb.inv_freq"):
+                    continue
+                if k in elsewhere:
+                    continue
+                if k not in expected:
+                    unexpected.append(k)
+                    continue
+                t = f.get_tensor(key)
+                part[k] = t
+                part_bytes += t.numel() * t.element_size()
+                if part_bytes >= _LOAD_CHUNK_BYTES:
+                    flush()
+            flush()
     missing = sorted(expected - loaded)
     if missing or unexpected:
         raise RuntimeError(f"checkpoint does not match the model: missing {missing[:5]}, unexpected {unexpected[:5]}")

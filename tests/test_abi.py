@@ -185,3 +185,42 @@ def test_load_checkpoint_hf_layout(tmp_path):
         assert torch.equal(sd[k].float(), v.to(torch.bfloat16).float()), k
     assert torch.equal(sd["vision.sem_to_pix.weight"].float(),
                        synthetic.mingtok_state_dict(tok, 0)["sem_to_pix.weight"].to(torch.bfloat16).float())
+
+
+def test_load_checkpoint_expert_parallel_shard(tmp_path, monkeypatch):
+    """load_checkpoint(ep_rank, ep_size): a rank allocates and READS only its own routed experts (direct
+    safetensors -> EP-sharded slabs); everything else is replicated; the staging chunks are flushed as they fill."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from ming_univision_b200 import mingunivisioninfer as MI
+
+    cfg, vh, tok = synthetic.LLM_TINY_CONFIG, synthetic.VISHEAD_TINY_CONFIG, synthetic.MINGTOK_TINY_CONFIG
+    llm_sd = synthetic.llm_state_dict(cfg, vh, tok["semantic_decoder"]["embed_dim"], 0)
+    top = {(k if k.startswith("linear_proj.") else "model." + k): v.contiguous() for k, v in llm_sd.items()}
+    save_file(top, str(tmp_path / "model.safetensors"))
+    (tmp_path / "models" / "MingTok-Vision").mkdir(parents=True)
+    save_file({k: v.contiguous() for k, v in synthetic.mingtok_state_dict(tok, 0).items()},
+              str(tmp_path / "models" / "MingTok-Vision" / "model.safetensors"))
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump({"llm_config": cfg, "vishead_diffloss_config": vh, "mingtok_config": tok}, f)
+    monkeypatch.setattr(MI, "_LOAD_CHUNK_BYTES", 64 << 10)  # many flushes on the tiny checkpoint
+    E = cfg["num_experts"]
+    world = 2
+    seen = set()
+    for rank in range(world):
+        m = MI.load_checkpoint(str(tmp_path), device="cpu", ep_rank=rank, ep_size=world)
+        sd = m.state_dict()
+        local = range(rank * E // world, (rank + 1) * E // world)
+        for k, v in top.items():
+            if ".mlp.experts." in k:
+                e = int(k.split(".mlp.experts.")[1].split(".")[0])
+                if e not in local:
+                    assert sd[k].is_meta, k            # other ranks' experts: never allocated, never read
+                    continue
+                seen.add(k)
+            assert not sd[k].is_meta and torch.equal(sd[k].float(), v.to(torch.bfloat16).float()), k
+    assert seen == {k for k in top if ".mlp.experts." in k}  # the ranks together hold every routed expert exactly once
+    with pytest.raises(ValueError):
+        MI.load_checkpoint(str(tmp_path), device="cpu", ep_rank=2, ep_size=2)
