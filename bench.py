@@ -20,9 +20,11 @@ tokens alone are reported next to it (`generated_tokens_per_s`).
   value     tokens/s with the step's inputs (normalised bf16 image, token ids) resident in HBM; CUDA-event timed
   e2e       the same through the public API from HOST buffers: pinned u8 image + ids host->device, on-device
             normalisation, the round, on-device u8 conversion, pinned u8 image device->host — all inside the timed region
-  roofline  bound "hbm": the weight-streaming kernel (mb::gemv_bf16_kernel: RF head, LLM dense layers, semantic decoder):
-            algorithmic bytes (N*K*2 per launch) of all its launches of a token step / their CUDA-event duration when
-            re-issued back to back, against the measured copy bandwidth in MEASURED_PEAKS.json
+  roofline  bound "hbm": the dominant kernel, mb::rf_sample_fused_kernel (the whole RF sampler of a token step as one
+            persistent weight-streaming launch): algorithmic bytes per launch (the bf16 weights it must stream: steps x
+            depth x (2H*W + W*H) x 2 = 28.99 GB) / the median CUDA-event duration of its launches on the launching
+            stream, against the measured copy bandwidth in MEASURED_PEAKS.json; `traffic` from the committed ncu capture;
+            `second_kernel`: the per-layer streaming GEMM (mb::gemv_bf16_kernel: LLM dense layers, semantic decoder, heads)
   stages    secondary: MingTok enc+dec batch=64 256x256 (BASELINE configs[1], last round's headline) with its tensor-core
             roofline, and the per-stage split of the round
   cpu_baseline / --impl reference: the CPU restatement of the reference (oracle/, kind "port": the reference is pure

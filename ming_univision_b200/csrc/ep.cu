@@ -31,8 +31,8 @@
 //
 // A peer that never arrives (crashed / diverged process) must not hang the GPU: the waits are bounded by a wall-clock
 // budget (%globaltimer; MB_EP_TIMEOUT_MS, default 20 s).  On expiry the kernel records an error code in the area's
-// control block and carries on (its output is garbage); the host reads the code with mb_ep_error() after the next
-// synchronisation and raises — the CUDA context survives, unlike with __trap().
+// control block and carries on (its output is garbage); the host reads the code from the control block (ep.PeerDispatch.check,
+// called once per request by the model's entry points) and raises — the CUDA context survives, unlike with __trap().
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>

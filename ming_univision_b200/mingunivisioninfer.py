@@ -4,10 +4,11 @@
                                                                   output_image_prefix="output", for_edit=False) -> str
     .reset_inner_state()
 
-The chat template, image fetching / resizing and tokenisation stay the reference's own CPU code
-(`processing_bailingmm.BailingMMProcessor`, `tokenization_bailing`; SURVEY.md §2.1 marks them API-only): they are
-imported from the reference checkout given by `reference_dir` (default: the directory holding the tokenizer files, as
-the reference's "./mingunivision").  Everything behind `self.model.generate(...)` is the B200-native path of this repo.
+The chat template, image fetching, placeholder expansion, tokenisation and the CFG masks are this package's
+`processing_bailingmm.BailingMMProcessor` (exact mirror of the reference's host code, tests/test_processing_cpu.py); only
+the tokenizer DATA (`tokenizer.json`, `tokenizer_config.json`, `preprocessor_config.json`) is read from `reference_dir`
+(default: the reference's "./mingunivision", mingunivisioninfer.py:43-44) or, if it holds them, from the checkpoint
+directory.  Everything behind `self.model.generate(...)` is the B200-native path of this repo.
 `dtype="int4" / "int8"` (bitsandbytes / quanto) are out of scope and raise.
 
 Tests inject `model`, `processor` and `tokenizer` directly; no pretrained checkpoint exists offline, so the checkpoint
@@ -19,7 +20,6 @@ from __future__ import annotations
 import glob
 import json
 import os
-import sys
 
 import torch
 
@@ -123,25 +123,31 @@ class MingUniVisionInfer:
         self.model_name_or_path = model_name_or_path
         self.dtype = dtype
         if processor is None or tokenizer is None:
-            tokenizer, processor = self._load_reference_processor(reference_dir)
+            tokenizer, processor = self._load_processor(model_name_or_path, reference_dir, tokenizer, processor)
         self.tokenizer, self.processor = tokenizer, processor
         self.model = model if model is not None else load_checkpoint(model_name_or_path)
         self.model.tokenizer = self.tokenizer
         self.model.model.tokenizer = self.tokenizer
 
     @staticmethod
-    def _load_reference_processor(reference_dir: str):
-        """The reference's own CPU pre/post-processing (mingunivisioninfer.py:43-44), imported from its checkout."""
-        ref = os.path.abspath(reference_dir)
-        if not os.path.isdir(ref):
-            raise RuntimeError(f"{ref}: the reference's processor / tokenizer files are needed for the chat template "
-                               "(pass processor= and tokenizer= to inject your own)")
-        if ref not in sys.path:
-            sys.path.insert(0, ref)
-        from transformers import AutoProcessor, AutoTokenizer
+    def _load_processor(model_dir, reference_dir: str, tokenizer=None, processor=None):
+        """mingunivisioninfer.py:43-44 (`AutoTokenizer` / `AutoProcessor.from_pretrained("./mingunivision")`): the tokenizer
+        data files from the checkpoint directory if it has them, else from `reference_dir`; the processor is this
+        package's mirror (the reference's own classes target transformers 4.52 and do not construct under 5.x)."""
+        from .processing_bailingmm import BailingMMProcessor, load_tokenizer
 
-        return (AutoTokenizer.from_pretrained(ref, trust_remote_code=True),
-                AutoProcessor.from_pretrained(ref, trust_remote_code=True))
+        data_dir = next((d for d in (str(model_dir), os.path.abspath(reference_dir))
+                         if os.path.isfile(os.path.join(d, "tokenizer.json"))), None)
+        if tokenizer is None:
+            if data_dir is None:
+                raise RuntimeError(f"tokenizer.json found neither in {model_dir} nor in {os.path.abspath(reference_dir)} "
+                                   "(pass processor= and tokenizer= to inject your own)")
+            tokenizer = load_tokenizer(data_dir)
+        if processor is None:
+            processor = (BailingMMProcessor.from_pretrained(data_dir) if data_dir is not None
+                         else BailingMMProcessor(tokenizer=tokenizer))
+            processor.tokenizer = tokenizer
+        return tokenizer, processor
 
     @property
     def device(self):

@@ -500,6 +500,14 @@ class BailingMoeModel(nn.Module):
         self.ep_tokens_replicated = mode != "dispatch"
         self.ep_graphable = size == 1 or mode in ("peer", "dispatch")
 
+    def check_expert_parallel(self) -> None:
+        """Raises if a bounded wait of the peer-memory exchange expired since the areas were created (a peer crashed or
+        diverged: csrc/ep.cu records an error code instead of hanging or trapping).  Reads 8 bytes of the local exchange
+        area, i.e. synchronises the stream: called once per request by the entry points, not per layer."""
+        peer = getattr(self, "ep_peer", None)
+        if peer is not None and hasattr(peer, "check"):
+            peer.check()
+
     def embed(self, input_ids: torch.Tensor) -> torch.Tensor:
         """word_embeddings lookup (row gather of the packed bf16 table; pure indexing, no arithmetic)."""
         return self._pack()["emb"][input_ids]

@@ -235,6 +235,7 @@ class MingUniVisionForConditionalGeneration(nn.Module):
         else:
             raise ValueError("PAST_MODE must be KEEP or DROP")
         llm.reset_image_gen_status()
+        llm.model.check_expert_parallel()
         return torch.cat((input_ids, torch.tensor([new_ids], dtype=input_ids.dtype, device=dev)), dim=1)
 
     @staticmethod
@@ -281,6 +282,7 @@ class MingUniVisionForConditionalGeneration(nn.Module):
             sem_to_pix_func=self.vision.forward_pixel_decoder, image_gen_temperature=image_gen_temperature,
             noises=noises)
         self.past_key_values, self.past_attention_mask = cache, fmask[0:1]
+        llm.model.check_expert_parallel()
         return (img[0:1] if G == 1 else img), fmask
 
     @torch.no_grad()
