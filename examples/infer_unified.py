@@ -3,10 +3,13 @@ demo (mingunivision/test_infer_unified.py), on the B200-native path.
 
     python examples/infer_unified.py --model <Ming-UniVision-16B-A3B checkpoint dir> --reference-dir <.../mingunivision>
 
-`--reference-dir` is the reference checkout's `mingunivision/` directory: its tokenizer files, chat template and
-`BailingMMProcessor` are host-side string code and are used as they are.  Needs the real checkpoint —
-there is none offline, so this script is exercised in the tests only through injected tiny models
-(tests/test_llm_gpu.py::test_infer_facade_calls_like_the_reference)."""
+`--reference-dir` is only a place to find the tokenizer DATA (`tokenizer.json`, `tokenizer_config.json`,
+`preprocessor_config.json`) when the checkpoint directory does not hold it — the reference keeps it in its
+`mingunivision/` directory.  Chat template, image fetching, token expansion and the CFG masks are this package's own
+`processing_bailingmm.BailingMMProcessor` (exact mirror, tests/test_processing_cpu.py).  Needs the real checkpoint — there
+is none offline, so this flow is exercised in the tests through injected tiny / stubbed models
+(tests/test_llm_gpu.py::test_infer_facade_calls_like_the_reference,
+tests/test_host_logic_cpu.py::test_facade_round_trip_with_the_processor)."""
 import argparse
 import os
 import sys

@@ -248,3 +248,86 @@ def test_flat_module_names_of_the_reference_resolve_to_the_package():
         "print('flat ok')\n" % root)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "flat ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_facade_round_trip_with_the_processor(stubbed, monkeypatch):
+    """MingUniVisionInfer.generate (mingunivisioninfer.py:82-117) end to end on the host: this package's processor (chat
+    template -> image fetch -> transform -> placeholder expansion -> ids + CFG masks) feeding the wrapper's `generate`
+    with the CUDA-backed pieces stubbed.  A text-to-image round, then an in-context EDIT round with an input image: the
+    masks the processor built reach generate_image behind the saved context, the image features land on the
+    `<imagePatch>` positions, and the decoded answer is the text after the prompt."""
+    import numpy as np
+    import torchvision.transforms as T
+    from PIL import Image
+
+    from ming_univision_b200.mingunivisioninfer import MingUniVisionInfer
+    from ming_univision_b200.processing_bailingmm import BailingMMProcessor
+    from test_processing_cpu import byte_tokenizer
+
+    m, llm, log, script, n_tok = stubbed
+    tok = byte_tokenizer()
+    ids_of = lambda s: tok.convert_tokens_to_ids(s)  # noqa: E731
+    cfg = llm.config
+    cfg.image_patch_token, cfg.image_start_token, cfg.pad_token_id = ids_of("<imagePatch>"), ids_of("<image>"), ids_of("<|endoftext|>")
+    half = [0.5, 0.5, 0.5]
+    tf = T.Compose([T.Resize(64), T.CenterCrop(64), T.ToTensor(), T.Normalize(half, half)])
+    proc = BailingMMProcessor(tokenizer=tok, vis_processor=tf, gen_processor=tf)
+    D = cfg.hidden_size
+    seen = {}
+
+    def extract_image_feature(pixel_values, grid_thw=None):
+        seen["pixels"] = (tuple(pixel_values.shape), pixel_values.dtype)
+        return torch.ones((int(grid_thw.prod()), D))
+
+    scattered = {}
+    real_wrap = m.prompt_wrap_vision
+
+    def prompt_wrap_vision(input_ids, emb, feats, image_token_id=None):
+        out, mask = real_wrap(input_ids, emb, feats, image_token_id)
+        scattered["mask"] = mask.clone()
+        return out, mask
+
+    m.extract_image_feature = extract_image_feature
+    m.prompt_wrap_vision = prompt_wrap_vision
+    monkeypatch.delenv("PAST_MODE", raising=False)
+    agent = MingUniVisionInfer("unused", model=m, processor=proc, tokenizer=tok)
+    eos, img_tok = cfg.pad_token_id, cfg.image_start_token
+    # ---- round 1: text -> image
+    script["tokens"] = [img_tok] + tok.encode("done", add_special_tokens=False) + [eos]
+    msg1 = [{"role": "HUMAN", "content": [{"type": "text", "text": "Generate a corgi."}]}]
+    answer = agent.generate(msg1, max_new_tokens=32)
+    assert answer == "done"                                        # special tokens (<image>, <|endoftext|>) are skipped
+    text1 = proc.apply_chat_template(msg1)
+    enc1 = proc(text=[text1])
+    S1 = enc1["input_ids"].shape[1]
+    assert log["prefill"] == [(0, S1)]
+    pos, un, tun = log["image"][0]
+    assert pos == S1
+    assert torch.equal(un.long(), enc1["uncond_attention_mask"]) and torch.equal(tun.long(), enc1["text_uncond_attention_mask"])
+    body = len(tok.encode("<role>HUMAN</role>", add_special_tokens=False))
+    tail = len(tok.encode("<role>ASSISTANT</role>", add_special_tokens=False))
+    assert un[0].tolist() == [1] * body + [0] * (S1 - body - tail) + [1] * tail   # the prompt's body is hidden from the uncond row
+    L1 = m.past_key_values.seq_len
+    assert L1 == S1 + (n_tok + 1) + len(tok.encode("done", add_special_tokens=False)) + 1 - 1
+    # ---- round 2: edit with an input image, behind the saved context
+    img = Image.fromarray(np.random.default_rng(0).integers(0, 256, (80, 120, 3), dtype=np.uint8))
+    msg2 = [{"role": "HUMAN", "content": [{"type": "image", "image": img}, {"type": "text", "text": "add a hat"}]}]
+    script["tokens"] = [img_tok, eos]
+    agent.generate(msg2, max_new_tokens=8, for_edit=True)
+    assert seen["pixels"] == ((1, 3, 64, 64), torch.bfloat16)      # the facade hands bf16 pixels to the model (:104-105)
+    n_patch = (64 // m.vision.patch_size) ** 2
+    side = 64 // m.vision.patch_size
+    text2 = proc._expand_image_tokens([proc.apply_chat_template(msg2)], torch.tensor([[1, side, side]]))[0]
+    enc2 = proc.tokenize([text2])
+    S2 = enc2["input_ids"].shape[1]
+    assert int(scattered["mask"].sum()) == n_patch == text2.count("<imagePatch>")
+    assert log["prefill"][1] == (L1, S2)
+    pos2, un2, tun2 = log["image"][1]
+    assert pos2 == L1 + S2 and un2.shape[1] == L1 + S2
+    # DROP mode: the saved context is visible to the text-uncond row and (except the padded tail) to the uncond row; this
+    # round's masks follow behind it
+    assert torch.equal(un2[:, L1:].long(), enc2["uncond_attention_mask"])
+    assert torch.equal(tun2[:, L1:].long(), enc2["text_uncond_attention_mask"])
+    assert int(tun2[0, L1:].sum()) >= n_patch + 2                  # the edit's input image stays visible without its text
+    agent.reset_inner_state()
+    assert m.past_key_values is None
