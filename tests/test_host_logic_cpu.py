@@ -331,3 +331,48 @@ def test_facade_round_trip_with_the_processor(stubbed, monkeypatch):
     assert int(tun2[0, L1:].sum()) >= n_patch + 2                  # the edit's input image stays visible without its text
     agent.reset_inner_state()
     assert m.past_key_values is None
+
+
+@pytest.mark.parametrize("mode", ["DROP", "KEEP"])
+def test_multi_round_state_matches_the_reference_trace(stubbed, mode, monkeypatch):
+    """SURVEY.md §8a row a23 against the LIVE reference: tests/golden/generate_trace.json holds what the reference's own
+    `MingUniVisionForConditionalGeneration.generate` + `prepare_inputs_for_generation` + `forward` + `generate_image` did
+    over three rounds of a scripted token stream (text, `<image>`, text, eos; an image right after the prompt; a round
+    cut by max_new_tokens), under both PAST_MODEs — driven by the restated HF 4.52.4 greedy loop
+    (oracle/hf_generate_oracle.py, the one part that is not the reference's: parity unpinned for it).  The same script
+    through this package's `generate` (compute stubbed) must give the same sequences, cache lengths, saved masks, the
+    same prefill extents, and hand generate_image the same cache length and masks."""
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generate_trace.json")) as f:
+        gold = json.load(f)
+    m, llm, log, script, n_tok = stubbed
+    assert n_tok == gold["n_image_tokens"] and llm.config.image_start_token == gold["image_start_token"]
+    monkeypatch.setenv("PAST_MODE", mode)
+    t = lambda v: torch.tensor([v], dtype=torch.int32)  # noqa: E731
+    for i, r in enumerate(gold[mode]):
+        script["tokens"] = list(r["script"])
+        n_pre, n_img = len(log["prefill"]), len(log["image"])
+        seq = m.generate(torch.tensor([r["prompt"]]), uncond_attention_mask=t(r["uncond"]),
+                         text_uncond_attention_mask=t(r["text_uncond"]), max_new_tokens=r["max_new_tokens"],
+                         eos_token_id=gold["eos"])
+        assert seq[0].tolist() == r["sequence"], (mode, i)
+        assert m.past_key_values.seq_len == r["cache_len"], (mode, i)
+        assert m.past_attention_mask[0].tolist() == r["past_attention_mask"]
+        assert m.past_uncond_attention_mask[0].tolist() == r["past_uncond_attention_mask"]
+        assert m.past_text_uncond_attention_mask[0].tolist() == r["past_text_uncond_attention_mask"]
+        # the round's prompt: ONE forward call of the reference behind the cached context, consecutive positions
+        first = r["forward_calls"][0]
+        assert log["prefill"][n_pre:] == [(first["cache_len"], first["fed"])]
+        assert first["position_ids"] == list(range(first["cache_len"], first["cache_len"] + first["fed"]))
+        # every later call of the reference feeds ONE token at position == cache length (what greedy_decode does),
+        # except the `<image>` start token, which runs generate_image (+ n_tok + 1 cache positions)
+        for c in r["forward_calls"][1:]:
+            assert c["fed"] == 1 and c["position_ids"] == [c["cache_len"]] and c["attention_mask_len"] == c["cache_len"] + 1
+        images = r["generate_image_calls"]
+        assert len(log["image"]) - n_img == len(images)
+        for (pos, un, tun), g in zip(log["image"][n_img:], images):
+            assert pos == g["cache_len"] and g["attention_mask"] == [1] * (g["cache_len"] + 1)
+            assert un[0].tolist() == g["uncond"] and tun[0].tolist() == g["text_uncond"]
+        assert r["cache_rows"] == 1  # the CFG rows are trimmed again after every image (:1954-1962)
+    m.reset_inner_state()
