@@ -376,3 +376,56 @@ def test_multi_round_state_matches_the_reference_trace(stubbed, mode, monkeypatc
             assert un[0].tolist() == g["uncond"] and tun[0].tolist() == g["text_uncond"]
         assert r["cache_rows"] == 1  # the CFG rows are trimmed again after every image (:1954-1962)
     m.reset_inner_state()
+
+
+def test_kv_cache_row_bookkeeping_and_growth():
+    """BailingKVCache (the static stand-in for the reference's DynamicCache): CFG-row replication / trim
+    (modeling_bailing_moe.py:1891-1902, :1954-1962), their batched forms for G requests generated together, and growth by
+    re-allocation (the reference's cache grows with every torch.cat) — pure tensor bookkeeping, checked on CPU tensors."""
+    from ming_univision_b200.modeling_bailing_moe import BailingKVCache
+
+    cfg = BailingMoeConfig(**synthetic.LLM_TINY_CONFIG)
+    L, Hkv, hd = cfg.num_hidden_layers, cfg.num_key_value_heads, cfg.head_dim
+    c = BailingKVCache(cfg, max_batch=6, max_len=8, device="cpu")
+    assert len(c.k) == L and tuple(c.k[0].shape) == (6, Hkv, 8, hd) and c.get_seq_length() == 0
+    g = torch.Generator().manual_seed(0)
+    T = 5
+    ref_k = [torch.randn((2, Hkv, T, hd), generator=g).to(torch.bfloat16) for _ in range(L)]
+    ref_v = [torch.randn((2, Hkv, T, hd), generator=g).to(torch.bfloat16) for _ in range(L)]
+    for li in range(L):  # two requests prefilled together: rows 0 and 1
+        c.k[li][:2, :, :T] = ref_k[li]
+        c.v[li][:2, :, :T] = ref_v[li]
+    c.seq_len, c.batch = T, 2
+    # G = 2 requests x B = 3 CFG rows: rows g*3 + b start as copies of request g's cond row
+    c.expand_groups(2, 3)
+    assert c.batch == 6
+    for li in range(L):
+        for gi in range(2):
+            for b in range(3):
+                assert torch.equal(c.k[li][gi * 3 + b, :, :T], ref_k[li][gi]) and torch.equal(c.v[li][gi * 3 + b, :, :T], ref_v[li][gi])
+    # the generation appends to every row; trimming keeps each request's cond row (row g*3 -> row g)
+    for li in range(L):
+        c.k[li][:, :, T] = torch.arange(6, dtype=torch.bfloat16).view(6, 1, 1)
+    c.seq_len = T + 1
+    c.trim_groups(2, 3)
+    assert c.batch == 2
+    for li in range(L):
+        assert torch.equal(c.k[li][0, :, :T], ref_k[li][0]) and torch.equal(c.k[li][1, :, :T], ref_k[li][1])
+        assert float(c.k[li][0, 0, T, 0]) == 0.0 and float(c.k[li][1, 0, T, 0]) == 3.0   # rows 0 and 3 of the six
+    with pytest.raises(ValueError):
+        c.expand_groups(3, 3)
+    # single request: repeat_rows / trim_rows
+    c.batch = 1
+    c.repeat_rows(3)
+    assert c.batch == 3 and all(torch.equal(c.k[li][2, :, :T + 1], c.k[li][0, :, :T + 1]) for li in range(L))
+    c.trim_rows()
+    assert c.batch == 1
+    with pytest.raises(ValueError):
+        c.repeat_rows(7)
+    # growth keeps the content, at least doubles, and changes max_len (the graph workspaces are keyed on it)
+    before = [k[:, :, :c.seq_len].clone() for k in c.k]
+    c.grow(9)
+    assert c.max_len == 16 and all(tuple(k.shape) == (6, Hkv, 16, hd) for k in c.k + c.v)
+    assert all(torch.equal(k[:, :, :c.seq_len], b) for k, b in zip(c.k, before))
+    c.grow(100)
+    assert c.max_len == 100 and all(torch.equal(k[:, :, :c.seq_len], b) for k, b in zip(c.k, before))
