@@ -105,6 +105,23 @@ class MingUniVisionForConditionalGeneration(nn.Module):
                     mod._buffers[name] = torch.zeros(b.shape, dtype=b.dtype, device=device)
         return m
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, *args, device_map="cuda", torch_dtype=None,
+                        quantization_config=None, ep_rank: int = 0, ep_size: int = 1, **kwargs):
+        """The call the reference's facade makes (mingunivisioninfer.py:72-78: `from_pretrained(path,
+        torch_dtype=torch.bfloat16, attn_implementation="flash_attention_2", trust_remote_code=True, device_map="cuda")`)
+        on a LOCAL checkpoint directory: `mingunivisioninfer.load_checkpoint` (meta-device construction, tensors straight
+        from the safetensors shards into the kernel slabs; `ep_rank` / `ep_size`: only this rank's routed experts).
+        `attn_implementation` / `trust_remote_code` are accepted and ignored; quantised loading is refused."""
+        from .mingunivisioninfer import load_checkpoint
+
+        if quantization_config is not None:
+            raise NotImplementedError("int4 / int8 loading (bitsandbytes / quanto) is outside the B200-native path")
+        if torch_dtype not in (None, BF16, "bfloat16", "auto"):
+            raise NotImplementedError(f"torch_dtype {torch_dtype!r}: the path computes in bf16")
+        device = device_map if isinstance(device_map, (str, torch.device)) and device_map != "auto" else "cuda"
+        return load_checkpoint(str(pretrained_model_name_or_path), device=device, ep_rank=ep_rank, ep_size=ep_size)
+
     def reset_inner_state(self):
         """modeling_bailingmm.py:303-308."""
         self.past_key_values = None

@@ -179,6 +179,14 @@ def test_load_checkpoint_hf_layout(tmp_path):
     m = load_checkpoint(str(tmp_path), device="cpu")
     sd = m.state_dict()
     assert sd["model.lm_head.weight"].dtype == torch.bfloat16
+    # the call the reference's facade makes (mingunivisioninfer.py:72-78) lands in the same loader
+    from ming_univision_b200.modeling_bailingmm import MingUniVisionForConditionalGeneration as Wrapper
+
+    m2 = Wrapper.from_pretrained(str(tmp_path), torch_dtype=torch.bfloat16, attn_implementation="flash_attention_2",
+                                 trust_remote_code=True, device_map="cpu")
+    assert all(torch.equal(v, m2.state_dict()[k]) for k, v in sd.items())
+    with pytest.raises(NotImplementedError):
+        Wrapper.from_pretrained(str(tmp_path), quantization_config=object(), device_map="cpu")
     for k, v in top.items():
         if k.endswith("inv_freq"):
             continue
