@@ -584,7 +584,7 @@ def run_ours(args, world, rank, local):
     # ---- CPU baseline (oracle port, bounded sample, extrapolated) + parity of that sample against the CUDA path
     del feats64
     cpu, parity = None, None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # rank 0 at N = 1 only (the contract); N > 1 lines carry null
         ref = CpuReference()
         t = ref.sample_step(keep=True)
         ex = ref.extrapolate({k: v for k, v in t.items() if not k.startswith("_")})
