@@ -15,13 +15,14 @@ __version__ = "0.1.0"
 # test_infer_unified.py: `from mingunivisioninfer import MingUniVisionInfer`; modeling_bailingmm.py:25:
 # `from mingtok.modeling_mingtok import MingTok`).  One call makes those unchanged import lines resolve to this package.
 _FLAT_MODULES = ("modeling_bailingmm", "modeling_bailing_moe", "diff_loss_rf_swiglu", "mingunivisioninfer",
-                 "image_processing_bailingmm", "mingtok", "mingtok.modeling_mingtok", "mingtok.utils",
-                 "mingtok.utils.processor")
+                 "image_processing_bailingmm", "processing_bailingmm", "mingtok", "mingtok.modeling_mingtok",
+                 "mingtok.utils", "mingtok.utils.processor")
 
 
 def install_flat_modules(force: bool = False) -> list:
     """Registers this package's modules under the reference's flat module names in `sys.modules` (`modeling_bailingmm`,
-    `modeling_bailing_moe`, `diff_loss_rf_swiglu`, `mingunivisioninfer`, `image_processing_bailingmm`, `mingtok.*`), so a
+    `modeling_bailing_moe`, `diff_loss_rf_swiglu`, `mingunivisioninfer`, `image_processing_bailingmm`,
+    `processing_bailingmm`, `mingtok.*`), so a
     reference script runs on the B200-native path with ONE added line at its top.  Names that are already imported (a
     reference checkout earlier on sys.path) are left alone unless `force`.  Returns the names it registered."""
     import importlib

@@ -244,7 +244,8 @@ def test_flat_module_names_of_the_reference_resolve_to_the_package():
         "from mingtok.utils.processor import CenterCropProcessor\n"
         "from mingunivisioninfer import MingUniVisionInfer\n"
         "from image_processing_bailingmm import BailingMMImageProcessor, smart_resize\n"
-        "assert MingTok.__module__.startswith('ming_univision_b200.') and len(names) == 9, names\n"
+        "from processing_bailingmm import BailingMMProcessor, MingTokUndProcessor, MingTokCenterCropProcessor\n"
+        "assert MingTok.__module__.startswith('ming_univision_b200.') and len(names) == 10, names\n"
         "print('flat ok')\n" % root)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "flat ok" in r.stdout, r.stdout + r.stderr
