@@ -28,6 +28,19 @@ from .modeling_bailing_moe import BailingMoeConfig
 from .modeling_bailingmm import MingUniVisionForConditionalGeneration
 
 
+def resolve_checkpoint_dir(name_or_path: str) -> str:
+    """A local directory is used as it is; anything else is taken for a Hugging Face hub id (the reference passes
+    "inclusionAI/Ming-UniVision-16B-A3B" to `from_pretrained`, README) and fetched / found in the local cache with
+    `huggingface_hub.snapshot_download`."""
+    if os.path.isdir(name_or_path):
+        return name_or_path
+    try:
+        from huggingface_hub import snapshot_download
+    except ImportError as e:  # pragma: no cover
+        raise FileNotFoundError(f"{name_or_path} is not a directory and huggingface_hub is not installed") from e
+    return snapshot_download(name_or_path)
+
+
 _LOAD_CHUNK_BYTES = 2 << 30  # staging memory of load_checkpoint: tensors are copied into the model in chunks of this size
 
 
@@ -46,6 +59,7 @@ def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
     touching their bytes (follow with `model.model.model.set_expert_parallel(...)`)."""
     from safetensors import safe_open
 
+    model_dir = resolve_checkpoint_dir(model_dir)
     with open(os.path.join(model_dir, "config.json")) as f:
         cfg = json.load(f)
     tok_cfg = cfg.get("mingtok_config")
@@ -122,10 +136,11 @@ class MingUniVisionInfer:
             raise NotImplementedError("int4 / int8 loading (bitsandbytes / quanto) is outside the B200-native path")
         self.model_name_or_path = model_name_or_path
         self.dtype = dtype
+        model_dir = str(model_name_or_path) if model is not None else resolve_checkpoint_dir(str(model_name_or_path))
         if processor is None or tokenizer is None:
-            tokenizer, processor = self._load_processor(model_name_or_path, reference_dir, tokenizer, processor)
+            tokenizer, processor = self._load_processor(model_dir, reference_dir, tokenizer, processor)
         self.tokenizer, self.processor = tokenizer, processor
-        self.model = model if model is not None else load_checkpoint(model_name_or_path)
+        self.model = model if model is not None else load_checkpoint(model_dir)
         self.model.tokenizer = self.tokenizer
         self.model.model.tokenizer = self.tokenizer
 
@@ -136,7 +151,7 @@ class MingUniVisionInfer:
         package's mirror (the reference's own classes target transformers 4.52 and do not construct under 5.x)."""
         from .processing_bailingmm import BailingMMProcessor, load_tokenizer
 
-        data_dir = next((d for d in (str(model_dir), os.path.abspath(reference_dir))
+        data_dir = next((d for d in (str(model_dir), os.path.abspath(reference_dir))  # (a hub id is not a directory: skipped)
                          if os.path.isfile(os.path.join(d, "tokenizer.json"))), None)
         if tokenizer is None:
             if data_dir is None:

@@ -151,7 +151,7 @@ def test_llm_state_dict_schema_live():
     assert not res.missing_keys and not res.unexpected_keys
 
 
-def test_load_checkpoint_hf_layout(tmp_path):
+def test_load_checkpoint_hf_layout(tmp_path, monkeypatch):
     """mingunivisioninfer.load_checkpoint: config.json + *.safetensors in the reference's HF layout (LLM + vis_head +
     diffloss + linear_proj shards at the top level, MingTok under models/MingTok-Vision) -> the wrapper module, with the
     reference-only buffers (rotary inv_freq) ignored.  Synthetic tiny checkpoint (no pretrained weights exist offline)."""
@@ -187,6 +187,14 @@ def test_load_checkpoint_hf_layout(tmp_path):
     assert all(torch.equal(v, m2.state_dict()[k]) for k, v in sd.items())
     with pytest.raises(NotImplementedError):
         Wrapper.from_pretrained(str(tmp_path), quantization_config=object(), device_map="cpu")
+    # a hub id instead of a directory goes through huggingface_hub's snapshot (stubbed: there is no network here)
+    import huggingface_hub
+
+    asked = []
+    monkeypatch.setattr(huggingface_hub, "snapshot_download", lambda name, **kw: asked.append(name) or str(tmp_path))
+    m3 = Wrapper.from_pretrained("inclusionAI/Ming-UniVision-16B-A3B", device_map="cpu")
+    assert asked == ["inclusionAI/Ming-UniVision-16B-A3B"] and torch.equal(m3.state_dict()["model.lm_head.weight"],
+                                                                           sd["model.lm_head.weight"])
     for k, v in top.items():
         if k.endswith("inv_freq"):
             continue
