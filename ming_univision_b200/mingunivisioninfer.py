@@ -28,6 +28,13 @@ from .modeling_bailing_moe import BailingMoeConfig
 from .modeling_bailingmm import MingUniVisionForConditionalGeneration
 
 
+def _mingtok_dir(model_dir: str) -> str:
+    """`models/MingTok-Vision` inside the checkpoint directory, else relative to the working directory — where the
+    reference looks (`MingTok.from_pretrained("./models/MingTok-Vision")`, modeling_bailingmm.py:102)."""
+    inside = os.path.join(model_dir, "models", "MingTok-Vision")
+    return inside if os.path.isdir(inside) else os.path.join(".", "models", "MingTok-Vision")
+
+
 def resolve_checkpoint_dir(name_or_path: str) -> str:
     """A local directory is used as it is; anything else is taken for a Hugging Face hub id (the reference passes
     "inclusionAI/Ming-UniVision-16B-A3B" to `from_pretrained`, README) and fetched / found in the local cache with
@@ -64,7 +71,7 @@ def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
         cfg = json.load(f)
     tok_cfg = cfg.get("mingtok_config")
     if tok_cfg is None:
-        with open(os.path.join(model_dir, "models", "MingTok-Vision", "config.json")) as f:
+        with open(os.path.join(_mingtok_dir(model_dir), "config.json")) as f:
             tok_cfg = json.load(f)
     llm_cfg = {k: v for k, v in cfg["llm_config"].items() if k not in ("architectures", "model_type", "torch_dtype",
                                                                        "transformers_version", "auto_map")}
@@ -92,7 +99,7 @@ def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
     del state
     loaded = set()
     shards = [(s, "") for s in sorted(glob.glob(os.path.join(model_dir, "*.safetensors")))]
-    tok_dir = os.path.join(model_dir, "models", "MingTok-Vision")
+    tok_dir = _mingtok_dir(model_dir)
     shards += [(s, "vision.") for s in sorted(glob.glob(os.path.join(tok_dir, "*.safetensors")))]
     unexpected = []
     part, part_bytes = {}, 0
