@@ -48,25 +48,10 @@ def resolve_checkpoint_dir(name_or_path: str) -> str:
     return snapshot_download(name_or_path)
 
 
-_LOAD_CHUNK_BYTES = 2 << 30  # staging memory of load_checkpoint: tensors are copied into the model in chunks of this size
-
-
-def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
-                    ep_size: int = 1) -> MingUniVisionForConditionalGeneration:
-    """Builds the wrapper from an HF-layout checkpoint directory: `config.json` with `llm_config`,
-    `vishead_diffloss_config` (modeling_bailingmm.py:93-129) and the MingTok config either inline (`mingtok_config`) or
-    in `models/MingTok-Vision/config.json` (the reference's hard-wired relative path, :102); weights from every
-    `*.safetensors` shard (reference key schema, SURVEY.md §3.5).
-
-    Direct safetensors -> kernel layout (SURVEY.md §8f.3): the module tree is built on the meta device with bf16 storage
-    (no HF `from_pretrained`, no fp32 copy, no weight init), the tensors are read straight from the
-    memory-mapped shards (`safe_open`, 2 GiB of staging at a time) and copied into place — the routed experts directly into the two contiguous slabs
-    per layer that the expert kernels stream, so they are never re-packed.  With `ep_size` > 1 (expert parallelism) only
-    this rank's 64 / ep_size routed experts are allocated AND read: the other ranks' expert tensors are skipped without
-    touching their bytes (follow with `model.model.model.set_expert_parallel(...)`)."""
-    from safetensors import safe_open
-
-    model_dir = resolve_checkpoint_dir(model_dir)
+def build_from_config(model_dir: str, device="cuda", ep_rank: int = 0,
+                      ep_size: int = 1) -> MingUniVisionForConditionalGeneration:
+    """The wrapper a checkpoint directory's `config.json` describes, with uninitialised bf16 storage on `device` (`"meta"`:
+    no storage at all — the full 16B-A3B parameter tree can be inspected anywhere)."""
     with open(os.path.join(model_dir, "config.json")) as f:
         cfg = json.load(f)
     tok_cfg = cfg.get("mingtok_config")
@@ -88,11 +73,39 @@ def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
         warnings.warn("config rope_scaling '3D' -> None: the generation path uses 2-D position ids and the 1-D legacy "
                       "rotary embedding (pass 3-D position ids to forward_tokens for the M-RoPE variant)")
     llm_cfg["rope_scaling"] = None
+    if cfg.get("mlp_depth", 2) != 2:
+        raise NotImplementedError(f"mlp_depth {cfg['mlp_depth']}: linear_proj is Linear-GELU-Linear on this path "
+                                  "(mingunivision/config.json:120)")
+    # the repository's own config.json carries no `vishead_diffloss_config`: the defaults of setup_vishead_diffloss
+    # (width 3072, depth 12, 16 steps, flow_matching_swiglu-4; modeling_bailing_moe.py:1559-1567) are the released head
+    vishead_cfg = dict(cfg.get("vishead_diffloss_config") or {})
     if not (ep_size >= 1 and 0 <= ep_rank < ep_size):
         raise ValueError(f"ep_rank {ep_rank} / ep_size {ep_size}")
     model = MingUniVisionForConditionalGeneration.on_device(BailingMoeConfig(**llm_cfg), MingTokConfig(**tok_cfg),
-                                                            cfg["vishead_diffloss_config"], device, ep_rank=ep_rank,
-                                                            ep_size=ep_size)
+                                                            vishead_cfg, device, ep_rank=ep_rank, ep_size=ep_size)
+    return model
+
+
+_LOAD_CHUNK_BYTES = 2 << 30  # staging memory of load_checkpoint: tensors are copied into the model in chunks of this size
+
+
+def load_checkpoint(model_dir: str, device="cuda", ep_rank: int = 0,
+                    ep_size: int = 1) -> MingUniVisionForConditionalGeneration:
+    """Builds the wrapper from an HF-layout checkpoint directory: `config.json` with `llm_config`,
+    `vishead_diffloss_config` (modeling_bailingmm.py:93-129) and the MingTok config either inline (`mingtok_config`) or
+    in `models/MingTok-Vision/config.json` (the reference's hard-wired relative path, :102); weights from every
+    `*.safetensors` shard (reference key schema, SURVEY.md §3.5).
+
+    Direct safetensors -> kernel layout (SURVEY.md §8f.3): the module tree is built on the meta device with bf16 storage
+    (no HF `from_pretrained`, no fp32 copy, no weight init), the tensors are read straight from the
+    memory-mapped shards (`safe_open`, 2 GiB of staging at a time) and copied into place — the routed experts directly into the two contiguous slabs
+    per layer that the expert kernels stream, so they are never re-packed.  With `ep_size` > 1 (expert parallelism) only
+    this rank's 64 / ep_size routed experts are allocated AND read: the other ranks' expert tensors are skipped without
+    touching their bytes (follow with `model.model.model.set_expert_parallel(...)`)."""
+    from safetensors import safe_open
+
+    model_dir = resolve_checkpoint_dir(model_dir)
+    model = build_from_config(model_dir, device, ep_rank, ep_size)
     state = model.state_dict()
     expected = {k for k, v in state.items() if not v.is_meta}
     elsewhere = {k for k, v in state.items() if v.is_meta}  # routed experts owned by other ranks

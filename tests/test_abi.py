@@ -240,3 +240,51 @@ def test_load_checkpoint_expert_parallel_shard(tmp_path, monkeypatch):
     assert seen == {k for k in top if ".mlp.experts." in k}  # the ranks together hold every routed expert exactly once
     with pytest.raises(ValueError):
         MI.load_checkpoint(str(tmp_path), device="cpu", ep_rank=2, ep_size=2)
+
+
+def test_full_size_tree_from_the_reference_config(tmp_path):
+    """`build_from_config` on the reference's REAL `mingunivision/config.json` + `mingtok/config/config_mingtok.json`
+    (data files of the checkout, when present; otherwise this package's own full-size configs), on the META device: the
+    complete 16B-A3B parameter tree without a byte of storage.  Parameter counts are SURVEY.md §8d's constants; with
+    expert parallelism a rank's tree has storage for its 64 / 8 routed experts only."""
+    import json
+    import shutil
+
+    from ming_univision_b200.mingunivisioninfer import build_from_config
+    from oracle import ref_shims
+
+    ref_cfg = os.path.join(ref_shims.REFERENCE_ROOT, "mingunivision", "config.json")
+    ref_tok = os.path.join(ref_shims.REFERENCE_ROOT, "mingtok", "config", "config_mingtok.json")
+    (tmp_path / "models" / "MingTok-Vision").mkdir(parents=True)
+    if os.path.isfile(ref_cfg) and os.path.isfile(ref_tok):
+        shutil.copy(ref_cfg, tmp_path / "config.json")           # (it carries no vishead_diffloss_config: defaults apply)
+        shutil.copy(ref_tok, tmp_path / "models" / "MingTok-Vision" / "config.json")
+    else:
+        with open(tmp_path / "config.json", "w") as f:
+            json.dump({"llm_config": synthetic.LLM_CONFIG, "vishead_diffloss_config": synthetic.VISHEAD_CONFIG}, f)
+        with open(tmp_path / "models" / "MingTok-Vision" / "config.json", "w") as f:
+            json.dump(synthetic.MINGTOK_CONFIG, f)
+    with pytest.warns(UserWarning) if os.path.isfile(ref_cfg) else _nullcontext():
+        m = build_from_config(str(tmp_path), device="meta")
+    n = lambda mod: sum(p.numel() for p in mod.parameters())  # noqa: E731
+    assert n(m.model.model) + n(m.model.lm_head) == 16_809_314_304        # 16.81 B (2.50 B active per token)
+    assert n(m.model.diffloss) == 1_284_876_320 and n(m.model.vis_head) == 6_300_672
+    assert n(m.vision) == 697_719_584 and n(m.linear_proj) == 6_295_552
+    assert all(p.is_meta and p.dtype == torch.bfloat16 for p in m.parameters())
+    cfg = m.model.config
+    assert (cfg.num_experts, cfg.num_experts_per_tok, cfg.num_hidden_layers, cfg.vocab_size) == (64, 6, 28, 126464)
+    rs = cfg.rope_scaling  # the checkpoint's "3D" entry is mapped to the 1-D legacy rotary (transformers 5 spells None "default")
+    assert rs is None or rs.get("rope_type", rs.get("type")) == "default"
+    assert cfg.image_patch_token == 126346 and cfg.image_start_token == 126347
+    m8 = build_from_config(str(tmp_path), device="meta", ep_rank=3, ep_size=8)
+    keys = [k for k in m8.state_dict() if ".mlp.experts." in k]
+    assert len(keys) == 28 * 64 * 3                                       # the key schema is unchanged under sharding
+    assert m8.model.model.layers[0].mlp.experts[24].gate_proj.weight.shape == (1408, 2048)
+
+
+class _nullcontext:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
