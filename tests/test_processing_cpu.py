@@ -263,3 +263,19 @@ def test_facade_loads_the_in_package_processor(tmp_path, tok):
     assert isinstance(p2, P.BailingMMProcessor)
     with pytest.raises(RuntimeError):
         MingUniVisionInfer._load_processor("/nonexistent-a", "/nonexistent-b")
+
+
+@needs_ref
+def test_from_pretrained_on_the_reference_data_files():
+    """The processor built from the reference directory's DATA files (tokenizer.json, tokenizer_config.json,
+    preprocessor_config.json): vocabulary, terminator, the video image processor's pixel budget and patch geometry, and
+    the two image transforms' configuration (processing_bailingmm.py:175-176)."""
+    p = P.BailingMMProcessor.from_pretrained(REF_DIR)
+    assert len(p.tokenizer) == 126368 and p.gen_terminator == [126081]
+    ip = p.image_processor
+    assert (ip.min_pixels, ip.max_pixels, ip.patch_size, ip.temporal_patch_size, ip.merge_size) == (78400, 802816, 14, 2, 2)
+    assert (p.vis_processor.image_size, p.gen_processor.image_size) == (1024, 512)
+    assert p.vis_processor.mean == (0.5, 0.5, 0.5) and p.gen_processor.std == (0.5, 0.5, 0.5)
+    # the ids the model's config hard-wires (mingunivision/config.json: image_patch_token / image_start_token) are the
+    # tokenizer's ids of the markup tokens
+    assert p.tokenizer.convert_tokens_to_ids(["<imagePatch>", "<image>", "</image>"]) == [126346, 126347, 126348]
