@@ -41,6 +41,8 @@ N > 1: every rank runs ITS OWN rounds (its own image / prompt) and the routed ex
 (expert parallelism, 64 / N experts per GPU): per MoE layer the rows are dispatched to the expert owners and the partial
 sums combined back through NVLink peer memory inside the kernels (csrc/ep.cu; no NCCL call, the whole token step stays
 one CUDA graph).  Per-GPU work is fixed -> "scaling": "weak"; value = all ranks' tokens / max-over-ranks time.
+`ep_check`: every rank also generates ONE identical request; the image digests of all ranks must agree (the exchange is
+deterministic and reduces in rank order) — the consistency check a multi-GPU box can run.
 """
 from __future__ import annotations
 
@@ -507,6 +509,30 @@ def run_ours(args, world, rank, local):
                   "note": "one edit round per step and GPU (3 rows per pass over the weights instead of 6)"}
         step_resident(0)
 
+    # ---- N > 1: consistency check of the peer-memory exchange on the hardware that has the peers (tests/test_ep_gpu.py
+    # needs >= 2 GPUs too and is skipped on a 1-GPU box).  Every rank generates the SAME request (same prompt, image and RF
+    # noise): its rows travel to the same expert owners and the partial sums are added in rank order, so every rank must
+    # end with the same image, bit for bit.
+    ep_check = None
+    if world > 1:
+        import torch.distributed as dist
+
+        probe = round_inputs(llm_cfg, 424242)
+        gen = torch.Generator().manual_seed(7)
+        probe_noises = [torch.randn((1, 32), generator=gen) for _ in range(N_GEN + 1)]
+        probe_px = ops.image_preprocess(probe[3].unsqueeze(0).to(dev), SIZE, SIZE, out_dtype=torch.bfloat16)
+        probe_img, _ = model.generate_image_from_prompt(probe[0].to(dev), pixel_values=probe_px,
+                                                        uncond_attention_mask=probe[1].to(dev),
+                                                        text_uncond_attention_mask=probe[2].to(dev), noises=probe_noises)
+        u8 = ops.image_postprocess(probe_img).to(torch.int64).flatten()
+        weights = torch.arange(u8.numel(), device=dev, dtype=torch.int64) % 8191 + 1
+        digest = torch.stack((u8.sum(), (u8 * weights).sum()))
+        digests = [torch.zeros_like(digest) for _ in range(world)]
+        dist.all_gather(digests, digest)
+        ep_check = {"what": "the same request generated on every rank (expert-parallel dispatch / combine): image digests",
+                    "identical_on_all_ranks": all(bool(torch.equal(d, digests[0])) for d in digests), "ranks": world}
+        step_resident(0)
+
     # ---- roofline of the dominant kernel, the persistent RF sampler (one launch per generated token: 16 Euler steps x 12
     # residual blocks): CUDA events around its launches on the eager path (launching stream), algorithmic bytes = the
     # bf16 weights it must stream = steps x depth x 3 H W x 2
@@ -609,7 +635,7 @@ def run_ours(args, world, rank, local):
                     "h2d_bytes_per_step": NI * (SIZE * SIZE * 3 + PROMPT_LEN * 8),
                     "d2h_bytes_per_step": NI * SIZE * SIZE * 3},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu, "parity": parity}
+            "cpu_baseline": cpu, "parity": parity, "ep_check": ep_check}
     print(json.dumps(line), flush=True)
 
 
