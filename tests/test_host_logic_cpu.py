@@ -251,7 +251,7 @@ def test_flat_module_names_of_the_reference_resolve_to_the_package():
     assert r.returncode == 0 and "flat ok" in r.stdout, r.stdout + r.stderr
 
 
-def test_facade_round_trip_with_the_processor(stubbed, monkeypatch):
+def test_facade_round_trip_with_the_processor(stubbed, monkeypatch, tmp_path):
     """MingUniVisionInfer.generate (mingunivisioninfer.py:82-117) end to end on the host: this package's processor (chat
     template -> image fetch -> transform -> placeholder expansion -> ids + CFG masks) feeding the wrapper's `generate`
     with the CUDA-backed pieces stubbed.  A text-to-image round, then an in-context EDIT round with an input image: the
@@ -296,7 +296,8 @@ def test_facade_round_trip_with_the_processor(stubbed, monkeypatch):
     # ---- round 1: text -> image
     script["tokens"] = [img_tok] + tok.encode("done", add_special_tokens=False) + [eos]
     msg1 = [{"role": "HUMAN", "content": [{"type": "text", "text": "Generate a corgi."}]}]
-    answer = agent.generate(msg1, max_new_tokens=32)
+    answer = agent.generate(msg1, max_new_tokens=32, output_image_prefix=str(tmp_path / "gen"))
+    assert (tmp_path / "gen.png").is_file()                       # the generated image is saved as `{prefix}.png` (:1788-1796)
     assert answer == "done"                                        # special tokens (<image>, <|endoftext|>) are skipped
     text1 = proc.apply_chat_template(msg1)
     enc1 = proc(text=[text1])
@@ -314,7 +315,7 @@ def test_facade_round_trip_with_the_processor(stubbed, monkeypatch):
     img = Image.fromarray(np.random.default_rng(0).integers(0, 256, (80, 120, 3), dtype=np.uint8))
     msg2 = [{"role": "HUMAN", "content": [{"type": "image", "image": img}, {"type": "text", "text": "add a hat"}]}]
     script["tokens"] = [img_tok, eos]
-    agent.generate(msg2, max_new_tokens=8, for_edit=True)
+    agent.generate(msg2, max_new_tokens=8, for_edit=True, output_image_prefix=str(tmp_path / "edit"))
     assert seen["pixels"] == ((1, 3, 64, 64), torch.bfloat16)      # the facade hands bf16 pixels to the model (:104-105)
     n_patch = (64 // m.vision.patch_size) ** 2
     side = 64 // m.vision.patch_size
